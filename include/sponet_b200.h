@@ -1,0 +1,222 @@
+/* sponet_b200 -- C ABI of the B200-native SPoNet ensemble path.
+ *
+ * The reference (lueckem/SPoNet v3.0.0) has no FFI: its boundary is a Python call surface over six
+ * private numba loops.  Every entry point below replaces one of those loops (or the host arithmetic
+ * wrapped around them) for a whole batch of realizations, and cites the reference site it stands
+ * in for.  INTEGRATION.md shows the ctypes stub a SPoNet maintainer would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every data pointer may be a HOST pointer or a DEVICE pointer
+ *     (detected with cudaPointerGetAttributes); host buffers are staged through device memory
+ *     inside the call.  The caller owns all buffers; the library owns graph handles and scratch.
+ *   - All calls run on the CURRENT CUDA device, on `cuda_stream` (a cudaStream_t, NULL = default
+ *     stream).  A call that received only device pointers returns without synchronising; a call
+ *     with any host output synchronises the stream before returning.
+ *   - Return value: SPONET_OK or an error code; sponet_last_error() gives the message (thread
+ *     local).  There is NO CPU fallback: without a CUDA device every run call fails.
+ *   - Agent states are uint8 for num_opinions <= 256 and uint16 above
+ *     (sponet/cnvm/model.py:98, sponet/cntm/model.py:63).
+ */
+#ifndef SPONET_B200_H
+#define SPONET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPONET_ABI_VERSION 1
+
+enum {
+    SPONET_OK = 0,
+    SPONET_ERR_INVALID = 1,          /* bad argument (-> ValueError on the Python side)            */
+    SPONET_ERR_CUDA = 2,             /* CUDA runtime error or no device                            */
+    SPONET_ERR_STREAM_EXHAUSTED = 3, /* replay: injected uint64 stream too short                   */
+    SPONET_ERR_UNSUPPORTED = 4,      /* valid request this build cannot serve                      */
+    SPONET_ERR_ZERO_RATE = 5         /* all rates zero: 1/0 in next_event_rate (cnvm/model.py:257)  */
+};
+
+const char* sponet_last_error(void);
+int sponet_abi_version(void);
+/* Number of visible CUDA devices (0 and SPONET_ERR_CUDA when there is none). */
+int sponet_device_count(int* count);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side setup arithmetic (sequential float64, bit-compatible with the numba code)
+ * ------------------------------------------------------------------------------------------- */
+
+/* sponet/sampling.py:54-96 build_alias_table (stack-based Vose; output depends on pop order). */
+int sponet_build_alias_table(const double* weights, int64_t n, double* table_prob, int32_t* table_alias);
+
+/* sponet/cnvm/model.py:257-258 (network) / :383-384 (complete, degree_alpha = NULL and
+ * max_degree_alpha used).  Sequential sum like numba's np.sum. */
+int sponet_cnvm_event_rates(const double* degree_alpha, int64_t n, double max_degree_alpha,
+                            double r_imit, double r_noise, double* next_event_rate,
+                            double* noise_probability);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph handle: CSR adjacency resident in HBM (replaces numba.typed.List(params.network),
+ * sponet/cnvm/model.py:26-28, sponet/cntm/model.py:29).  Row order is preserved: neighbour slot k
+ * is what `int(u * deg)` indexes (cnvm/model.py:286).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sponet_graph sponet_graph;
+
+int sponet_graph_create(int64_t num_agents, const int32_t* row_ptr /* [n+1] */,
+                        const int32_t* col /* [row_ptr[n]] */, sponet_graph** out);
+int sponet_graph_destroy(sponet_graph* g);
+int sponet_graph_info(const sponet_graph* g, int64_t* num_agents, int64_t* nnz, int32_t* min_degree,
+                      int32_t* max_degree, int* device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model parameters as the reference loops receive them
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t num_opinions;
+    double r_imit, r_noise;     /* sponet/cnvm/parameters.py:293-338 convert_rate_to_cnvm          */
+    const double* prob_imit;    /* [M*M] C order, HOST pointer                                      */
+    const double* prob_noise;   /* [M*M] C order, HOST pointer                                      */
+    const double* degree_alpha; /* d_i^(1-alpha), [n], HOST pointer (cnvm/model.py:30-42);          */
+                                /* complete graph: only degree_alpha[0] is read (:382)              */
+} sponet_cnvm_params;
+
+typedef struct {
+    double next_event_rate; /* 1 / (N (r + r_tilde))   sponet/cntm/model.py:32-34                   */
+    double noise_prob;      /* r_tilde / (r + r_tilde) sponet/cntm/model.py:31                      */
+    double threshold_01, threshold_10;
+} sponet_cntm_params;
+
+/* Work list of one replay worker: states [state_begin, state_end) x runs [run_begin, run_end),
+ * iterated state-major exactly like _Worker.__call__ (sponet/multiprocessing.py:171-182), consuming
+ * ONE sequential uint64 stream.  Outputs are indexed by the global (state, run). */
+typedef struct {
+    int64_t state_begin, state_end, run_begin, run_end;
+    int64_t stream_offset, stream_len; /* slice of `streams` owned by this worker */
+} sponet_replay_work;
+
+/* ---------------------------------------------------------------------------------------------
+ * REPLAY mode: bit-exact re-execution of the reference loops on an injected raw-uint64 stream
+ * (BitGenerator.random_raw).  Uniforms are (u >> 11) * 2^-53, exponentials the 256-layer ziggurat
+ * of numba/np/random/distributions.py:105-119.  One GPU warp per worker; lane 0 walks the chain.
+ *
+ *   x_init      [S, n]        uint8 (M <= 256) or uint16
+ *   t_eval      [T]           float64, already validated (sponet/utils.py:173-190)
+ *   out_t       [S, R, T]     event times as the reference returns them (t_traj)
+ *   out_x       [S, R, T, n]  snapshots (x_traj), may be NULL
+ *   stream_used [W]           uint64 values consumed per worker
+ *   events      [W]           loop iterations per worker (may be NULL)
+ * ------------------------------------------------------------------------------------------- */
+
+/* sponet/cnvm/model.py:239-308 (_simulate_teval, g != NULL) and :365-433 (_simulate_complete_teval,
+ * g == NULL). */
+int sponet_cnvm_replay(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* params,
+                       const void* x_init, int64_t S, int64_t R, const double* t_eval, int64_t T,
+                       const uint64_t* streams, const sponet_replay_work* work, int64_t W,
+                       double* out_t, void* out_x, int64_t* stream_used, int64_t* events,
+                       void* cuda_stream);
+
+/* sponet/cntm/model.py:163-227 (_simulate_teval). */
+int sponet_cntm_replay(const sponet_graph* g, const sponet_cntm_params* params, const uint8_t* x_init,
+                       int64_t S, int64_t R, const double* t_eval, int64_t T, const uint64_t* streams,
+                       const sponet_replay_work* work, int64_t W, double* out_t, uint8_t* out_x,
+                       int64_t* stream_used, int64_t* events, void* cuda_stream);
+
+/* Store-every-change variants (t_eval = None): sponet/cnvm/model.py:184-236, :311-362 and
+ * sponet/cntm/model.py:111-160, for ONE realization, returned as an event log of accepted changes
+ * (the reference copies all n agents per change, model.py:233).  log_* have capacity `cap`;
+ * *num_changes receives the number of entries, *events the loop iterations. */
+int sponet_cnvm_replay_all(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* params,
+                           const void* x_init, double t_max, const uint64_t* stream,
+                           int64_t stream_len, int64_t cap, double* log_t, int32_t* log_agent,
+                           int32_t* log_opinion, int64_t* num_changes, int64_t* stream_used,
+                           int64_t* events, void* cuda_stream);
+int sponet_cntm_replay_all(const sponet_graph* g, const sponet_cntm_params* params,
+                           const uint8_t* x_init, double t_max, const uint64_t* stream,
+                           int64_t stream_len, int64_t cap, double* log_t, int32_t* log_agent,
+                           int32_t* log_opinion, int64_t* num_changes, int64_t* stream_used,
+                           int64_t* events, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NATIVE mode: the production ensemble path.  Chains (state j, run i) are independent; chain id
+ * j * R_total + i keys a Philox4x32-10 stream, so results do not depend on how runs are sharded
+ * over calls or GPUs.  This call executes runs [run_begin, run_end) of every one of the S initial
+ * states.  One warp per chain, 32 candidate events per warp step, agent states bit-packed in shared
+ * memory (global-memory fallback when a chain does not fit), collective variables reduced in-kernel.
+ * DESIGN.md section 3 gives the sampling scheme; oracle/oracle_native.inc states it sequentially.
+ * ------------------------------------------------------------------------------------------- */
+
+/* In-kernel collective variable = OpinionShares (sponet/collective_variables.py:63-124 without
+ * weights): out[d] = count[idx[d]] / divisor.  divisor 1.0 = counts, num_agents = normalize=True. */
+typedef struct {
+    int32_t dimension;  /* D = len(idx_to_return)                       */
+    const int32_t* idx; /* [D] HOST pointer, opinion indices to return  */
+    double divisor;
+} sponet_shares_cv;
+
+typedef struct {
+    uint64_t seed;
+    int64_t num_runs_total; /* R_total: stride of the chain id                                      */
+    int64_t run_begin, run_end;
+    /* optional [S, run_end-run_begin, T-1] int64: candidate-event counts per output interval,
+     * overriding the in-kernel Poisson(dt / next_event_rate) sampler (tests, host-side schedules) */
+    const int64_t* event_counts;
+    int32_t force_global_state; /* debug/tests: keep chain state in global memory                   */
+} sponet_native_opts;
+
+/* counters: [0] candidate events executed, [1] accepted changes, [2] warp steps, [3] extra commit
+ * rounds caused by intra-step hazards.  May be NULL. */
+#define SPONET_NUM_COUNTERS 4
+
+/* CNVM on a network (g != NULL; replaces cnvm/model.py:239-308 + utils.py:96-135 +
+ * collective_variables.py:400-405 for a batch) or on the complete graph (g == NULL, :365-433).
+ *   out_x   [S, nrun, T, n] uint8 snapshots, or NULL
+ *   out_cv  [S, nrun, T, D] float64, or NULL          (needs cv)
+ *   out_sum, out_sumsq [S, T, D] int64 sums over runs of count and count^2 (raw counts of the
+ *           selected opinions; ACCUMULATED into, caller zeroes) -- the per-GPU partials of
+ *           sample_moments (sponet/sample_moments.py:106-108), or NULL                           */
+int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* params,
+                    const uint8_t* x_init, int64_t S, const double* t_eval, int64_t T,
+                    const sponet_native_opts* opts, const sponet_shares_cv* cv, uint8_t* out_x,
+                    double* out_cv, int64_t* out_sum, int64_t* out_sumsq, uint64_t* counters,
+                    void* cuda_stream);
+
+/* Complete graph, count-only fast path: the chain state is the M opinion counts, kept in registers
+ * (valid because agents are exchangeable on the complete graph and OpinionShares only reads counts).
+ *   counts_init [S, M] int64 initial opinion counts. */
+int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_cnvm_params* params,
+                                    const int64_t* counts_init, int64_t S, const double* t_eval,
+                                    int64_t T, const sponet_native_opts* opts,
+                                    const sponet_shares_cv* cv, double* out_cv, int64_t* out_sum,
+                                    int64_t* out_sumsq, uint64_t* counters, void* cuda_stream);
+
+/* CNTM (replaces cntm/model.py:163-227 for a batch); num_opinions is 2. */
+int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* params, const uint8_t* x_init,
+                    int64_t S, const double* t_eval, int64_t T, const sponet_native_opts* opts,
+                    const sponet_shares_cv* cv, uint8_t* out_x, double* out_cv, int64_t* out_sum,
+                    int64_t* out_sumsq, uint64_t* counters, void* cuda_stream);
+
+/* The interval schedule native mode draws: counts[c, k-1] ~ Poisson((t_eval[k]-t_eval[k-1]) /
+ * next_event_rate) for chain ids chain_begin .. chain_begin+num_chains-1 (+1 on the first interval,
+ * see DESIGN.md).  Exposed so tests can check it against the oracle. */
+int sponet_native_event_counts(uint64_t seed, int64_t chain_begin, int64_t num_chains,
+                               const double* t_eval, int64_t T, double next_event_rate,
+                               int64_t* counts, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Collective variables on stored states (the `cv(x)` call on user arrays)
+ * ------------------------------------------------------------------------------------------- */
+
+/* sponet/collective_variables.py:400-405 _opinion_shares_numba: out[s, m] = sum_j w[j] [x[s,j]==m]
+ * (weights NULL = 1).  x is uint8 [S, n]; out float64 [S, M].  Integer-valued weights give exact
+ * results; general weights are summed in a fixed tree order (tolerance in tests/test_cv.py). */
+int sponet_opinion_shares(const uint8_t* x, int64_t S, int64_t num_agents, int32_t num_opinions,
+                          const double* weights, double* out, void* cuda_stream);
+
+/* sum and sum of squares over the run axis: x [R, L] float64 -> sum[L], sumsq[L]
+ * (sponet/sample_moments.py:107-108), fixed-order reduction. */
+int sponet_moments(const double* x, int64_t R, int64_t L, double* sum, double* sumsq, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPONET_B200_H */

@@ -1,0 +1,29 @@
+"""sponet_b200 -- B200-native ensemble path for SPoNet's continuous-time spreading models.
+
+Drop-in names for the hot path of lueckem/SPoNet (``CNVM``, ``CNTM``, their parameter classes, the
+OpinionShares family of collective variables, ``sample_many_runs``, ``sample_moments``,
+``estimate_steady_state``).  The event loops run as sm_100a CUDA kernels inside
+``libsponet_b200.so`` (C ABI: include/sponet_b200.h); there is no CPU fallback.
+"""
+from .cntm import CNTM, CNTMParameters
+from .cnvm import CNVM, CNVMParameters
+from .collective_variables import (
+    CollectiveVariable,
+    CompositeCollectiveVariable,
+    DegreeWeightedOpinionShares,
+    OpinionShares,
+    OpinionSharesByDegree,
+)
+from .engine import set_default_mode
+from .multiprocessing import sample_many_runs
+from .parameters import Parameters, load_params, save_params
+from .sample_moments import sample_moments
+from .steady_state import estimate_steady_state
+
+__all__ = [
+    "CNTM", "CNTMParameters", "CNVM", "CNVMParameters", "CollectiveVariable",
+    "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "OpinionShares",
+    "OpinionSharesByDegree", "Parameters", "load_params", "save_params", "sample_many_runs",
+    "sample_moments", "estimate_steady_state", "set_default_mode",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,170 @@
+"""Collective variables (reference: sponet/collective_variables.py).
+
+The OpinionShares family is a (weighted) histogram of opinions per snapshot.  Calling a CV on an
+array of states runs the histogram kernel of libsponet_b200 (``sponet_opinion_shares``); inside
+``sample_many_runs`` the unweighted OpinionShares is not called at all -- the simulation kernel keeps
+the counts incrementally and emits them at the output times.
+
+Every class keeps the reference's constructor, ``dimension`` attribute and ``__call__`` contract:
+``(num_agents,) -> (dimension,)`` and ``(num_states, num_agents) -> (num_states, dimension)``.
+"""
+from __future__ import annotations
+
+from typing import Protocol
+
+import numpy as np
+from numpy.typing import ArrayLike, NDArray
+
+from . import _lib
+
+
+class CollectiveVariable(Protocol):
+    dimension: int
+
+    def __call__(self, x: NDArray) -> NDArray: ...
+
+
+def _weighted_histogram(x, num_opinions: int, weights: NDArray | None):
+    """``out[s, m] = sum_j weights[j] * [x[s, j] == m]`` on the GPU.
+
+    ``x`` is a host array (S, N) or a CUDA ``torch.Tensor``; the result lives where ``x`` lives.
+    Reference: ``_opinion_shares_numba`` (sponet/collective_variables.py:400-405).
+    """
+    if num_opinions > 256:
+        raise NotImplementedError("histogram kernel supports num_opinions <= 256")
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    if isinstance(x, np.ndarray):
+        if x.size and (x.min() < 0 or x.max() >= num_opinions):
+            # np.bincount would grow the output / raise; the reference then fails on assignment
+            raise ValueError("state contains opinions outside [0, num_opinions)")
+        xs = np.ascontiguousarray(x, dtype=np.uint8)
+        out = np.empty((xs.shape[0], num_opinions), dtype=np.float64)
+        _lib.check(
+            _lib.lib().sponet_opinion_shares(
+                _lib.ptr(xs), xs.shape[0], xs.shape[1], num_opinions, _lib.ptr(w), _lib.ptr(out), None
+            )
+        )
+        return out
+    import torch  # device tensor path
+
+    xs = x.contiguous()
+    if xs.dtype != torch.uint8:
+        xs = xs.to(torch.uint8)
+    out = torch.empty((xs.shape[0], num_opinions), dtype=torch.float64, device=xs.device)
+    with torch.cuda.device(xs.device):
+        _lib.check(
+            _lib.lib().sponet_opinion_shares(
+                _lib.ptr(xs), xs.shape[0], xs.shape[1], num_opinions, _lib.ptr(w), _lib.ptr(out),
+                _lib.current_stream_ptr(),
+            )
+        )
+    return out
+
+
+def _as_2d(x):
+    """(states_2d, was_1d) -- the reference's ``handle_1d`` decorator (collective_variables.py:40-60)."""
+    if isinstance(x, np.ndarray) or not hasattr(x, "data_ptr"):
+        x = np.asarray(x)
+    if x.ndim == 1:
+        return x[None, :], True
+    return x, False
+
+
+def _select(idx_to_return, num_opinions):
+    if idx_to_return is None:
+        return np.arange(num_opinions)
+    return np.atleast_1d(np.array(idx_to_return))
+
+
+class OpinionShares:
+    """Counts (or shares) of each opinion, optionally weighted per agent.
+
+    Reference: sponet/collective_variables.py:63-124.  ``normalize`` divides by ``num_agents`` when
+    unweighted and by ``sum(|weights|)`` otherwise; ``idx_to_return`` selects opinions.
+    """
+
+    def __init__(
+        self,
+        num_opinions: int,
+        normalize: bool = False,
+        weights: ArrayLike | None = None,
+        idx_to_return: ArrayLike | None = None,
+    ):
+        self.num_opinions = num_opinions
+        self.weights = None if weights is None else np.array(weights)
+        self.normalize = normalize
+        self.normalization = None if weights is None else np.sum(np.abs(weights))
+        self.idx_to_return = _select(idx_to_return, num_opinions)
+        self.dimension = len(self.idx_to_return)
+
+    def __call__(self, x):
+        xs, was_1d = _as_2d(x)
+        agg = _weighted_histogram(xs, self.num_opinions, self.weights)[:, self.idx_to_return]
+        if self.normalize:
+            agg = agg / (xs.shape[1] if self.normalization is None else self.normalization)
+        return agg[0] if was_1d else agg
+
+    # -- what the simulation kernels need to compute this CV on the fly -----------------------
+    def _kernel_spec(self, num_agents: int):
+        """(idx int32[D], divisor) when the CV is an unweighted histogram, else None."""
+        if self.weights is not None:
+            return None
+        return self.idx_to_return.astype(np.int32), float(num_agents) if self.normalize else 1.0
+
+
+class DegreeWeightedOpinionShares(OpinionShares):
+    """OpinionShares with each agent weighted by its degree (collective_variables.py:127-149)."""
+
+    def __init__(self, num_opinions: int, network, normalize: bool = False, idx_to_return: ArrayLike | None = None):
+        weights = np.array([d for _, d in network.degree()])
+        super().__init__(num_opinions, normalize, weights, idx_to_return)
+
+
+class OpinionSharesByDegree:
+    """Opinion counts within each degree class, smallest degree first (collective_variables.py:152-220)."""
+
+    def __init__(self, num_opinions: int, network, normalize: bool = False, idx_to_return: ArrayLike | None = None):
+        self.degrees_of_nodes = np.array([d for _, d in network.degree()])
+        self.degrees = np.sort(np.unique(self.degrees_of_nodes))
+        self.num_opinions = num_opinions
+        self.normalize = normalize
+        self.idx_to_return = _select(idx_to_return, num_opinions)
+        self.dimension = len(self.idx_to_return) * self.degrees.shape[0]
+
+    def __call__(self, x):
+        xs, was_1d = _as_2d(x)
+        k = len(self.idx_to_return)
+        blocks = []
+        for deg in self.degrees:
+            mask = (self.degrees_of_nodes == deg).astype(np.float64)
+            agg = _weighted_histogram(xs, self.num_opinions, mask)[:, self.idx_to_return]
+            if self.normalize:
+                agg = agg / np.sum(mask)
+            blocks.append(agg)
+        if isinstance(blocks[0], np.ndarray):
+            cv = np.concatenate(blocks, axis=1)
+        else:
+            import torch
+
+            cv = torch.cat(blocks, dim=1)
+        assert cv.shape[1] == k * len(self.degrees)
+        return cv[0] if was_1d else cv
+
+
+class CompositeCollectiveVariable:
+    """Concatenation of several CVs (collective_variables.py:223-256)."""
+
+    def __init__(self, collective_variables: list[CollectiveVariable]):
+        self.collective_variables = collective_variables
+        self.dimension = sum(cv.dimension for cv in collective_variables)
+
+    def __call__(self, x):
+        xs, was_1d = _as_2d(x)
+        parts = [cv(xs) for cv in self.collective_variables]
+        if all(isinstance(p, np.ndarray) for p in parts):
+            out = np.concatenate(parts, axis=1)
+        else:
+            import torch
+
+            out = torch.cat([p if hasattr(p, "data_ptr") else torch.as_tensor(p, device=xs.device) for p in parts], dim=1)
+        return out[0] if was_1d else out

@@ -1,0 +1,177 @@
+// Shared host/device helpers of libsponet_b200: error reporting, host<->device staging of the
+// caller's buffers, the graph handle, Philox4x32-10 and the draw->decision primitives of native mode.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sponet_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+std::string& sponet_err_slot();
+int sponet_fail(int code, const char* fmt, ...);
+
+#define SP_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t _e = (call);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return sponet_fail(SPONET_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                 \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+    } while (0)
+
+#define SP_REQUIRE(cond, ...)                                          \
+    do {                                                               \
+        if (!(cond)) return sponet_fail(SPONET_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define SP_TRY(expr)                  \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != SPONET_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// graph handle
+// ---------------------------------------------------------------------------------------------
+struct sponet_graph {
+    int device;
+    int64_t n, nnz;
+    int32_t min_degree, max_degree;
+    int32_t* d_row_ptr;  // [n+1]
+    int2* d_row;         // [n] (begin, degree): one 8-byte gather per agent instead of two
+    int32_t* d_col;      // [nnz]
+};
+
+// ---------------------------------------------------------------------------------------------
+// staging: a caller pointer may live on the host or on the device
+// ---------------------------------------------------------------------------------------------
+inline bool sp_is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// RAII pool of temporary device allocations tied to one call.
+struct SpScratch {
+    cudaStream_t stream;
+    std::vector<void*> ptrs;
+    struct Copyback {
+        void* host;
+        const void* dev;
+        size_t bytes;
+    };
+    std::vector<Copyback> copybacks;
+    explicit SpScratch(cudaStream_t s) : stream(s) {}
+    ~SpScratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
+    }
+    cudaError_t alloc(void** out, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(out, bytes, stream);
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+    // Input: returns a device pointer holding `bytes` of `p` (copying if p is a host pointer).
+    template <typename T>
+    cudaError_t in(const T* p, size_t count, const T** out) {
+        if (!p) { *out = nullptr; return cudaSuccess; }
+        if (sp_is_device_ptr(p)) { *out = p; return cudaSuccess; }
+        void* d;
+        cudaError_t e = alloc(&d, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        *out = (const T*)d;
+        return cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, stream);
+    }
+    // Output: returns a device pointer; host targets get a device temp that finish() copies back.
+    // `preload` copies the host contents in first (accumulate-into outputs).
+    template <typename T>
+    cudaError_t out(T* p, size_t count, T** dev, bool preload = false) {
+        if (!p) { *dev = nullptr; return cudaSuccess; }
+        if (sp_is_device_ptr(p)) { *dev = p; return cudaSuccess; }
+        void* d;
+        cudaError_t e = alloc(&d, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        *dev = (T*)d;
+        copybacks.push_back({(void*)p, d, count * sizeof(T)});
+        if (preload) return cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, stream);
+        return cudaSuccess;
+    }
+    // Copies host outputs back; synchronises only if there was anything to copy (or `force`).
+    cudaError_t finish(bool force_sync = false) {
+        for (auto& c : copybacks) {
+            cudaError_t e = cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return e;
+        }
+        bool need = force_sync || !copybacks.empty();
+        copybacks.clear();
+        if (need) return cudaStreamSynchronize(stream);
+        return cudaSuccess;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// native-mode primitives (device)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+__device__ __forceinline__ uint4 sp_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// counter = (e_lo, e_hi, chain_lo, chain_hi[24] | tag << 24), key = seed
+__device__ __forceinline__ uint4 sp_native_draw(uint64_t seed, uint64_t chain, uint32_t tag, uint64_t e) {
+    return sp_philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)chain,
+                            ((uint32_t)(chain >> 32) & 0x00FFFFFFu) | (tag << 24), (uint32_t)seed,
+                            (uint32_t)(seed >> 32));
+}
+
+// accept iff r < floor(p * 2^32); thr == 0xFFFFFFFF encodes p >= 1 (always).
+__device__ __forceinline__ bool sp_thr_accept(uint32_t r, uint32_t thr) {
+    return (r < thr) | (thr == 0xFFFFFFFFu);
+}
+
+__device__ __forceinline__ double sp_u53(uint32_t a, uint32_t b) {
+    return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+#endif  // __CUDACC__
+
+// p -> floor(p * 2^32) saturated to 0xFFFFFFFF
+inline uint32_t sp_prob_to_thr(double p) {
+    if (!(p > 0.0)) return 0u;
+    if (p >= 1.0) return 0xFFFFFFFFu;
+    double t = p * 4294967296.0;
+    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)t;
+}
+
+// launchers implemented in the kernel translation units --------------------------------------
+struct SpCvDev {
+    int32_t D;
+    const int32_t* d_idx;  // device [D]
+    double divisor;
+};

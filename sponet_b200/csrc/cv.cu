@@ -1,0 +1,114 @@
+// Collective variables on stored states and the moment reduction.
+//   sponet_opinion_shares  <- sponet/collective_variables.py:400-405 (_opinion_shares_numba:
+//                             np.bincount(x[i], weights, minlength=M) per snapshot)
+//   sponet_moments         <- sponet/sample_moments.py:107-108 (np.sum(x, 0), np.sum(x**2, 0))
+#include "common.cuh"
+
+namespace {
+
+constexpr int CV_THREADS = 256;
+
+// One CTA per snapshot.  Thread t sums agents t, t+256, ... into its private column of a
+// [MAXM][256] shared array, then the columns are folded with a fixed binary tree: deterministic,
+// and exact whenever the weights are integers (unweighted counts, degree weights, group masks).
+template <int MAXM>
+__global__ void __launch_bounds__(CV_THREADS) opinion_shares_kernel(const uint8_t* __restrict__ x,
+                                                                    int64_t n, int M,
+                                                                    const double* __restrict__ w,
+                                                                    double* __restrict__ out) {
+    __shared__ double acc[MAXM * CV_THREADS];
+    const int t = threadIdx.x;
+    const int64_t s = blockIdx.x;
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) acc[m * CV_THREADS + t] = 0.0;
+    const uint8_t* xs = x + s * n;
+    for (int64_t a = t; a < n; a += CV_THREADS) {
+        const int m = xs[a];
+        if (m < M) acc[m * CV_THREADS + t] += w ? w[a] : 1.0;
+    }
+    __syncthreads();
+    for (int stride = CV_THREADS / 2; stride > 0; stride >>= 1) {
+        if (t < stride) {
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m)
+                if (m < M) acc[m * CV_THREADS + t] += acc[m * CV_THREADS + t + stride];
+        }
+        __syncthreads();
+    }
+    if (t < M) out[s * M + t] = acc[t * CV_THREADS];
+}
+
+// Many opinions: shared-memory float64 atomics (order not fixed; exact for integer weights).
+__global__ void __launch_bounds__(CV_THREADS) opinion_shares_atomic_kernel(const uint8_t* __restrict__ x,
+                                                                           int64_t n, int M,
+                                                                           const double* __restrict__ w,
+                                                                           double* __restrict__ out) {
+    extern __shared__ double hist[];
+    const int t = threadIdx.x;
+    const int64_t s = blockIdx.x;
+    for (int m = t; m < M; m += CV_THREADS) hist[m] = 0.0;
+    __syncthreads();
+    const uint8_t* xs = x + s * n;
+    for (int64_t a = t; a < n; a += CV_THREADS) {
+        const int m = xs[a];
+        if (m < M) atomicAdd(&hist[m], w ? w[a] : 1.0);
+    }
+    __syncthreads();
+    for (int m = t; m < M; m += CV_THREADS) out[s * M + m] = hist[m];
+}
+
+// Thread per column, rows added in order -- the same order numpy uses for an axis-0 reduction.
+__global__ void moments_kernel(const double* __restrict__ x, int64_t R, int64_t L,
+                               double* __restrict__ sum, double* __restrict__ sumsq) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    double s = 0.0, q = 0.0;
+    for (int64_t r = 0; r < R; ++r) {
+        const double v = x[r * L + l];
+        s = __dadd_rn(s, v);
+        q = __dadd_rn(q, __dmul_rn(v, v));
+    }
+    sum[l] = s;
+    sumsq[l] = q;
+}
+
+}  // namespace
+
+extern "C" int sponet_opinion_shares(const uint8_t* x, int64_t S, int64_t n, int32_t M,
+                                     const double* weights, double* out, void* cuda_stream) {
+    SP_REQUIRE(x && out && S >= 0 && n >= 1 && M >= 1 && M <= 256, "opinion_shares: bad arguments");
+    if (S == 0) return SPONET_OK;
+    SP_REQUIRE(S < ((int64_t)1 << 31), "opinion_shares: too many snapshots for one launch");
+    SpScratch sc((cudaStream_t)cuda_stream);
+    const uint8_t* d_x;
+    const double* d_w;
+    double* d_out;
+    SP_CUDA(sc.in(x, (size_t)S * n, &d_x));
+    SP_CUDA(sc.in(weights, (size_t)n, &d_w));
+    SP_CUDA(sc.out(out, (size_t)S * M, &d_out));
+    const unsigned grid = (unsigned)S;
+    if (M <= 2) opinion_shares_kernel<2><<<grid, CV_THREADS, 0, sc.stream>>>(d_x, n, M, d_w, d_out);
+    else if (M <= 4) opinion_shares_kernel<4><<<grid, CV_THREADS, 0, sc.stream>>>(d_x, n, M, d_w, d_out);
+    else if (M <= 8) opinion_shares_kernel<8><<<grid, CV_THREADS, 0, sc.stream>>>(d_x, n, M, d_w, d_out);
+    else if (M <= 16) opinion_shares_kernel<16><<<grid, CV_THREADS, 0, sc.stream>>>(d_x, n, M, d_w, d_out);
+    else opinion_shares_atomic_kernel<<<grid, CV_THREADS, M * sizeof(double), sc.stream>>>(d_x, n, M, d_w, d_out);
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(sc.finish());
+    return SPONET_OK;
+}
+
+extern "C" int sponet_moments(const double* x, int64_t R, int64_t L, double* sum, double* sumsq,
+                              void* cuda_stream) {
+    SP_REQUIRE(x && sum && sumsq && R >= 0 && L >= 1, "moments: bad arguments");
+    SpScratch sc((cudaStream_t)cuda_stream);
+    const double* d_x;
+    double *d_s, *d_q;
+    SP_CUDA(sc.in(x, (size_t)R * L, &d_x));
+    SP_CUDA(sc.out(sum, (size_t)L, &d_s));
+    SP_CUDA(sc.out(sumsq, (size_t)L, &d_q));
+    const int block = 128;
+    moments_kernel<<<(unsigned)((L + block - 1) / block), block, 0, sc.stream>>>(d_x, R, L, d_s, d_q);
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(sc.finish());
+    return SPONET_OK;
+}

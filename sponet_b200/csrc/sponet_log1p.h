@@ -68,7 +68,7 @@ SPL_HD double sponet_log1p(double x) {
     int32_t hx = spl_hi(x), ax = hx & 0x7fffffff, hu = 0, k = 1;
     if (hx < 0x3FDA827A) {
         if (ax >= 0x3ff00000) {  // x <= -1: -inf / nan (never reached from the ziggurat)
-            return (x == -1.0) ? -1.0 / 0.0 : (x - x) / 0.0;
+            return spl_sethi(0.0, (x == -1.0) ? (int32_t)0xfff00000 : (int32_t)0x7ff80000);
         }
         if (ax < 0x3e200000) {  // |x| < 2^-29
             if (ax < 0x3c900000) return x;

@@ -1,0 +1,341 @@
+"""Thin host layer between the reference-shaped Python API and the C ABI (include/sponet_b200.h).
+
+Nothing here computes: it validates, marshals numpy / torch buffers into the ABI structs, sizes the
+injected streams for replay mode and retries when a stream was too short.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+from numpy.random import Generator
+
+from . import _lib
+from .utils import neighbor_list_to_csr
+
+_DEFAULT_MODE = os.environ.get("SPONET_B200_MODE", "native")
+
+
+def set_default_mode(mode: str) -> None:
+    """``"native"`` (Philox, production path) or ``"replay"`` (bit-exact re-execution of the reference)."""
+    global _DEFAULT_MODE
+    if mode not in ("native", "replay"):
+        raise ValueError("mode must be 'native' or 'replay'")
+    _DEFAULT_MODE = mode
+
+
+def resolve_mode(mode: str | None) -> str:
+    mode = _DEFAULT_MODE if mode is None else mode
+    if mode not in ("native", "replay"):
+        raise ValueError("mode must be 'native' or 'replay'")
+    return mode
+
+
+def current_device() -> int:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+class GraphHandle:
+    """Device-resident CSR of one network on one GPU (sponet_graph_create / _destroy)."""
+
+    def __init__(self, neighbor_list):
+        _lib.require_device()
+        self.row_ptr, self.col = neighbor_list_to_csr(neighbor_list)
+        self.num_agents = len(neighbor_list)
+        self.degrees = np.diff(self.row_ptr)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().sponet_graph_create(self.num_agents, _lib.ptr(self.row_ptr), _lib.ptr(self.col), C.byref(h)))
+        self._h = h
+        self.device = current_device()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                _lib.lib().sponet_graph_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    __del__ = close
+
+
+class GraphCache:
+    """One GraphHandle per (network identity, device); rebuilt when the adjacency object changes."""
+
+    def __init__(self):
+        self._obj = None
+        self._handles: dict[int, GraphHandle] = {}
+
+    def get(self, neighbor_list) -> GraphHandle:
+        if neighbor_list is not self._obj:
+            self.clear()
+            self._obj = neighbor_list
+        dev = current_device()
+        if dev not in self._handles:
+            self._handles[dev] = GraphHandle(neighbor_list)
+        return self._handles[dev]
+
+    def clear(self):
+        for h in self._handles.values():
+            h.close()
+        self._handles = {}
+        self._obj = None
+
+
+# ---------------------------------------------------------------------------------------------
+# struct marshalling
+# ---------------------------------------------------------------------------------------------
+def cnvm_struct(params, degree_alpha):
+    """sponet_cnvm_params + the arrays it points to (keep both alive for the duration of the call)."""
+    pi = np.ascontiguousarray(params.prob_imit, dtype=np.float64)
+    pn = np.ascontiguousarray(params.prob_noise, dtype=np.float64)
+    da = np.ascontiguousarray(degree_alpha, dtype=np.float64)
+    s = _lib.sponet_cnvm_params(
+        int(params.num_opinions), float(params.r_imit), float(params.r_noise), _lib.ptr(pi), _lib.ptr(pn), _lib.ptr(da)
+    )
+    return s, (pi, pn, da)
+
+
+def cntm_struct(next_event_rate, noise_prob, params):
+    return _lib.sponet_cntm_params(
+        float(next_event_rate), float(noise_prob), float(params.threshold_01), float(params.threshold_10)
+    )
+
+
+def cnvm_event_rates(params, degree_alpha, complete: bool) -> tuple[float, float]:
+    """(next_event_rate, noise_probability) with numba's sequential sum (cnvm/model.py:257-258, :383-384)."""
+    ner, npr = C.c_double(), C.c_double()
+    da = np.ascontiguousarray(degree_alpha, dtype=np.float64)
+    _lib.check(
+        _lib.lib().sponet_cnvm_event_rates(
+            None if complete else _lib.ptr(da), int(params.num_agents), float(da[0]), float(params.r_imit),
+            float(params.r_noise), C.byref(ner), C.byref(npr),
+        )
+    )
+    return ner.value, npr.value
+
+
+def cv_struct(spec):
+    if spec is None:
+        return None, None
+    idx, divisor = spec
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    return _lib.sponet_shares_cv(int(idx.size), _lib.ptr(idx), float(divisor)), idx
+
+
+def draw_seed(rng: Generator) -> int:
+    """One uint64 from the caller's generator keys the Philox stream of a native-mode call."""
+    return int(rng.integers(0, 2**64, dtype=np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# native mode
+# ---------------------------------------------------------------------------------------------
+def _alloc(shape, dtype, like):
+    """Output buffer next to the inputs: torch CUDA tensor if ``like`` is one, numpy otherwise."""
+    if like is not None and hasattr(like, "data_ptr") and like.is_cuda:
+        import torch
+
+        tdt = {np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}[dtype]
+        return torch.empty(shape, dtype=tdt, device=like.device)
+    return np.empty(shape, dtype=dtype)
+
+
+def run_native(
+    kind: str,
+    graph: GraphHandle | None,
+    num_agents: int,
+    model_struct,
+    x_init,
+    t_eval: np.ndarray,
+    seed: int,
+    num_runs_total: int,
+    run_begin: int,
+    run_end: int,
+    cv_spec=None,
+    want_x: bool = False,
+    want_cv: bool = False,
+    sums=None,
+    event_counts=None,
+    counters=None,
+    force_global_state: bool = False,
+    counts_init=None,
+):
+    """One C-ABI call of the native ensemble path.
+
+    kind: "cnvm" | "cnvm_counts" | "cntm".  ``x_init`` is (S, N) uint8, numpy or CUDA tensor; outputs
+    are allocated on the same side.  ``sums`` = (sum, sumsq) int64 arrays [S, T, D] accumulated into.
+    Returns (out_x or None, out_cv or None).
+    """
+    L = _lib.lib()
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    T = t_eval.size
+    nrun = run_end - run_begin
+    like = counts_init if kind == "cnvm_counts" else x_init
+    S = like.shape[0]
+    cvs, cv_keep = cv_struct(cv_spec)
+    D = 0 if cv_spec is None else cv_keep.size
+    out_x = _alloc((S, nrun, T, num_agents), np.uint8, like) if want_x else None
+    out_cv = _alloc((S, nrun, T, D), np.float64, like) if want_cv else None
+    opts = _lib.sponet_native_opts(
+        seed & (2**64 - 1), num_runs_total, run_begin, run_end, _lib.ptr(event_counts), int(force_global_state)
+    )
+    sum_p = sumsq_p = None
+    if sums is not None:
+        sum_p, sumsq_p = _lib.ptr(sums[0]), _lib.ptr(sums[1])
+    stream = _lib.current_stream_ptr()
+    cvp = None if cvs is None else C.byref(cvs)
+    if kind == "cnvm":
+        rc = L.sponet_cnvm_run(
+            graph.handle if graph is not None else None, num_agents, C.byref(model_struct), _lib.ptr(x_init), S,
+            _lib.ptr(t_eval), T, C.byref(opts), cvp, _lib.ptr(out_x), _lib.ptr(out_cv), sum_p, sumsq_p,
+            _lib.ptr(counters), stream,
+        )
+    elif kind == "cnvm_counts":
+        rc = L.sponet_cnvm_run_complete_counts(
+            num_agents, C.byref(model_struct), _lib.ptr(counts_init), S, _lib.ptr(t_eval), T, C.byref(opts), cvp,
+            _lib.ptr(out_cv), sum_p, sumsq_p, _lib.ptr(counters), stream,
+        )
+    elif kind == "cntm":
+        rc = L.sponet_cntm_run(
+            graph.handle, C.byref(model_struct), _lib.ptr(x_init), S, _lib.ptr(t_eval), T, C.byref(opts), cvp,
+            _lib.ptr(out_x), _lib.ptr(out_cv), sum_p, sumsq_p, _lib.ptr(counters), stream,
+        )
+    else:
+        raise ValueError(kind)
+    _lib.check(rc)
+    return out_x, out_cv
+
+
+# ---------------------------------------------------------------------------------------------
+# replay mode
+# ---------------------------------------------------------------------------------------------
+def stream_budget(expected_events: float, draws_per_event: float) -> int:
+    """uint64 values to pull for ``expected_events`` loop iterations (Poisson spread + ziggurat retries)."""
+    e = max(expected_events, 1.0)
+    return int(math.ceil(draws_per_event * 1.03 * (e + 10.0 * math.sqrt(e)))) + 4096
+
+
+class RawStream:
+    """Replays a numpy BitGenerator: pulls raw uint64s, and afterwards leaves the generator advanced
+    by exactly the number of values the kernel consumed -- as if the reference loop had run on it."""
+
+    def __init__(self, rng: Generator):
+        self.bitgen = rng.bit_generator
+        self.saved = self.bitgen.state
+
+    def pull(self, n: int) -> np.ndarray:
+        self.bitgen.state = self.saved
+        return self.bitgen.random_raw(n)
+
+    def commit(self, used: int) -> None:
+        self.bitgen.state = self.saved
+        if used:
+            self.bitgen.random_raw(used)
+
+
+def run_replay(
+    kind: str,
+    graph: GraphHandle | None,
+    num_agents: int,
+    model_struct,
+    x_init: np.ndarray,
+    num_runs: int,
+    t_eval: np.ndarray,
+    rngs: list[Generator],
+    work: list[tuple[int, int, int, int]],
+    per_run_budget: int,
+    want_x: bool = True,
+):
+    """Bit-exact replay of W workers, worker w consuming ``rngs[w]`` over its (state, run) block.
+
+    Returns (out_t [S,R,T], out_x [S,R,T,N] or None, events per worker).
+    """
+    L = _lib.lib()
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    S, T, W = x_init.shape[0], t_eval.size, len(work)
+    streams = [RawStream(r) for r in rngs]
+    out_t = np.empty((S, num_runs, T), dtype=np.float64)
+    out_x = np.empty((S, num_runs, T, num_agents), dtype=x_init.dtype) if want_x else None
+    used = np.zeros(W, dtype=np.int64)
+    events = np.zeros(W, dtype=np.int64)
+    scale = 1
+    while True:
+        lens = [max(1, (sb_e - sb) * (rb_e - rb)) * per_run_budget * scale for (sb, sb_e, rb, rb_e) in work]
+        raw = np.concatenate([s.pull(n) for s, n in zip(streams, lens)])
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        warr = (_lib.sponet_replay_work * W)(
+            *[_lib.sponet_replay_work(sb, se, rb, re, int(offs[w]), int(lens[w])) for w, (sb, se, rb, re) in enumerate(work)]
+        )
+        args_tail = (
+            _lib.ptr(x_init), S, num_runs, _lib.ptr(t_eval), T, _lib.ptr(raw), C.cast(warr, C.c_void_p), W,
+            _lib.ptr(out_t), _lib.ptr(out_x), _lib.ptr(used), _lib.ptr(events), None,
+        )
+        if kind == "cnvm":
+            rc = L.sponet_cnvm_replay(graph.handle if graph is not None else None, num_agents, C.byref(model_struct), *args_tail)
+        else:
+            rc = L.sponet_cntm_replay(graph.handle, C.byref(model_struct), *args_tail)
+        try:
+            _lib.check(rc)
+            break
+        except _lib.StreamExhausted:
+            scale *= 2
+            if scale > 1 << 12:
+                raise
+    for s, u in zip(streams, used):
+        s.commit(int(u))
+    return out_t, out_x, events
+
+
+def run_replay_all(kind, graph, num_agents, model_struct, x_init: np.ndarray, t_max: float, rng: Generator,
+                   expected_events: float, draws_per_event: float):
+    """Store-every-change replay of one realization -> (t_traj, x_traj) like the reference lists."""
+    L = _lib.lib()
+    stream = RawStream(rng)
+    budget = stream_budget(expected_events, draws_per_event)
+    cap = int(expected_events + 10 * math.sqrt(max(expected_events, 1.0))) + 1024
+    while True:
+        raw = stream.pull(budget)
+        log_t = np.empty(cap, dtype=np.float64)
+        log_a = np.empty(cap, dtype=np.int32)
+        log_o = np.empty(cap, dtype=np.int32)
+        cnt, used, events = (np.zeros(1, dtype=np.int64) for _ in range(3))
+        tail = (_lib.ptr(x_init), float(t_max), _lib.ptr(raw), raw.size, cap, _lib.ptr(log_t), _lib.ptr(log_a),
+                _lib.ptr(log_o), _lib.ptr(cnt), _lib.ptr(used), _lib.ptr(events), None)
+        if kind == "cnvm":
+            rc = L.sponet_cnvm_replay_all(graph.handle if graph is not None else None, num_agents, C.byref(model_struct), *tail)
+        else:
+            rc = L.sponet_cntm_replay_all(graph.handle, C.byref(model_struct), *tail)
+        try:
+            _lib.check(rc)
+            break
+        except _lib.StreamExhausted:
+            budget *= 2
+        except ValueError as err:
+            if "capacity" not in str(err):
+                raise
+            cap *= 2
+    stream.commit(int(used[0]))
+    k = int(cnt[0])
+    t_traj = np.concatenate(([0.0], log_t[:k]))
+    # the reference stores a full copy of x per accepted change (cnvm/model.py:232-234)
+    x_traj = np.empty((k + 1, num_agents), dtype=x_init.dtype)
+    x = x_init.copy()
+    x_traj[0] = x
+    for i in range(k):
+        x[log_a[i]] = log_o[i]
+        x_traj[i + 1] = x
+    return t_traj, x_traj

@@ -1,0 +1,279 @@
+"""Ensemble driver (reference: sponet/multiprocessing.py:18-196).
+
+``sample_many_runs`` keeps the reference's signature and output shapes.  What changes is who does
+the work: all ``num_initial_states x num_runs`` realizations go to the GPU in one batched C-ABI
+call instead of a process pool of numba loops.
+
+native mode (default)
+    Chain (j, i) = (initial state j, run i) draws from the Philox stream keyed by one uint64 taken
+    from ``rng`` and countered by ``j * num_runs + i``: results depend on the seed only -- not on
+    ``n_jobs`` (accepted, ignored), not on how runs are sharded over GPUs.  An unweighted
+    ``OpinionShares`` CV is reduced inside the simulation kernel (complete graphs take the count-only
+    kernel); other CVs are evaluated on the GPU from snapshot slabs, run-chunk by run-chunk.
+    Under ``torch.distributed`` (one process per GPU) the runs are split over the ranks like
+    ``_split_runs`` and the pieces are all-gathered, so every rank returns the full array.
+
+replay mode
+    Reproduces the reference bit for bit, including its stream discipline: ``n_jobs in (None, 1)``
+    threads ONE generator through all runs (multiprocessing.py:171-178), otherwise ``rng.spawn(n_jobs)``
+    gives one stream per chunk (:90-103).  One GPU warp replays each stream.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+from numpy.random import Generator, default_rng
+from numpy.typing import ArrayLike, NDArray
+
+from . import engine
+from .cntm.model import CNTM
+from .cntm.parameters import CNTMParameters
+from .cnvm.model import CNVM
+from .cnvm.parameters import CNVMParameters
+from .collective_variables import CollectiveVariable, OpinionShares
+from .parameters import Parameters
+from .utils import t_eval_to_ndarray
+
+# device memory budget for snapshot slabs when a CV has to be evaluated from stored states
+_SLAB_BYTES = int(os.environ.get("SPONET_B200_SLAB_BYTES", 2 << 30))
+
+
+def _split_runs(num_runs: int, num_chunks: int) -> np.ndarray:
+    """Near-equal chunk sizes, larger chunks first (reference :190-196): (20, 6) -> [4,4,3,3,3,3]."""
+    base, extra = divmod(num_runs, num_chunks)
+    chunks = np.full(num_chunks, base, dtype=int)
+    chunks[:extra] += 1
+    return chunks
+
+
+def _make_model(params: Parameters):
+    if isinstance(params, CNVMParameters):
+        return CNVM(params), "cnvm"
+    if isinstance(params, CNTMParameters):
+        return CNTM(params), "cntm"
+    raise ValueError("Parameters not valid.")
+
+
+def _dist():
+    """(rank, world) of an initialised torch.distributed job, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def sample_many_runs(
+    params: Parameters,
+    initial_states: ArrayLike,
+    t_max: float,
+    t_eval: ArrayLike,
+    num_runs: int,
+    n_jobs: int | None = None,
+    collective_variable: CollectiveVariable | None = None,
+    rng: Generator = default_rng(),
+    progress_bar: bool = False,
+    mode: str | None = None,
+) -> tuple[NDArray, NDArray]:
+    """Sample ``num_runs`` realizations per initial state.
+
+    Returns ``(t_out, x_out)`` with ``t_out.shape == (T,)`` and ``x_out.shape == (S, R, T, N)`` (dtype of
+    the opinions) or ``(S, R, T, D)`` float64 with a collective variable; the leading axis is dropped
+    for a single 1-D initial state.
+    """
+    initial_states = np.array(initial_states, ndmin=1)
+    is_1d = initial_states.ndim == 1
+    if is_1d:
+        initial_states = initial_states[None, :]
+    t_out = t_eval_to_ndarray(t_eval, t_max)
+    model, kind = _make_model(params)
+    mode = engine.resolve_mode(mode)
+    dtype = np.min_scalar_type(params.num_opinions - 1)
+
+    per_run_network = getattr(params, "network_generator", None) is not None
+    if mode == "replay" or params.num_opinions > 256 or per_run_network:
+        x_out = _sample_replay(model, kind, initial_states.astype(dtype), t_max, t_out, num_runs, n_jobs,
+                               collective_variable, rng, progress_bar, per_run_network)
+    else:
+        x_out = _sample_native(model, kind, initial_states.astype(np.uint8), t_out, num_runs,
+                               collective_variable, rng, progress_bar).astype(
+            dtype if collective_variable is None else np.float64, copy=False)
+    return t_out, (x_out[0] if is_1d else x_out)
+
+
+# ---------------------------------------------------------------------------------------------
+# native
+# ---------------------------------------------------------------------------------------------
+def _kernel_cv_spec(cv, num_agents):
+    if isinstance(cv, OpinionShares):
+        return cv._kernel_spec(num_agents)
+    return None
+
+
+def _native_call(model, kind, x_init, t_out, seed, R_total, rb, re, **kw):
+    p = model.params
+    if kind == "cnvm":
+        struct, keep = model._struct()
+        out = engine.run_native("cnvm", model._graph(), p.num_agents, struct, x_init, t_out, seed, R_total, rb, re, **kw)
+        del keep
+        return out
+    return engine.run_native("cntm", model._graph(), p.num_agents, model._struct(), x_init, t_out, seed, R_total, rb, re, **kw)
+
+
+def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
+    p = model.params
+    S, N, T = states.shape[0], p.num_agents, t_out.size
+    seed = engine.draw_seed(rng)
+    rank, world = _dist()
+    if world > 1:  # every rank must use the same key: take rank 0's
+        seed = _broadcast_seed(seed)
+    bounds = np.concatenate(([0], np.cumsum(_split_runs(num_runs, world))))
+    rb, re = int(bounds[rank]), int(bounds[rank + 1])
+    states = np.ascontiguousarray(states)
+    pbar = _progress(progress_bar, S * (re - rb))
+
+    spec = _kernel_cv_spec(cv, N)
+    if spec is not None:
+        if kind == "cnvm" and model.is_complete and p.num_opinions <= 16:
+            counts0 = np.stack([np.bincount(s, minlength=p.num_opinions) for s in states]).astype(np.int64)
+            struct, keep = model._struct()
+            _, local = engine.run_native("cnvm_counts", None, N, struct, None, t_out, seed, num_runs, rb, re,
+                                         cv_spec=spec, want_cv=True, counts_init=counts0)
+            del keep
+        else:
+            _, local = _native_call(model, kind, states, t_out, seed, num_runs, rb, re, cv_spec=spec, want_cv=True)
+        _tick(pbar, S * (re - rb))
+    elif cv is None:
+        local, _ = _native_call(model, kind, states, t_out, seed, num_runs, rb, re, want_x=True)
+        _tick(pbar, S * (re - rb))
+    else:
+        local = _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, pbar)
+    _close(pbar)
+    return _gather_runs(local, bounds, world) if world > 1 else local
+
+
+def _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, pbar):
+    """CV evaluated from snapshot slabs that stay on the GPU; runs are processed in memory-sized chunks."""
+    import torch
+
+    p = model.params
+    S, N, T = states.shape[0], p.num_agents, t_out.size
+    out = np.empty((S, re - rb, T, cv.dimension), dtype=np.float64)
+    chunk = max(1, int(_SLAB_BYTES // max(1, S * T * N)))
+    d_states = torch.as_tensor(states, device="cuda")
+    for lo in range(rb, re, chunk):
+        hi = min(re, lo + chunk)
+        slab, _ = _native_call(model, kind, d_states, t_out, seed, num_runs, lo, hi, want_x=True)
+        try:
+            c = cv(slab.reshape(-1, N))  # GPU path of the OpinionShares family
+        except (TypeError, AttributeError):  # user-defined CV: host evaluation on the copied slab
+            c = cv(slab.reshape(-1, N).cpu().numpy())
+        c = c.cpu().numpy() if hasattr(c, "cpu") else np.asarray(c)
+        out[:, lo - rb : hi - rb] = c.reshape(S, hi - lo, T, cv.dimension)
+        _tick(pbar, S * (hi - lo))
+    return out
+
+
+def _broadcast_seed(seed: int) -> int:
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, seed >> 63], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=0)
+    return int(t[0].item()) | (int(t[1].item()) << 63)
+
+
+def _gather_runs(local: np.ndarray, bounds: np.ndarray, world: int) -> np.ndarray:
+    """All-gather the per-rank run slices (axis 1) into the full array on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    sizes = np.diff(bounds)
+    width = int(sizes.max())
+    shape = list(local.shape)
+    shape[1] = width
+    pad = torch.zeros(shape, dtype=torch.from_numpy(local[:0]).dtype, device=dev)
+    pad[:, : local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    pieces = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(pieces, pad)
+    return np.concatenate([pc[:, : int(sizes[r])].cpu().numpy() for r, pc in enumerate(pieces)], axis=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# replay
+# ---------------------------------------------------------------------------------------------
+def _sample_replay(model, kind, states, t_max, t_out, num_runs, n_jobs, cv, rng, progress_bar, per_run_network):
+    p = model.params
+    S, N, T = states.shape[0], p.num_agents, t_out.size
+    D = N if cv is None else cv.dimension
+    x_out = np.zeros((S, num_runs, T, D), dtype=states.dtype if cv is None else np.float64)
+
+    if per_run_network:
+        # A NetworkGenerator resamples the graph inside every simulate() call (cnvm/model.py:95-96):
+        # run the realizations one by one on a single generator, exactly like _Worker.__call__.
+        pbar = _progress(progress_bar, S * num_runs)
+        for j in range(S):
+            for i in range(num_runs):
+                _, x = model.simulate(t_max, x_init=states[j], t_eval=t_out, rng=rng, mode="replay")
+                x_out[j, i] = x if cv is None else cv(x)
+                _tick(pbar, 1)
+        _close(pbar)
+        return x_out
+
+    if n_jobs is None or n_jobs == 1:
+        rngs, work = [rng], [(0, S, 0, num_runs)]
+    else:
+        if n_jobs == -1:
+            n_jobs = os.cpu_count()
+            if n_jobs is None:
+                raise RuntimeError("Could not determine number of available CPUs.")
+        rngs = rng.spawn(n_jobs)
+        if num_runs >= S:  # split along runs (reference :96-99)
+            b = np.concatenate(([0], np.cumsum(_split_runs(num_runs, n_jobs))))
+            work = [(0, S, int(b[w]), int(b[w + 1])) for w in range(n_jobs)]
+        else:  # split along initial states (reference :100-103, np.array_split sizes)
+            b = np.concatenate(([0], np.cumsum([len(c) for c in np.array_split(np.arange(S), n_jobs)])))
+            work = [(int(b[w]), int(b[w + 1]), 0, num_runs) for w in range(n_jobs)]
+
+    if kind == "cnvm":
+        struct, keep = model._struct()
+        rate, _ = model.event_rates()
+    else:
+        struct, keep, rate = model._struct(), None, model.next_event_rate
+    budget = engine.stream_budget((t_out[-1] - t_out[0]) / rate + 1, model._draws_per_event())
+    _, xs, _ = engine.run_replay(kind, model._graph(), N, struct, np.ascontiguousarray(states), num_runs, t_out,
+                                 rngs, work, budget)
+    del keep
+    if cv is None:
+        return xs
+    for j in range(S):
+        for i in range(num_runs):
+            x_out[j, i] = cv(xs[j, i])
+    return x_out
+
+
+# ---------------------------------------------------------------------------------------------
+# progress bar plumbing (reference shows tqdm for worker 0 only, :92-94, :169, :184-185)
+# ---------------------------------------------------------------------------------------------
+def _progress(enabled: bool, total: int):
+    if not enabled:
+        return None
+    from tqdm import tqdm
+
+    return tqdm(total=total)
+
+
+def _tick(pbar, n):
+    if pbar is not None:
+        pbar.update(n)
+
+
+def _close(pbar):
+    if pbar is not None:
+        pbar.close()

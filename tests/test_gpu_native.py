@@ -1,0 +1,185 @@
+"""GPU: the native-mode kernels against their sequential statement (oracle/oracle_native.inc).
+
+The kernels evaluate 32 candidate events per warp step in parallel; the oracle executes the same
+Philox-keyed chain one event at a time.  Results must be identical (integer states / counts).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R3 = np.array([[0, 1, 2], [1, 0, 1], [2, 0, 0]], dtype=float)
+RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
+
+
+def _net(kind, n, seed):
+    import networkx as nx
+
+    if kind == "er":
+        g = nx.erdos_renyi_graph(n, 10 / (n - 1), seed=seed)
+    elif kind == "ba":
+        g = nx.barabasi_albert_graph(n, 5, seed=seed)
+    else:
+        g = nx.cycle_graph(n)
+    for v in list(nx.isolates(g)):
+        g.add_edge(v, (v + 1) % n)
+    return g
+
+
+def test_event_counts_match_oracle(oracle):
+    from sponet_b200 import _lib
+
+    t_eval = np.array([0.0, 0.1, 0.25, 0.2500001, 1.0, 1.00002, 3.0])
+    rate = 1.0 / 2.6e4  # lam from 2.6e-3 to 5.2e4 across the intervals
+    out = np.empty((40, t_eval.size - 1), dtype=np.int64)
+    _lib.check(_lib.lib().sponet_native_event_counts(99, 1000, 40, _lib.ptr(t_eval), t_eval.size, rate, _lib.ptr(out), None))
+    np.testing.assert_array_equal(out, oracle.native_event_counts(99, 1000, 40, t_eval, rate))
+
+
+@pytest.mark.parametrize("kind,n,M,alpha,force_global", [
+    ("er", 1000, 3, 1.0, False),
+    ("er", 1000, 3, 1.0, True),
+    ("ba", 600, 3, 0.5, False),   # alias tables
+    ("cycle", 64, 2, 1.0, False),  # tiny N: many intra-step hazards
+    ("er", 300, 7, 1.0, False),    # 4-bit packing, shared-memory counters
+    ("er", 300, 40, 0.0, False),   # 8-bit packing, thresholds in global memory
+    ("complete", 500, 3, 1.0, False),
+    ("complete", 33, 2, 1.0, True),
+])
+def test_cnvm_native_matches_sequential_oracle(oracle, kind, n, M, alpha, force_global):
+    from sponet_b200 import CNVM, CNVMParameters, engine
+
+    rng = np.random.default_rng(3)
+    if M == 3:
+        r, rt = R3, RT3
+    else:
+        r, rt = rng.random((M, M)), 0.05 * rng.random((M, M))
+    if kind == "complete":
+        params = CNVMParameters(num_opinions=M, num_agents=n, r=r, r_tilde=rt, alpha=alpha)
+        rp = col = None
+    else:
+        params = CNVMParameters(num_opinions=M, network=_net(kind, n, 1), r=r, r_tilde=rt, alpha=alpha)
+        rp, col = oracle.neighbor_list_to_csr(params.network)
+    model = CNVM(params)
+    S, R, T = 2, 5, 6
+    states = rng.integers(0, M, (S, n)).astype(np.uint8)
+    t_eval = np.linspace(0, 4.0, T)
+    seed = 0xC0FFEE123456789
+    struct, keep = model._struct()
+    counters = np.zeros(4, dtype=np.uint64)
+    spec = (np.arange(M, dtype=np.int32), 1.0)
+    sums = (np.zeros((S, T, M), dtype=np.int64), np.zeros((S, T, M), dtype=np.int64))
+    out_x, out_cv = engine.run_native("cnvm", model._graph(), n, struct, states, t_eval, seed, R, 0, R, cv_spec=spec,
+                                      want_x=True, want_cv=True, sums=sums, counters=counters,
+                                      force_global_state=force_global)
+    rate, noise_p = model.event_rates()
+    thr_i, thr_n = oracle.prob_to_thr(params.prob_imit), oracle.prob_to_thr(params.prob_noise)
+    noise_thr = int(oracle.prob_to_thr(noise_p))
+    da = np.asarray(model.degree_alpha, dtype=float)
+    if kind != "complete" and not np.all(da == da[0]):
+        prob, alias = oracle.build_alias_table(da)
+        alias_thr = oracle.prob_to_thr(prob)
+    else:
+        alias_thr = alias = None
+    total_ev = total_acc = 0
+    exp_sum = np.zeros((S, T, M), dtype=np.int64)
+    exp_sq = np.zeros((S, T, M), dtype=np.int64)
+    for j in range(S):
+        for i in range(R):
+            chain = j * R + i
+            counts = oracle.native_event_counts(seed, chain, 1, t_eval, rate)[0]
+            ox, oc, ev, acc = oracle.cnvm_native(states[j], M, rp, col, noise_thr, thr_i, thr_n, alias_thr, alias,
+                                                 counts, seed, chain)
+            np.testing.assert_array_equal(out_x[j, i], ox, err_msg=f"states differ for chain ({j},{i})")
+            np.testing.assert_array_equal(out_cv[j, i], oc.astype(float))
+            exp_sum[j] += oc
+            exp_sq[j] += oc * oc
+            total_ev += ev
+            total_acc += acc
+    np.testing.assert_array_equal(sums[0], exp_sum)
+    np.testing.assert_array_equal(sums[1], exp_sq)
+    assert int(counters[0]) == total_ev and int(counters[1]) == total_acc
+    del keep
+
+
+def test_cnvm_native_sharding_is_invisible(oracle):
+    """Runs [0,R) in one call == runs split over two calls (what two GPUs would do)."""
+    from sponet_b200 import CNVM, CNVMParameters, engine
+
+    params = CNVMParameters(num_opinions=3, network=_net("er", 400, 2), r=R3, r_tilde=RT3)
+    model = CNVM(params)
+    states = np.random.default_rng(0).integers(0, 3, (2, 400)).astype(np.uint8)
+    t_eval = np.linspace(0, 2.0, 5)
+    struct, keep = model._struct()
+    spec = (np.array([2, 0], dtype=np.int32), 400.0)
+    _, full = engine.run_native("cnvm", model._graph(), 400, struct, states, t_eval, 7, 9, 0, 9, cv_spec=spec, want_cv=True)
+    _, a = engine.run_native("cnvm", model._graph(), 400, struct, states, t_eval, 7, 9, 0, 4, cv_spec=spec, want_cv=True)
+    _, b = engine.run_native("cnvm", model._graph(), 400, struct, states, t_eval, 7, 9, 4, 9, cv_spec=spec, want_cv=True)
+    np.testing.assert_array_equal(full, np.concatenate([a, b], axis=1))
+    del keep
+
+
+def test_cnvm_complete_counts_matches_oracle(oracle):
+    from sponet_b200 import CNVM, CNVMParameters, engine
+
+    for M, n in ((2, 1000), (3, 777), (6, 300)):
+        rng = np.random.default_rng(M)
+        r, rt = (R3, RT3) if M == 3 else (rng.random((M, M)), 0.1 * rng.random((M, M)))
+        params = CNVMParameters(num_opinions=M, num_agents=n, r=r, r_tilde=rt)
+        model = CNVM(params)
+        S, R, T = 2, 40, 7
+        c0 = np.stack([np.bincount(rng.integers(0, M, n), minlength=M) for _ in range(S)]).astype(np.int64)
+        t_eval = np.linspace(0, 3.0, T)
+        struct, keep = model._struct()
+        spec = (np.arange(M, dtype=np.int32), 1.0)
+        counters = np.zeros(4, dtype=np.uint64)
+        _, out = engine.run_native("cnvm_counts", None, n, struct, None, t_eval, 42, R, 0, R, cv_spec=spec, want_cv=True,
+                                   counts_init=c0, counters=counters)
+        rate, noise_p = model.event_rates()
+        thr_i, thr_n = oracle.prob_to_thr(params.prob_imit), oracle.prob_to_thr(params.prob_noise)
+        ev_total = 0
+        for j in range(S):
+            for i in range(R):
+                chain = j * R + i
+                counts = oracle.native_event_counts(42, chain, 1, t_eval, rate)[0]
+                oc, ev = oracle.cnvm_complete_counts_native(c0[j], n, M, int(oracle.prob_to_thr(noise_p)), thr_i, thr_n,
+                                                            counts, 42, chain)
+                np.testing.assert_array_equal(out[j, i], oc.astype(float))
+                ev_total += ev
+        assert int(counters[0]) == ev_total
+        del keep
+
+
+@pytest.mark.parametrize("kind,n,force_global", [("er", 500, False), ("ba", 800, False), ("ba", 800, True), ("cycle", 40, False)])
+def test_cntm_native_matches_sequential_oracle(oracle, kind, n, force_global):
+    import networkx as nx
+
+    from sponet_b200 import CNTM, CNTMParameters, engine
+
+    g = _net(kind, n, 4) if kind != "er" else nx.erdos_renyi_graph(n, 4 / n, seed=4)  # ER keeps isolates
+    params = CNTMParameters(g, 1.0, 0.2, 0.4, 0.55)
+    model = CNTM(params)
+    S, R, T = 2, 4, 6
+    states = np.random.default_rng(5).integers(0, 2, (S, n)).astype(np.uint8)
+    t_eval = np.linspace(0, 6.0, T)
+    seed = 2024
+    spec = (np.array([0, 1], dtype=np.int32), 1.0)
+    counters = np.zeros(4, dtype=np.uint64)
+    out_x, out_cv = engine.run_native("cntm", model._graph(), n, model._struct(), states, t_eval, seed, R, 0, R,
+                                      cv_spec=spec, want_x=True, want_cv=True, counters=counters,
+                                      force_global_state=force_global)
+    rp, col = oracle.neighbor_list_to_csr(model.neighbor_list)
+    noise_thr = int(oracle.prob_to_thr(model.noise_prob))
+    ev_total = acc_total = 0
+    for j in range(S):
+        for i in range(R):
+            chain = j * R + i
+            counts = oracle.native_event_counts(seed, chain, 1, t_eval, model.next_event_rate)[0]
+            ox, oc, ev, acc = oracle.cntm_native(states[j], rp, col, noise_thr, 0.4, 0.55, counts, seed, chain)
+            np.testing.assert_array_equal(out_x[j, i], ox)
+            np.testing.assert_array_equal(out_cv[j, i], oc.astype(float))
+            ev_total += ev
+            acc_total += acc
+    assert int(counters[0]) == ev_total and int(counters[1]) == acc_total
