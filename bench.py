@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-update events/s of the CNVM ensemble on an Erdos-Renyi N=1e5 network.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json metric, SURVEY.md section 8(d) "H", BASELINE.md section 3 headline row):
+CNVM, M = 3, ER G(1e5, 10/(N-1)) seed 12345 (nnz 998 782), fixture rates (r_imit 2, r_noise 0.6),
+alpha = 1, x_init = default_rng(0).integers(0, 3, N), t_max = 10, 101 output times, OpinionShares(3)
+reduced in-kernel, 10^4 realizations per GPU.  One "step" = one pass of the hot path over that batch
+(~2.6e10 candidate events per GPU).  An "event" is one iteration of the reference while-loop
+(sponet/cnvm/model.py:274-306): one candidate event of the uniformised chain, accepted or not.
+
+Numbers on the JSON line
+  value     whole-job events/s, inputs resident in HBM, timed per step with CUDA events on the
+            launching stream (L2 flushed between steps), max over ranks.
+  e2e       the same metric through the public API `sample_many_runs` with HOST numpy buffers:
+            graph lookup, H2D of the inputs, kernels, D2H of the [R, T, 3] float64 result.
+  roofline  algorithmic bytes (14 B per imitation event + 1 B per noise event + 1 B
+            per accepted write) / step time, against the measured HBM copy bandwidth.
+  cpu_baseline  the oracle port of the reference loop (oracle/, plain C, pthreads over runs) timed
+            on this box's host cores on a bounded sample of the same workload.
+
+`--impl reference` times that CPU implementation alone (the reference is Python + numba with no
+compiled sources to build here; oracle/ is its bit-exact C restatement).
+Multi-GPU: one process per GPU (torchrun), runs sharded by index, no data-path collective ("weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-update events/sec (CNVM, ER N=1e5, ensemble)"
+N_AGENTS = 100_000
+RUNS_PER_GPU = 10_000
+T_MAX = 10.0
+NUM_T = 101
+WORKLOAD = (
+    "H: CNVM M=3 on ER N=1e5 <d>=10 (fast_gnp seed 12345, nnz 998782), fixture rates r_imit=2 r_noise=0.6, "
+    "alpha=1, t_max=10, 101 output times, OpinionShares(3) in-kernel, 1e4 realizations per GPU"
+)
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as fh:
+                return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as fh:
+                return json.load(fh).get("cnvm_native_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = (
+        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference loop on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(num_runs: int, threads: int, seed: int):
+    """Runs `num_runs` realizations of H on `threads` host threads.  Returns (events, seconds)."""
+    import oracle
+    from sponet_b200 import workloads
+
+    ctx = cpu_reference_run.__dict__
+    if "setup" not in ctx:
+        params, x0, _ = workloads.headline_cnvm(N_AGENTS)
+        row_ptr, col = oracle.neighbor_list_to_csr(params.network)
+        ctx["setup"] = (params, x0, row_ptr, col)
+        oracle.lib()
+    params, x0, row_ptr, col = ctx["setup"]
+    t_eval = np.linspace(0, T_MAX, NUM_T)
+    da = np.ones(N_AGENTS)  # alpha = 1
+    t0 = time.perf_counter()
+    _, events = oracle.sample_many_runs(
+        "cnvm", x0, num_runs, t_eval, 3, row_ptr=row_ptr, col=col, r_imit=params.r_imit, r_noise=params.r_noise,
+        prob_imit=params.prob_imit, prob_noise=params.prob_noise, degree_alpha=da, seed=seed, num_threads=threads)
+    return int(events), time.perf_counter() - t0
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    # calibrate: one run per thread, then size each step for ~8 s
+    ev, sec = cpu_reference_run(threads, threads, 1)
+    per_run = sec  # wall time of one run per thread
+    runs_per_step = max(threads, int(threads * max(1.0, 8.0 / max(per_run, 1e-3))))
+    for w in range(args.warmup):
+        cpu_reference_run(threads, threads, 100 + w)
+    tot_ev, tot_sec = 0, 0.0
+    for k in range(args.steps):
+        ev, sec = cpu_reference_run(runs_per_step, threads, 1000 + k)
+        tot_ev += ev
+        tot_sec += sec
+    value = tot_ev / tot_sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_arm": "oracle port of sponet/cnvm/model.py:239-308 (C, pthreads over runs)"},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": threads, "kind": "port",
+                         "sample": f"{runs_per_step} realizations of H per step on {threads} threads"},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from sponet_b200 import CNVM, OpinionShares, engine, sample_many_runs, workloads
+    from sponet_b200 import multiprocessing as smp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    params, x0, rate = workloads.headline_cnvm(N_AGENTS)
+    model = CNVM(params)
+    graph = model._graph()
+    struct, keep = model._struct()
+    t_eval = np.linspace(0, T_MAX, NUM_T)
+    spec = (np.arange(3, dtype=np.int32), 1.0)
+    d_x0 = torch.as_tensor(x0[None, :], device="cuda")
+    R, R_total = RUNS_PER_GPU, RUNS_PER_GPU * world
+    rb, re = rank * R, (rank + 1) * R
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step(seed, counters=None):
+        return engine.run_native("cnvm", graph, N_AGENTS, struct, d_x0, t_eval, seed, R_total, rb, re,
+                                 cv_spec=spec, want_cv=True, counters=counters)
+
+    for w in range(args.warmup):
+        step(10 + w)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    step_ms = []
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # evict L2 between timed iterations (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(1000 + k, counters)
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+
+    c = counters.cpu().numpy().astype(np.float64)
+    stats = torch.tensor([sum(step_ms), c[0], c[1]], dtype=torch.float64, device="cuda")
+    tmax = stats[:1].clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    total_ms = float(tmax.item())
+    events, accepted = float(stats[1].item()), float(stats[2].item())
+    value = events / (total_ms * 1e-3)
+
+    # ---- e2e: public API, host buffers in, host array out ----
+    cv = OpinionShares(3)
+    rng = np.random.default_rng(7)
+    if world > 1:
+        # each rank drives its own 1e4 runs through the public API (no gather: weak scaling)
+        smp_dist = smp._dist
+        smp._dist = lambda: (0, 1)
+    e2e_steps = max(1, min(args.steps, 3))
+    sample_many_runs(params, x0, T_MAX, NUM_T, R, collective_variable=cv, rng=rng)  # warm (graph upload, caches)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, x = sample_many_runs(params, x0, T_MAX, NUM_T, R, collective_variable=cv, rng=rng)
+    torch.cuda.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
+    if world > 1:
+        smp._dist = smp_dist
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_events = events / max(args.steps, 1) * e2e_steps  # same expected work per step (Poisson counts)
+    e2e_value = e2e_events / float(e2e_t.item())
+    h2d = int(x0.nbytes + t_eval.nbytes + 2 * 9 * 4 + 3 * 4)
+    d2h = int(x.nbytes)
+
+    if rank == 0:
+        p_acc = accepted / max(events, 1.0)
+        p_noise = params.r_noise * N_AGENTS / rate
+        bytes_per_event = (1.0 - p_noise) * 14.0 + p_noise * 1.0 + p_acc * 1.0
+        peak, peak_src = measured_peaks()
+        per_gpu_events_per_s = value / world
+        achieved = per_gpu_events_per_s * bytes_per_event / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 (2-bit packed states, u32 Philox draws)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"runs sharded over {world} GPU(s), no collective",
+                       "l2": "flushed between timed steps (256 MiB write)", "events_per_step_per_gpu": events / max(args.steps, 1) / world,
+                       "accepted_fraction": p_acc},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "sponet_b200.sample_many_runs(params, x_init, 10.0, 101, 10000, collective_variable=OpinionShares(3))",
+                    "steps": e2e_steps},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_event": bytes_per_event,
+                         "kernel": "cnvm_native_kernel<2,smem,csr>", "note": "chain states live in shared memory and the CSR in L2, so DRAM traffic is far below the algorithmic bytes by design; the kernel is issue/latency bound (DESIGN.md section 5)"},
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            cpu_reference_run(threads, threads, 1)  # warm + calibrate
+            ev, sec = cpu_reference_run(threads, threads, 2)
+            runs = max(threads, int(threads * max(1.0, 12.0 / max(sec, 1e-3))))
+            ev, sec = cpu_reference_run(runs, threads, 3)
+            line["cpu_baseline"] = {"value": ev / sec, "unit": "events/s", "cores": threads, "kind": "port",
+                                    "sample": f"{runs} realizations of H (t_max=10, T=101) on {threads} host threads, {sec:.1f} s"}
+        print(json.dumps(line), flush=True)
+    del keep
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        port = str(29500 + os.getpid() % 2000)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", port,
+                                   os.path.abspath(__file__), *sys.argv[1:]])
+    run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ replay mode
 from __future__ import annotations
 
 import os
+import weakref
 
 import numpy as np
 from numpy.random import Generator, default_rng
@@ -47,12 +48,37 @@ def _split_runs(num_runs: int, num_chunks: int) -> np.ndarray:
     return chunks
 
 
+# The reference rebuilds the model in every worker (multiprocessing.py:146-151).  Here that would mean
+# re-deriving the CSR and re-uploading it to HBM on every call, so models are kept per parameter
+# object for as long as the network / alpha they were built from are unchanged.
+_MODEL_CACHE: dict[int, tuple] = {}
+
+
+def _fingerprint(params):
+    net = getattr(params, "network", None)
+    if isinstance(params, CNVMParameters):
+        return (id(net), params.alpha, params.num_agents)
+    return (id(net), net.number_of_nodes(), net.number_of_edges(), params.r, params.r_tilde)
+
+
 def _make_model(params: Parameters):
     if isinstance(params, CNVMParameters):
-        return CNVM(params), "cnvm"
-    if isinstance(params, CNTMParameters):
-        return CNTM(params), "cntm"
-    raise ValueError("Parameters not valid.")
+        kind, cls = "cnvm", CNVM
+    elif isinstance(params, CNTMParameters):
+        kind, cls = "cntm", CNTM
+    else:
+        raise ValueError("Parameters not valid.")
+    if getattr(params, "network_generator", None) is not None:
+        return cls(params), kind
+    key, fp = id(params), _fingerprint(params)
+    hit = _MODEL_CACHE.get(key)
+    if hit is not None and hit[0]() is params and hit[2] == fp:
+        return hit[1], kind
+    model = cls(params)
+    if len(_MODEL_CACHE) >= 8:
+        _MODEL_CACHE.pop(next(iter(_MODEL_CACHE)))
+    _MODEL_CACHE[key] = (weakref.ref(params), model, fp)
+    return model, kind
 
 
 def _dist():
