@@ -1,0 +1,76 @@
+"""Reference CV samples for the statistical parity tests of native mode (build container only).
+
+    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_stats_golden.py
+
+For each small configuration the UNMODIFIED reference runs >= 1e4 realizations through
+`sample_many_runs(..., n_jobs=8)` with OpinionShares as collective variable; the per-run counts
+[R, T, M] are stored as uint16 in tests/golden/stats_*.npz together with the inputs.
+"""
+import os
+import sys
+
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+sys.path.insert(0, "/root/reference")
+
+import networkx as nx  # noqa: E402
+import numpy as np  # noqa: E402
+
+from sponet import CNTMParameters, CNVMParameters, OpinionShares, sample_many_runs  # noqa: E402
+from sponet.utils import calculate_neighbor_list  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+R3 = np.array([[0, 1, 2], [1, 0, 1], [2, 0, 0]], dtype=float)
+RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
+RUNS = 12_000
+
+
+def csr(nl):
+    deg = np.array([len(nb) for nb in nl])
+    rp = np.zeros(len(nl) + 1, dtype=np.int32)
+    np.cumsum(deg, out=rp[1:])
+    return rp, np.concatenate([np.asarray(nb, dtype=np.int32) for nb in nl])
+
+
+def patch(g):
+    for v in list(nx.isolates(g)):
+        g.add_edge(v, (v + 1) % g.number_of_nodes())
+    return g
+
+
+def run(name, params, M, x0, t_max, T, extra):
+    cv = OpinionShares(M)
+    _, x = sample_many_runs(params, x0, t_max, T, RUNS, n_jobs=8, collective_variable=cv, rng=np.random.default_rng(hash(name) % 2**32))
+    np.savez_compressed(os.path.join(OUT, f"stats_{name}.npz"), counts=x.astype(np.uint16), x_init=x0.astype(np.uint8),
+                        t_max=t_max, num_t=T, num_opinions=M, **extra)
+    print(name, x.shape, "mean at t_max:", x[:, -1].mean(0))
+
+
+# CNVM on a network, alpha = 1 (uniform agent choice)
+g = patch(nx.fast_gnp_random_graph(500, 10 / 499, seed=1))
+nl = calculate_neighbor_list(g)
+rp, col = csr(nl)
+x0 = np.random.default_rng(0).integers(0, 3, 500)
+run("cnvm_er500", CNVMParameters(num_opinions=3, network=nl, r=R3, r_tilde=RT3), 3, x0, 5.0, 6,
+    dict(model="cnvm", row_ptr=rp, col=col, r=R3, r_tilde=RT3, alpha=1.0))
+
+# CNVM on a heterogeneous network with alpha = 0 (alias tables)
+g = nx.barabasi_albert_graph(400, 3, seed=2)
+nl = calculate_neighbor_list(g)
+rp, col = csr(nl)
+x0 = np.random.default_rng(1).integers(0, 3, 400)
+run("cnvm_ba400_alpha0", CNVMParameters(num_opinions=3, network=nl, r=R3, r_tilde=RT3, alpha=0.0), 3, x0, 2.0, 5,
+    dict(model="cnvm", row_ptr=rp, col=col, r=R3, r_tilde=RT3, alpha=0.0))
+
+# CNVM complete graph (BASELINE config 1 rates, smaller N)
+x0 = np.random.default_rng(2).integers(0, 2, 300)
+r2, rt2 = np.array([[0, 1.0], [1.0, 0]]), np.array([[0, 0.01], [0.01, 0]])
+run("cnvm_complete300", CNVMParameters(num_opinions=2, num_agents=300, r=1.0, r_tilde=0.01), 2, x0, 20.0, 5,
+    dict(model="cnvm_complete", r=r2, r_tilde=rt2, alpha=1.0))
+
+# CNTM
+g = nx.fast_gnp_random_graph(400, 8 / 399, seed=3)
+nl = calculate_neighbor_list(g)
+rp, col = csr(nl)
+x0 = np.random.default_rng(3).integers(0, 2, 400)
+run("cntm_er400", CNTMParameters(network=g, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5), 2, x0, 10.0, 6,
+    dict(model="cntm", row_ptr=rp, col=col, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5))

@@ -1,0 +1,50 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sponet_b200.h declares; run calls fail
+loudly without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sponet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sponet_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sponet_b200 import _lib
+
+    L = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(L, name), f"libsponet_b200.so does not export {name}"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert L.sponet_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    from sponet_b200 import CNVM, CNVMParameters, _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert _lib.device_count() == 0
+    p = CNVMParameters(num_opinions=2, num_agents=20, r=1, r_tilde=0.1)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        CNVM(p).simulate(1.0, np.zeros(20, dtype=np.uint8), 3)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under sponet_b200/ may import, link or call it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sponet_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "libsponet_oracle" not in text and "sponet_oracle.c" not in text, f

@@ -1,0 +1,231 @@
+"""GPU: API-level behaviour mirroring the reference's own tests (shapes, dtypes, determinism,
+absorbing states, CV known answers) -- tests/tests_cnvm/test_cnvm_simulate.py,
+tests/tests_cntm/test_cntm_simulate.py, tests/test_multiprocessing.py, tests/test_sample_moments.py,
+tests/test_steady_state.py, tests/tests_collective_variables/*.py of the reference."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+R3 = np.array([[0, 1, 2], [1, 0, 1], [2, 0, 0]], dtype=float)
+RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
+
+
+def _networks():
+    import networkx as nx
+
+    return [None, nx.barabasi_albert_graph(100, 2, seed=1), nx.cycle_graph(100)]
+
+
+@pytest.mark.parametrize("mode", ["native", "replay"])
+@pytest.mark.parametrize("net_id", [0, 1, 2])
+def test_cnvm_simulate_contract(mode, net_id):
+    from sponet_b200 import CNVM, CNVMParameters
+
+    net = _networks()[net_id]
+    params = CNVMParameters(num_opinions=3, num_agents=100, network=net, r=R3, r_tilde=RT3)
+    model = CNVM(params)
+    x0 = np.random.default_rng(0).integers(0, 3, 100)
+    t, x = model.simulate(10.0, x0, 11, rng=np.random.default_rng(1), mode=mode)
+    assert t.shape == (11,) and x.shape == (11, 100) and x.dtype == np.uint8
+    assert t[0] == 0 and 9.9 < t[-1] < 10.1 and np.allclose(t, np.linspace(0, 10, 11), atol=0.01)
+    assert (x[0] == x0).all() and set(np.unique(x)) <= {0, 1, 2}
+    t2, x2 = model.simulate(10.0, x0, 11, rng=np.random.default_rng(1), mode=mode)  # same seed -> same result
+    assert (t == t2).all() and (x == x2).all()
+    t3, x3 = model.simulate(10.0, x0, [1.0, 2.5, 7.0], rng=np.random.default_rng(2), mode=mode)
+    assert t3.shape == (3,) and x3.shape == (3, 100) and np.allclose(t3, [1.0, 2.5, 7.0], atol=0.01)
+    tr, xr = model.simulate(5.0, None, 3, rng=np.random.default_rng(3), mode=mode)  # random initial state
+    assert xr.shape == (3, 100)
+
+
+def test_store_all_is_concise_and_fine_grid_has_duplicates():
+    from sponet_b200 import CNVM, CNVMParameters
+    from sponet_b200.utils import mask_subsequent_duplicates
+
+    params = CNVMParameters(num_opinions=3, num_agents=100, r=R3, r_tilde=RT3)
+    model = CNVM(params)
+    x0 = np.random.default_rng(0).integers(0, 3, 100)
+    t, x = model.simulate(1.0, x0, rng=np.random.default_rng(1))
+    assert t[0] == 0 and x.shape == (t.shape[0], 100) and (np.diff(t) > 0).all()
+    assert mask_subsequent_duplicates(x).all()  # every stored snapshot differs from its predecessor
+    t, x = model.simulate(0.01, x0, 2001, rng=np.random.default_rng(1))  # grid finer than the event spacing
+    assert not mask_subsequent_duplicates(x).all()
+
+
+@pytest.mark.parametrize("M,dtype", [(2, np.uint8), (10, np.uint8), (257, np.uint16)])
+def test_output_dtype(M, dtype):
+    from sponet_b200 import CNVM, CNVMParameters, sample_many_runs
+
+    params = CNVMParameters(num_opinions=M, num_agents=50, r=1, r_tilde=0.1)
+    t, x = CNVM(params).simulate(1.0, None, 3, rng=np.random.default_rng(0))
+    assert x.dtype == dtype and x.max() < M
+    x0 = np.random.default_rng(1).integers(0, M, 50)
+    _, xs = sample_many_runs(params, x0, 1.0, 3, 2, rng=np.random.default_rng(2))
+    assert xs.dtype == dtype and xs.shape == (2, 3, 50)
+
+
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_absorbing_state(mode):
+    """r = [[0,1],[0,0]], r_tilde = 0: opinion 0 dies out and the all-1 state is kept."""
+    from sponet_b200 import CNVM, CNVMParameters
+
+    params = CNVMParameters(num_opinions=2, num_agents=50, r=np.array([[0, 1], [0, 0]]), r_tilde=0)
+    x0 = np.array([0] * 25 + [1] * 25)
+    t, x = CNVM(params).simulate(200.0, x0, 21, rng=np.random.default_rng(5), mode=mode)
+    assert (x[-1] == 1).all()
+    first = int(np.argmax((x == 1).all(axis=1)))
+    assert (x[first:] == 1).all()
+
+
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_cntm_simulate_contract(mode):
+    import networkx as nx
+
+    from sponet_b200 import CNTM, CNTMParameters
+
+    g = nx.erdos_renyi_graph(100, 0.1, seed=123)
+    model = CNTM(CNTMParameters(g, 1, 0.2, 0.5, 0.5))
+    x0 = np.random.default_rng(0).integers(0, 2, 100)
+    t, x = model.simulate(10.0, x0, 11, rng=np.random.default_rng(1), mode=mode)
+    assert t.shape == (11,) and x.shape == (11, 100) and x.dtype == np.uint8 and (x[0] == x0).all()
+    assert np.allclose(t, np.linspace(0, 10, 11), atol=0.05)
+    t2, x2 = model.simulate(10.0, x0, 11, rng=np.random.default_rng(1), mode=mode)
+    assert (x == x2).all() and (t == t2).all()
+    # thresholds 0 / 1 and no noise: every evaluated node with >= 0 share of ones flips to 1 and stays
+    model = CNTM(CNTMParameters(nx.complete_graph(30), 1, 0.0, 0.0, 1.1))
+    t, x = model.simulate(50.0, np.zeros(30, dtype=int), 6, rng=np.random.default_rng(2), mode=mode)
+    assert (x[-1] == 1).all()
+    ta, xa = model.simulate(2.0, np.zeros(30, dtype=int), rng=np.random.default_rng(3))  # store-all
+    assert xa.shape[1] == 30 and (np.diff(xa.sum(1)) == 1).all()
+
+
+def test_sample_many_runs_shapes_and_determinism():
+    import networkx as nx
+
+    from sponet_b200 import CNTMParameters, CNVMParameters, OpinionShares, sample_many_runs
+
+    params = CNVMParameters(num_opinions=3, network=nx.barabasi_albert_graph(100, 2, seed=1), r=R3, r_tilde=RT3)
+    states = np.random.default_rng(0).integers(0, 3, (4, 100))
+    t, x = sample_many_runs(params, states, 2.0, 5, 6, rng=np.random.default_rng(1))
+    assert t.shape == (5,) and x.shape == (4, 6, 5, 100) and x.dtype == np.uint8
+    assert (x[:, :, 0] == states[:, None, :]).all()
+    t, x1 = sample_many_runs(params, states[0], 2.0, 5, 6, n_jobs=2, rng=np.random.default_rng(1))
+    assert x1.shape == (6, 5, 100)  # 1-D initial state drops the leading axis
+    cv = OpinionShares(3, normalize=True, idx_to_return=[0, 2])
+    t, c = sample_many_runs(params, states, 2.0, [0.5, 1.0, 2.0], 6, collective_variable=cv, rng=np.random.default_rng(1))
+    assert c.shape == (4, 6, 3, 2) and c.dtype == np.float64 and (c >= 0).all() and (c <= 1).all()
+    _, c2 = sample_many_runs(params, states, 2.0, [0.5, 1.0, 2.0], 6, n_jobs=-1, collective_variable=cv,
+                             rng=np.random.default_rng(1))
+    assert (c == c2).all()  # native mode: same seed -> same output, whatever n_jobs says
+    # in-kernel CV == CV evaluated on the stored states of the same chains
+    _, xs = sample_many_runs(params, states, 2.0, [0.5, 1.0, 2.0], 6, rng=np.random.default_rng(1))
+    np.testing.assert_array_equal(cv(xs.reshape(-1, 100)).reshape(c.shape), c)
+    with pytest.raises(ValueError, match="Parameters not valid"):
+        sample_many_runs(object(), states, 1.0, 2, 1)
+    p2 = CNTMParameters(nx.erdos_renyi_graph(100, 0.1, seed=3), 1, 0.2, 0.5, 0.5)
+    _, xt = sample_many_runs(p2, states[:2] % 2, 2.0, 4, 3, collective_variable=OpinionShares(2), rng=np.random.default_rng(2))
+    assert xt.shape == (2, 3, 4, 2) and (xt.sum(-1) == 100).all()
+
+
+def test_complete_graph_count_only_path_agrees_with_agent_level_statistics():
+    from sponet_b200 import CNVM, CNVMParameters, OpinionShares, engine, sample_many_runs
+
+    params = CNVMParameters(num_opinions=3, num_agents=300, r=R3, r_tilde=RT3)
+    x0 = np.random.default_rng(0).integers(0, 3, 300)
+    _, c = sample_many_runs(params, x0, 3.0, 4, 20000, collective_variable=OpinionShares(3), rng=np.random.default_rng(1))
+    model = CNVM(params)
+    struct, keep = model._struct()
+    _, a = engine.run_native("cnvm", None, 300, struct, x0[None].astype(np.uint8), np.linspace(0, 3, 4), 99, 20000, 0,
+                             20000, cv_spec=(np.arange(3, dtype=np.int32), 1.0), want_cv=True)
+    a = a[0]
+    z = np.abs(c.mean(0) - a.mean(0))[1:] / np.sqrt(c.var(0)[1:] / 20000 + a.var(0)[1:] / 20000)
+    assert z.max() < 4.75
+
+
+def test_generic_cv_paths():
+    import networkx as nx
+
+    from sponet_b200 import (CNVMParameters, CompositeCollectiveVariable, DegreeWeightedOpinionShares, OpinionShares,
+                             OpinionSharesByDegree, sample_many_runs)
+
+    g = nx.barabasi_albert_graph(100, 2, seed=1)
+    params = CNVMParameters(num_opinions=3, network=g, r=R3, r_tilde=RT3)
+    x0 = np.random.default_rng(0).integers(0, 3, 100)
+    w = np.random.default_rng(1).random(100)
+    cvs = [OpinionShares(3, weights=w), DegreeWeightedOpinionShares(3, g, normalize=True), OpinionSharesByDegree(3, g),
+           CompositeCollectiveVariable([OpinionShares(3), OpinionShares(3, True, w, 1)])]
+    _, xs = sample_many_runs(params, x0, 1.0, 3, 4, rng=np.random.default_rng(5))
+    for cv in cvs:
+        _, c = sample_many_runs(params, x0, 1.0, 3, 4, collective_variable=cv, rng=np.random.default_rng(5))
+        assert c.shape == (4, 3, cv.dimension)
+        np.testing.assert_allclose(c, cv(xs.reshape(-1, 100)).reshape(c.shape), rtol=1e-13, atol=0)
+
+    class HostOnlyCV:  # a user-defined CV that only understands numpy
+        dimension = 1
+
+        def __call__(self, x):
+            return np.asarray(x, dtype=float).sum(axis=-1, keepdims=True)
+
+    _, c = sample_many_runs(params, x0, 1.0, 3, 4, collective_variable=HostOnlyCV(), rng=np.random.default_rng(5))
+    np.testing.assert_array_equal(c[..., 0], xs.sum(-1))
+
+
+def test_collective_variables_known_answers():
+    """Values produced by the reference's own classes (fixture cv_known_answers)."""
+    import networkx as nx
+
+    from sponet_b200 import DegreeWeightedOpinionShares, OpinionShares, OpinionSharesByDegree
+
+    g = load_golden("cv_known_answers")
+    x, w = g["x"], g["weights"]
+    net = nx.Graph()
+    net.add_nodes_from(range(100))
+    net.add_edges_from((i, int(j)) for i in range(100) for j in g["col"][g["row_ptr"][i]:g["row_ptr"][i + 1]] if i < j)
+    assert [d for _, d in net.degree()] == g["degrees"].tolist()
+    np.testing.assert_array_equal(OpinionShares(3)(x), g["shares"])
+    np.testing.assert_array_equal(OpinionShares(3, normalize=True)(x), g["shares_norm"])
+    # float weights: fixed-tree summation on the GPU vs sequential bincount -> 1e-13 relative
+    np.testing.assert_allclose(OpinionShares(3, weights=w)(x), g["shares_w"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(OpinionShares(3, True, w, [2, 0])(x), g["shares_w_norm"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_array_equal(DegreeWeightedOpinionShares(3, net)(x), g["shares_deg"])  # integer weights: exact
+    np.testing.assert_array_equal(DegreeWeightedOpinionShares(3, net, True, 1)(x), g["shares_deg_norm"])
+    np.testing.assert_array_equal(OpinionSharesByDegree(3, net)(x), g["by_degree"])
+    np.testing.assert_array_equal(OpinionSharesByDegree(3, net, True, [0, 2])(x), g["by_degree_norm"])
+    np.testing.assert_array_equal(OpinionShares(3)(x[0]), g["shares"][0])  # 1-D input -> 1-D output
+    # the reference's hand-written cases (tests_collective_variables/test_opinion_shares.py)
+    xs = np.array([[0, 1, 0, 1, 2, 2, 0, 0, 1, 0], [1, 1, 1, 1, 1, 1, 1, 1, 1, 1]])
+    np.testing.assert_array_equal(OpinionShares(3)(xs), [[5, 3, 2], [0, 10, 0]])
+    np.testing.assert_array_equal(OpinionShares(3, idx_to_return=0)(xs), [[5], [0]])
+    star = nx.star_graph(9)  # centre has degree 9
+    np.testing.assert_array_equal(DegreeWeightedOpinionShares(3, star)(xs[0]), [9 + 4, 3, 2])
+
+
+def test_sample_moments_and_steady_state():
+    import time
+
+    import networkx as nx
+
+    from sponet_b200 import CNVMParameters, OpinionShares, estimate_steady_state, sample_many_runs, sample_moments
+
+    params = CNVMParameters(num_opinions=3, network=nx.barabasi_albert_graph(100, 2, seed=1), r=R3, r_tilde=RT3)
+    x0 = np.random.default_rng(0).integers(0, 3, 100)
+    cv = OpinionShares(3, normalize=True)
+    t, mean, var, n = sample_moments(params, x0, 2.0, 5, 500, rel_tol=0.05, collective_variable=cv, rng=np.random.default_rng(1))
+    assert t.shape == (5,) and mean.shape == (5, 3) and var.shape == (5, 3) and n % 500 == 0
+    np.testing.assert_allclose(mean[0], np.bincount(x0, minlength=3) / 100)
+    np.testing.assert_allclose(mean.sum(1), 1.0)
+    # fused integer moments == moments of the per-run values of the same chains (same seed)
+    _, c = sample_many_runs(params, x0, 2.0, 5, 500, collective_variable=cv, rng=np.random.default_rng(7))
+    _, m1, v1, n1 = sample_moments(params, x0, 2.0, 5, 500, rel_tol=1e9, collective_variable=cv, rng=np.random.default_rng(7))
+    assert n1 == 500
+    np.testing.assert_allclose(m1, c.mean(0), rtol=1e-12)
+    np.testing.assert_allclose(v1, c.var(0), rtol=1e-9, atol=1e-15)
+    # no CV: moments of the agent states; timeout honoured
+    start = time.time()
+    t, mean, var, n = sample_moments(params, x0, 1.0, 3, 50, rel_tol=1e-9, timeout_seconds=2, rng=np.random.default_rng(2))
+    assert time.time() - start < 20 and mean.shape == (3, 100)
+    p2 = CNVMParameters(num_opinions=2, num_agents=100, r=1, r_tilde=0.2)
+    est = estimate_steady_state(p2, OpinionShares(2, normalize=True), tol_abs=0.05, rng=np.random.default_rng(3), verbose=False)
+    assert est.shape == (2,) and abs(est.sum() - 1) < 1e-12 and abs(est[0] - 0.5) < 0.2

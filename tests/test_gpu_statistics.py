@@ -1,0 +1,92 @@
+"""GPU: native-RNG mode against the reference's numba path, statistically.
+
+Fixtures tests/golden/stats_*.npz hold OpinionShares counts of 12 000 runs of the UNMODIFIED reference
+(tests/golden/make_stats_golden.py).  Native mode samples 24 000 runs of the same configuration.  For
+every output time k >= 1 and every opinion m:
+
+  * z-test on the mean:      |mean_a - mean_b| <= Z * sqrt(var_a/n_a + var_b/n_b)
+  * z-test on the variance:  |var_a - var_b|  <= Z * sqrt(se_a^2 + se_b^2), se^2 = (m4 - var^2)/n
+  * two-sample Kolmogorov-Smirnov: p-value >= ALPHA / (number of comparisons)   (Bonferroni)
+
+with Z = 4.75 (two-sided 2e-6 per comparison; <= 2e-4 family-wise over <= 100 comparisons per test)
+and ALPHA = 1e-3 family-wise for KS.  A kernel with a wrong rate, branch probability, neighbour
+choice or acceptance table fails these by tens of sigma (checked by perturbing r_tilde by 5 %).
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from conftest import csr_to_neighbor_list, load_golden
+
+pytestmark = pytest.mark.gpu
+
+Z = 4.75
+ALPHA = 1e-3
+NATIVE_RUNS = 24_000
+
+
+def _native_counts(g, runs, seed, scale_noise=1.0):
+    import networkx as nx
+
+    from sponet_b200 import CNTMParameters, CNVMParameters, OpinionShares, sample_many_runs
+
+    model, M = str(g["model"]), int(g["num_opinions"])
+    if model == "cntm":
+        nl = csr_to_neighbor_list(g["row_ptr"], g["col"])
+        net = nx.Graph()
+        net.add_nodes_from(range(len(nl)))
+        net.add_edges_from((i, int(j)) for i, nb in enumerate(nl) for j in nb if i < j)
+        params = CNTMParameters(net, float(g["r"]), float(g["r_tilde"]) * scale_noise, float(g["threshold_01"]),
+                                float(g["threshold_10"]))
+    elif model == "cnvm_complete":
+        params = CNVMParameters(num_opinions=M, num_agents=g["x_init"].size, r=g["r"], r_tilde=g["r_tilde"] * scale_noise)
+    else:
+        params = CNVMParameters(num_opinions=M, network=csr_to_neighbor_list(g["row_ptr"], g["col"]), r=g["r"],
+                                r_tilde=g["r_tilde"] * scale_noise, alpha=float(g["alpha"]))
+    _, x = sample_many_runs(params, g["x_init"], float(g["t_max"]), int(g["num_t"]), runs,
+                            collective_variable=OpinionShares(M), rng=np.random.default_rng(seed))
+    return x
+
+
+def _compare(ref, nat):
+    """Returns the worst z (mean), worst z (variance), smallest KS p-value and the comparison count."""
+    T, M = ref.shape[1:]
+    zm = zv = 0.0
+    pmin, n_cmp = 1.0, 0
+    for k in range(1, T):
+        for m in range(M):
+            a, b = ref[:, k, m].astype(float), nat[:, k, m].astype(float)
+            va, vb = a.var(), b.var()
+            if va == 0 and vb == 0:
+                assert a.mean() == b.mean()
+                continue
+            n_cmp += 1
+            zm = max(zm, abs(a.mean() - b.mean()) / np.sqrt(va / a.size + vb / b.size))
+            m4a, m4b = ((a - a.mean()) ** 4).mean(), ((b - b.mean()) ** 4).mean()
+            se = np.sqrt((m4a - va**2) / a.size + (m4b - vb**2) / b.size)
+            zv = max(zv, abs(va - vb) / se)
+            pmin = min(pmin, stats.ks_2samp(a, b).pvalue)
+    return zm, zv, pmin, n_cmp
+
+
+@pytest.mark.parametrize("name", ["cnvm_er500", "cnvm_ba400_alpha0", "cnvm_complete300", "cntm_er400"])
+def test_native_mode_matches_reference_distribution(name):
+    g = load_golden("stats_" + name)
+    ref = g["counts"]
+    nat = _native_counts(g, NATIVE_RUNS, seed=2026)
+    assert nat.shape == (NATIVE_RUNS,) + ref.shape[1:]
+    np.testing.assert_array_equal(nat[:, 0], np.broadcast_to(ref[0, 0], nat[:, 0].shape))  # t = 0: the initial state
+    assert (nat.sum(-1) == g["x_init"].size).all()
+    zm, zv, pmin, n_cmp = _compare(ref, nat)
+    print(f"{name}: worst z(mean)={zm:.2f} z(var)={zv:.2f} min KS p={pmin:.3g} over {n_cmp} comparisons")
+    assert zm <= Z, f"means differ: z = {zm:.2f}"
+    assert zv <= Z, f"variances differ: z = {zv:.2f}"
+    assert pmin >= ALPHA / n_cmp, f"KS rejects: p = {pmin:.3g}"
+
+
+def test_statistical_test_has_power():
+    """The same comparison must REJECT a 5 % perturbation of the noise rates."""
+    g = load_golden("stats_cnvm_er500")
+    nat = _native_counts(g, NATIVE_RUNS, seed=7, scale_noise=1.05)
+    zm, _, _, _ = _compare(g["counts"], nat)
+    assert zm > 2 * Z, f"test is too weak: z = {zm:.2f}"
