@@ -26,8 +26,7 @@ struct NativeCnvmArgs {
     const int2* row;  // (begin, degree); nullptr = complete graph
     const int32_t* col;
     uint32_t noise_thr;
-    const uint32_t* alias_thr;  // nullptr = uniform agent weights
-    const int32_t* alias;
+    const uint2* alias_tab;  // (threshold, alias) per agent; nullptr = uniform agent weights
     const uint32_t* thr;  // [2*M*M]: imitation thresholds, then noise thresholds
     const uint8_t* x_init;
     const int64_t* counts;  // [S*nrun, T-1]
@@ -45,6 +44,7 @@ struct NativeCnvmArgs {
     uint32_t* gstate;  // global chain states (fallback), [total_warps, words]
     int32_t words;     // 32-bit words per chain
     int32_t warps_per_cta;
+    int32_t bloom_log2;  // log2 of the per-warp Bloom filter size in bits (0 = disabled)
 };
 
 template <int BITS>
@@ -63,19 +63,41 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 
 // ---------------------------------------------------------------------------------------------
 // agent-level kernel
+//
+// Per warp step (32 consecutive candidate events of one chain) the work is split into
+//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued
+//   stage 2  neighbour slot from the row; column gather issued
+//   stage 3  dependency mask: which EARLIER lanes touch an agent this lane reads.  Agents and
+//            neighbours never depend on the chain state, so this is computed before the commit:
+//            match.any on the agents + a per-warp Bloom filter (shared memory) on the neighbours
+//            prove "no overlap" for most steps; only when the filter fires the exact all-pairs
+//            shuffle comparison runs
+//   commit   read x[a], x[nbr]; accept; hazard = dep & ballot(accepting lanes); lanes before the
+//            first hazard write (atomicXor on the packed word), the rest re-evaluate
+// Stages 1 and 2 of the NEXT steps are issued before the commit of the current one (software
+// pipeline, depth 2), so both L2 gathers are in flight while a step commits.
 // ---------------------------------------------------------------------------------------------
+struct StepDesc {
+    uint64_t e0;  // index of the step's first event within the chain
+    int nb;       // number of events in the step (lanes >= nb are idle)
+    int snaps;    // output snapshots completed by this step
+};
+
 template <int BITS, bool SMEM, bool CSR>
 __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
-    constexpr bool REGCNT = (BITS <= 2);   // M <= 4: opinion counts live in registers
-    constexpr bool THR_SMEM = (BITS <= 4); // M <= 16: threshold tables staged in shared memory
+    constexpr bool REGCNT = (BITS <= 2);    // M <= 4: opinion counts live in registers
+    constexpr bool THR_SMEM = (BITS <= 4);  // M <= 16: threshold tables staged in shared memory
+    constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int M = A.M, MM = M * M;
     const uint32_t n = (uint32_t)A.n;
+    const uint32_t noise_thr = A.noise_thr;
+    const uint32_t lane_lt = (1u << lane) - 1u;
 
-    // shared layout: [thr 2*MM (if THR_SMEM)] [counts W*M (if !REGCNT)] [states W*words (if SMEM)]
+    // shared layout: [thr 2*MM (if THR_SMEM)] [counts W*M (if !REGCNT)] [bloom W*BW] [states W*words (if SMEM)]
     uint32_t* sp = smem;
     const uint32_t* thr = A.thr;
     if (THR_SMEM) {
@@ -87,6 +109,12 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     if (!REGCNT) {
         cnt_mem = (int32_t*)sp + warp * M;
         sp += A.warps_per_cta * M;
+    }
+    const int bloom_log2 = A.bloom_log2;  // log2(bits per warp); 0 = no filter (always exact)
+    uint32_t* bloom = sp + (size_t)warp * (bloom_log2 ? (1u << (bloom_log2 - 5)) : 0u);
+    if (bloom_log2) {
+        for (int i = threadIdx.x; i < (A.warps_per_cta << (bloom_log2 - 5)); i += blockDim.x) sp[i] = 0u;
+        sp += (size_t)A.warps_per_cta << (bloom_log2 - 5);
     }
     uint32_t* state;
     if (SMEM) state = sp + (size_t)warp * A.words;
@@ -102,6 +130,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint8_t* x0 = A.x_init + j * (int64_t)n;
+        const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
 
         // ---- load + pack the initial state, count opinions ----
         int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -131,92 +160,41 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             state[w] = packed;
         }
         if (REGCNT) {
-            c0 = __reduce_add_sync(0xffffffffu, c0);
-            c1 = __reduce_add_sync(0xffffffffu, c1);
-            c2 = __reduce_add_sync(0xffffffffu, c2);
-            c3 = __reduce_add_sync(0xffffffffu, c3);
+            c0 = __reduce_add_sync(FULL, c0);
+            c1 = __reduce_add_sync(FULL, c1);
+            c2 = __reduce_add_sync(FULL, c2);
+            c3 = __reduce_add_sync(FULL, c3);
         }
         if (!SMEM) __threadfence_block();
         __syncwarp();
 
-        uint64_t e_base = 0;
-        for (int k = 0; k < T; ++k) {
-            if (k > 0) {
-                int64_t K = A.counts[cl * (int64_t)(T - 1) + (k - 1)];
-                while (K > 0) {
-                    const int nb = K < 32 ? (int)K : 32;
-                    const uint4 r = sp_native_draw(A.seed, chain, 0u, e_base + (uint64_t)lane);
-                    const bool noise = r.x < A.noise_thr;
-                    const uint32_t idx = __umulhi(r.y, n);
-                    uint32_t a = idx, nbr = idx;
-                    const uint32_t nw_noise = __umulhi(r.z, (uint32_t)M);
-                    if (!noise) {
-                        if (A.alias_thr) {
-                            const uint32_t at = __ldg(A.alias_thr + idx);
-                            if (!sp_thr_accept(r.y * n, at)) a = (uint32_t)__ldg(A.alias + idx);
-                        }
-                        if (CSR) {
-                            const int2 rw = __ldg(A.row + a);
-                            nbr = (uint32_t)__ldg(A.col + rw.x + __umulhi(r.z, (uint32_t)rw.y));
-                        } else {
-                            nbr = __umulhi(r.z, n - 1);
-                            nbr += (nbr >= a);
-                        }
-                    }
-                    const uint32_t wa = P::word(a), sa = P::shift(a);
-                    const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
-                    const uint32_t tbase = noise ? (uint32_t)MM : 0u;
-
-                    bool pending = lane < nb;
-                    int rounds = 0;
-                    for (;;) {
-                        const uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
-                        const uint32_t nw = noise ? nw_noise : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                        const uint32_t th = THR_SMEM ? thr[tbase + m * M + nw] : __ldg(thr + tbase + m * M + nw);
-                        const bool acc = pending && sp_thr_accept(r.w, th);
-                        const uint32_t wmask = __ballot_sync(0xffffffffu, acc);
-                        // hazard: an earlier lane that writes an agent this lane reads
-                        bool hz = false;
-                        for (uint32_t mm = wmask; mm; mm &= mm - 1) {
-                            const int jl = __ffs(mm) - 1;
-                            const uint32_t aj = __shfl_sync(0xffffffffu, a, jl);
-                            hz |= (jl < lane) & ((aj == a) | (aj == nbr));
-                        }
-                        const uint32_t hmask = __ballot_sync(0xffffffffu, hz && pending);
-                        const int first = hmask ? (__ffs(hmask) - 1) : 32;
-                        const bool commit = acc && lane < first;
-                        if (commit) atomicXor(state + wa, (m ^ nw) << sa);
-                        const uint32_t cmask = __ballot_sync(0xffffffffu, commit);
-                        acc_total += __popc(cmask);
-                        if (REGCNT) {
-                            c0 += __popc(__ballot_sync(0xffffffffu, commit && nw == 0)) -
-                                  __popc(__ballot_sync(0xffffffffu, commit && m == 0));
-                            c1 += __popc(__ballot_sync(0xffffffffu, commit && nw == 1)) -
-                                  __popc(__ballot_sync(0xffffffffu, commit && m == 1));
-                            if (BITS == 2) {
-                                c2 += __popc(__ballot_sync(0xffffffffu, commit && nw == 2)) -
-                                      __popc(__ballot_sync(0xffffffffu, commit && m == 2));
-                                c3 += __popc(__ballot_sync(0xffffffffu, commit && nw == 3)) -
-                                      __popc(__ballot_sync(0xffffffffu, commit && m == 3));
-                            }
-                        } else if (commit) {
-                            atomicAdd(&cnt_mem[m], -1);
-                            atomicAdd(&cnt_mem[nw], 1);
-                        }
-                        pending = pending && lane >= first;
-                        if (!SMEM) __threadfence_block();
-                        __syncwarp();
-                        if (first == 32) break;
-                        ++rounds;
-                    }
-                    extra_rounds += rounds;
-                    ++step_total;
-                    ev_total += nb;
-                    e_base += nb;
-                    K -= nb;
-                }
+        // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into
+        // c0..c3 before any field can leave [-127, 127].
+        uint32_t dpack = 0;
+        int dsteps = 0;
+        auto fold_counts = [&]() {
+            if (REGCNT) {
+                uint32_t t = dpack;
+                const int d0 = (int)(int8_t)(t & 0xFF);
+                t = (uint32_t)(((int)t - d0) >> 8);
+                const int d1 = (int)(int8_t)(t & 0xFF);
+                t = (uint32_t)(((int)t - d1) >> 8);
+                const int d2 = (int)(int8_t)(t & 0xFF);
+                t = (uint32_t)(((int)t - d2) >> 8);
+                const int d3 = (int)(int8_t)(t & 0xFF);
+                c0 += __reduce_add_sync(FULL, d0);
+                c1 += __reduce_add_sync(FULL, d1);
+                c2 += __reduce_add_sync(FULL, d2);
+                c3 += __reduce_add_sync(FULL, d3);
+                dpack = 0;
+                dsteps = 0;
             }
-            // ---- snapshot k ----
+        };
+
+        int ksnap = 0;
+        auto snapshot = [&]() {
+            fold_counts();
+            const int k = ksnap++;
             const int64_t snap = cl * (int64_t)T + k;
             if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
@@ -238,6 +216,166 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 for (uint32_t a = lane; a < n; a += 32)
                     dst[a] = (uint8_t)((state_load<SMEM>(state + P::word(a)) >> P::shift(a)) & P::VM);
             }
+        };
+
+        // ---- step generator: walks the per-interval event counts, two steps ahead of the commit ----
+        int gk = 1;
+        int64_t gK = 0;
+        uint64_t ge = 0;
+        bool gdone = (T <= 1);
+        snapshot();  // k = 0: the initial state
+        if (!gdone) {
+            gK = kcounts[0];
+            while (gK == 0) {  // leading empty intervals repeat the initial state
+                snapshot();
+                if (++gk >= T) { gdone = true; break; }
+                gK = kcounts[gk - 1];
+            }
+        }
+        auto gen = [&](StepDesc& d) -> bool {
+            d.e0 = ge;
+            d.snaps = 0;
+            if (gdone) { d.nb = 0; return false; }
+            d.nb = gK < 32 ? (int)gK : 32;
+            ge += (uint64_t)d.nb;
+            gK -= d.nb;
+            if (gK == 0) {
+                d.snaps = 1;
+                for (;;) {
+                    if (++gk >= T) { gdone = true; break; }
+                    gK = kcounts[gk - 1];
+                    if (gK > 0) break;
+                    ++d.snaps;
+                }
+            }
+            return true;
+        };
+
+        // ---- pipeline registers ----
+        // stage 1 (row gather in flight)
+        uint32_t s1_a = 0, s1_r2 = 0, s1_r3 = 0, s1_meta = 0;
+        int2 s1_row = make_int2(0, 1);
+        // stage 2 (column gather in flight)
+        uint32_t s2_a = 0, s2_r3 = 0, s2_meta = 0, s2_nbr = 0;
+        StepDesc d1, d2;
+
+        auto issue1 = [&](const StepDesc& d) {
+            const uint4 r = sp_native_draw(A.seed, chain, 0u, d.e0 + (uint64_t)lane);
+            const bool noise = r.x < noise_thr;
+            const uint32_t idx = __umulhi(r.y, n);
+            uint32_t a = idx;
+            if (!noise && A.alias_tab) {  // sampling.py:117-122 with integer thresholds
+                const uint2 at = __ldg(A.alias_tab + idx);
+                if (!sp_thr_accept(r.y * n, at.x)) a = at.y;
+            }
+            s1_a = a;
+            s1_r2 = r.z;
+            s1_r3 = r.w;
+            s1_meta = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
+            if (CSR) s1_row = __ldg(A.row + a);
+        };
+        auto issue2 = [&]() {
+            s2_a = s1_a;
+            s2_r3 = s1_r3;
+            s2_meta = s1_meta;
+            uint32_t nbr = s1_a;
+            if (!(s1_meta & 1u)) {
+                if (CSR) {
+                    nbr = (uint32_t)__ldg(A.col + s1_row.x + __umulhi(s1_r2, (uint32_t)s1_row.y));
+                } else {
+                    nbr = __umulhi(s1_r2, n - 1);
+                    nbr += (nbr >= s1_a);
+                }
+            }
+            s2_nbr = nbr;
+        };
+
+        bool v1 = gen(d1);
+        if (v1) issue1(d1);
+        bool v2 = v1;
+        d2 = d1;
+        if (v2) issue2();
+        v1 = gen(d1);
+        if (v1) issue1(d1);
+
+        while (v2) {
+            // current step = stage 2 contents
+            const uint32_t a = s2_a, nbr = s2_nbr, r3 = s2_r3, meta = s2_meta;
+            const StepDesc dc = d2;
+            // advance the pipeline: next step's column gather, the one after's Philox + row gather
+            v2 = v1;
+            d2 = d1;
+            if (v2) issue2();
+            v1 = gen(d1);
+            if (v1) issue1(d1);
+
+            const bool noise = meta & 1u;
+            const uint32_t nw_noise = meta >> 8;
+            const int nb = dc.nb;
+
+            // ---- stage 3: dependency mask of this step ----
+            uint32_t dep = 0;
+            bool suspect;
+            {
+                if (bloom_log2) {
+                    const uint32_t ha = (a * 2654435761u) >> (32 - bloom_log2);
+                    atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
+                    const uint32_t same = __match_any_sync(FULL, a);
+                    __syncwarp();
+                    bool hit = same != (1u << lane);
+                    if (!noise) {
+                        const uint32_t hn = (nbr * 2654435761u) >> (32 - bloom_log2);
+                        hit |= (bloom[hn >> 5] >> (hn & 31)) & 1u;
+                    }
+                    suspect = __any_sync(FULL, hit);
+                    bloom[ha >> 5] = 0u;  // clear (same value from every lane sharing the word)
+                } else {
+                    suspect = true;
+                }
+                if (suspect) {
+#pragma unroll
+                    for (int jl = 0; jl < 32; ++jl) {
+                        const uint32_t aj = __shfl_sync(FULL, a, jl);
+                        dep |= (uint32_t)((aj == a) | (aj == nbr)) << jl;
+                    }
+                    dep &= lane_lt;
+                }
+            }
+
+            // ---- commit ----
+            const uint32_t wa = P::word(a), sa = P::shift(a);
+            const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
+            const uint32_t tbase = noise ? (uint32_t)MM : 0u;
+            bool pending = lane < nb;
+            for (;;) {
+                const uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
+                const uint32_t nw = noise ? nw_noise : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
+                const uint32_t th = THR_SMEM ? thr[tbase + m * M + nw] : __ldg(thr + tbase + m * M + nw);
+                const bool acc = pending && sp_thr_accept(r3, th);
+                const uint32_t wmask = __ballot_sync(FULL, acc);
+                const uint32_t hmask = suspect ? __ballot_sync(FULL, pending && (dep & wmask) != 0u) : 0u;
+                const int first = hmask ? (__ffs(hmask) - 1) : 32;
+                const bool commit = acc && lane < first;
+                if (commit) {
+                    atomicXor(state + wa, (m ^ nw) << sa);
+                    if (REGCNT) {
+                        dpack += (1u << (8 * nw)) - (1u << (8 * m));
+                    } else {
+                        atomicAdd(&cnt_mem[m], -1);
+                        atomicAdd(&cnt_mem[nw], 1);
+                    }
+                }
+                acc_total += __popc(hmask ? __ballot_sync(FULL, commit) : wmask);
+                pending = pending && lane >= first;
+                if (!SMEM) __threadfence_block();
+                __syncwarp();
+                if (first == 32) break;
+                ++extra_rounds;
+            }
+            ++step_total;
+            ev_total += nb;
+            if (REGCNT && ++dsteps >= 120) fold_counts();
+            for (int q = 0; q < dc.snaps; ++q) snapshot();
         }
         __syncwarp();
     }
@@ -579,18 +717,14 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         if (!uniform) {
             std::vector<double> prob(n);
             std::vector<int32_t> alias(n);
-            std::vector<uint32_t> athr(n);
+            std::vector<uint2> tab(n);
             SP_TRY(sponet_build_alias_table(p->degree_alpha, n, prob.data(), alias.data()));
-            for (int64_t i = 0; i < n; ++i) athr[i] = sp_prob_to_thr(prob[i]);
-            uint32_t* d_at;
-            int32_t* d_al;
-            SP_CUDA(sc.alloc((void**)&d_at, n * sizeof(uint32_t)));
-            SP_CUDA(sc.alloc((void**)&d_al, n * sizeof(int32_t)));
-            SP_CUDA(cudaMemcpyAsync(d_at, athr.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, sc.stream));
-            SP_CUDA(cudaMemcpyAsync(d_al, alias.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, sc.stream));
+            for (int64_t i = 0; i < n; ++i) tab[i] = make_uint2(sp_prob_to_thr(prob[i]), (uint32_t)alias[i]);
+            uint2* d_tab;
+            SP_CUDA(sc.alloc((void**)&d_tab, n * sizeof(uint2)));
+            SP_CUDA(cudaMemcpyAsync(d_tab, tab.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, sc.stream));
             SP_CUDA(cudaStreamSynchronize(sc.stream));
-            A.alias_thr = d_at;
-            A.alias = d_al;
+            A.alias_tab = d_tab;
         }
         A.row = g->d_row;
         A.col = g->d_col;
@@ -658,6 +792,21 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     } else {
         warps = 8;
         smem_bytes = fixed + cnt_bytes * warps;
+    }
+    // Per-warp Bloom filter for the dependency pre-check: the largest power of two (<= 64 Kbit) that the
+    // shared memory left over by the chain states can hold; below 1 Kbit it is not worth having.
+    {
+        const size_t spare = smem_max > smem_bytes + 64 ? (smem_max - smem_bytes - 64) / warps : 0;
+        int lg = 0;
+        while (lg < 16 && ((size_t)1 << (lg + 1)) / 8 <= spare) ++lg;
+        // no larger than ~N/4 bits (false-positive rate ~ 32*25/bits per step vs a true overlap rate of
+        // ~1000/N), so that small chains keep their occupancy; only spare bytes are used, a chain is
+        // never given up for a larger filter
+        int want = 10;
+        while (want < 16 && ((int64_t)1 << want) < n / 4) ++want;
+        lg = std::min(lg, want);
+        A.bloom_log2 = lg >= 10 ? lg : 0;
+        if (A.bloom_log2) smem_bytes += ((size_t)1 << A.bloom_log2) / 8 * warps;
     }
     A.warps_per_cta = warps;
     const int threads = warps * 32;
