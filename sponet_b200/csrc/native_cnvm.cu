@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
 
         // ---- pipeline registers ----
         // stage 1 (row gather in flight)
-        uint32_t s1_a = 0, s1_r2 = 0, s1_r3 = 0, s1_meta = 0;
+        uint32_t s1_a = 0, s1_r2 = 0, s1_r3 = 0, s1_meta = 0, s1_same = 0;
         int2 s1_row = make_int2(0, 1);
         // stage 2 (column gather in flight)
-        uint32_t s2_a = 0, s2_r3 = 0, s2_meta = 0, s2_nbr = 0;
+        uint32_t s2_a = 0, s2_r3 = 0, s2_meta = 0, s2_nbr = 0, s2_same = 0;
         StepDesc d1, d2;
 
         auto issue1 = [&](const StepDesc& d) {
@@ -271,6 +271,8 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             s1_a = a;
             s1_r2 = r.z;
             s1_r3 = r.w;
+            // MATCH.ANY is slow: it is issued here, two steps before its result is first looked at
+            s1_same = __match_any_sync(FULL, a);
             s1_meta = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
             if (CSR) s1_row = __ldg(A.row + a);
         };
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             s2_a = s1_a;
             s2_r3 = s1_r3;
             s2_meta = s1_meta;
+            s2_same = s1_same;
             uint32_t nbr = s1_a;
             if (!(s1_meta & 1u)) {
                 if (CSR) {
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
 
         while (v2) {
             // current step = stage 2 contents
-            const uint32_t a = s2_a, nbr = s2_nbr, r3 = s2_r3, meta = s2_meta;
+            const uint32_t a = s2_a, nbr = s2_nbr, r3 = s2_r3, meta = s2_meta, same = s2_same;
             const StepDesc dc = d2;
             // advance the pipeline: next step's column gather, the one after's Philox + row gather
             v2 = v1;
@@ -320,7 +323,6 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 if (bloom_log2) {
                     const uint32_t ha = (a * 2654435761u) >> (32 - bloom_log2);
                     atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
-                    const uint32_t same = __match_any_sync(FULL, a);
                     __syncwarp();
                     bool hit = same != (1u << lane);
                     if (!noise) {
