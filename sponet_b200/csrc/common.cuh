@@ -142,6 +142,22 @@ __device__ __forceinline__ uint4 sp_philox4x32_10(uint32_t c0, uint32_t c1, uint
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Same function with the ten round keys precomputed on the host (kernel-parameter constants: the key
+// schedule costs no instructions in the event loop).
+__device__ __forceinline__ uint4 sp_philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // counter = (e_lo, e_hi, chain_lo, chain_hi[24] | tag << 24), key = seed
 __device__ __forceinline__ uint4 sp_native_draw(uint64_t seed, uint64_t chain, uint32_t tag, uint64_t e) {
     return sp_philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)chain,

@@ -44,7 +44,8 @@ struct NativeCnvmArgs {
     uint32_t* gstate;  // global chain states (fallback), [total_warps, words]
     int32_t words;     // 32-bit words per chain
     int32_t warps_per_cta;
-    int32_t bloom_log2;  // log2 of the per-warp Bloom filter size in bits (0 = disabled)
+    int32_t bloom_words;  // per-warp Bloom filter size in 32-bit words (0 = disabled)
+    uint32_t rk[20];      // Philox4x32-10 round keys of the seed: (k0 + r*W0, k1 + r*W1), r = 0..9
 };
 
 template <int BITS>
@@ -65,25 +66,21 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // agent-level kernel
 //
 // Per warp step (32 consecutive candidate events of one chain) the work is split into
-//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued
+//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued;
+//            MATCH.ANY on the agents issued (slow instruction, result needed two steps later)
 //   stage 2  neighbour slot from the row; column gather issued
 //   stage 3  dependency mask: which EARLIER lanes touch an agent this lane reads.  Agents and
-//            neighbours never depend on the chain state, so this is computed before the commit:
-//            match.any on the agents + a per-warp Bloom filter (shared memory) on the neighbours
-//            prove "no overlap" for most steps; only when the filter fires the exact all-pairs
-//            shuffle comparison runs
+//            neighbours never depend on the chain state, so this is known before the commit:
+//            the MATCH result flags equal agents, a per-warp Bloom filter in shared memory flags
+//            neighbours that may equal another lane's agent; only flagged lanes (none in most
+//            steps) get an exact mask, built with two shuffles and a ballot per flagged lane
 //   commit   read x[a], x[nbr]; accept; hazard = dep & ballot(accepting lanes); lanes before the
 //            first hazard write (atomicXor on the packed word), the rest re-evaluate
-// Stages 1 and 2 of the NEXT steps are issued before the commit of the current one (software
-// pipeline, depth 2), so both L2 gathers are in flight while a step commits.
+// Stages 1 and 2 of the NEXT two steps are issued before the commit of the current one (software
+// pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies):
+// both L2 gathers and the MATCH are in flight while a step commits.
 // ---------------------------------------------------------------------------------------------
-struct StepDesc {
-    uint64_t e0;  // index of the step's first event within the chain
-    int nb;       // number of events in the step (lanes >= nb are idle)
-    int snaps;    // output snapshots completed by this step
-};
-
-template <int BITS, bool SMEM, bool CSR>
+template <int BITS, bool SMEM, bool CSR, bool ALIAS>
 __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
     constexpr bool REGCNT = (BITS <= 2);    // M <= 4: opinion counts live in registers
@@ -95,12 +92,20 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     const int M = A.M, MM = M * M;
     const uint32_t n = (uint32_t)A.n;
     const uint32_t noise_thr = A.noise_thr;
-    const uint32_t lane_lt = (1u << lane) - 1u;
+    const uint32_t lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
 
-    // shared layout: [thr 2*MM (if THR_SMEM)] [counts W*M (if !REGCNT)] [bloom W*BW] [states W*words (if SMEM)]
+    // shared layout: [thr] [counts W*M (if !REGCNT)] [bloom W*bloom_words] [states W*words (if SMEM)]
+    // thr: M <= 4 -> 32 entries indexed (noise << 4 | m << 2 | nw); M <= 16 -> 2*MM entries
     uint32_t* sp = smem;
     const uint32_t* thr = A.thr;
-    if (THR_SMEM) {
+    if (REGCNT) {
+        for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+            const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
+            sp[i] = (m < M && w < M) ? A.thr[nz * MM + m * M + w] : 0u;
+        }
+        thr = sp;
+        sp += 32;
+    } else if (THR_SMEM) {
         for (int i = threadIdx.x; i < 2 * MM; i += blockDim.x) sp[i] = A.thr[i];
         thr = sp;
         sp += 2 * MM;
@@ -110,12 +115,10 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         cnt_mem = (int32_t*)sp + warp * M;
         sp += A.warps_per_cta * M;
     }
-    const int bloom_log2 = A.bloom_log2;  // log2(bits per warp); 0 = no filter (always exact)
-    uint32_t* bloom = sp + (size_t)warp * (bloom_log2 ? (1u << (bloom_log2 - 5)) : 0u);
-    if (bloom_log2) {
-        for (int i = threadIdx.x; i < (A.warps_per_cta << (bloom_log2 - 5)); i += blockDim.x) sp[i] = 0u;
-        sp += (size_t)A.warps_per_cta << (bloom_log2 - 5);
-    }
+    const uint32_t bloom_bits = (uint32_t)A.bloom_words * 32u;  // per warp; 0 = no filter (all lanes flagged)
+    uint32_t* bloom = sp + (size_t)warp * A.bloom_words;
+    for (int i = threadIdx.x; i < A.warps_per_cta * A.bloom_words; i += blockDim.x) sp[i] = 0u;
+    sp += (size_t)A.warps_per_cta * A.bloom_words;
     uint32_t* state;
     if (SMEM) state = sp + (size_t)warp * A.words;
     else state = A.gstate + ((size_t)blockIdx.x * A.warps_per_cta + warp) * A.words;
@@ -123,12 +126,13 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
 
     const int64_t total_warps = (int64_t)gridDim.x * A.warps_per_cta;
     const int64_t num_chains = A.S * A.nrun;
-    unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_rounds = 0;
+    unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_total = 0;
     const int T = A.T;
 
     for (int64_t cl = (int64_t)blockIdx.x * A.warps_per_cta + warp; cl < num_chains; cl += total_warps) {
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
+        const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
         const uint8_t* x0 = A.x_init + j * (int64_t)n;
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
 
@@ -169,8 +173,8 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         __syncwarp();
 
         // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into
-        // c0..c3 before any field can leave [-127, 127].
-        uint32_t dpack = 0;
+        // c0..c3 before any field can leave [-127, 127]; 32-bit per-lane statistics folded with them.
+        uint32_t dpack = 0, my_acc = 0, n_steps = 0, n_events = 0, n_extra = 0;
         int dsteps = 0;
         auto fold_counts = [&]() {
             if (REGCNT) {
@@ -194,6 +198,11 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         int ksnap = 0;
         auto snapshot = [&]() {
             fold_counts();
+            acc_total += __reduce_add_sync(FULL, my_acc);
+            ev_total += n_events;
+            step_total += n_steps;
+            extra_total += n_extra;
+            my_acc = n_events = n_steps = n_extra = 0;
             const int k = ksnap++;
             const int64_t snap = cl * (int64_t)T + k;
             if (A.out_cv || A.out_sum) {
@@ -232,160 +241,189 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 gK = kcounts[gk - 1];
             }
         }
-        auto gen = [&](StepDesc& d) -> bool {
-            d.e0 = ge;
-            d.snaps = 0;
-            if (gdone) { d.nb = 0; return false; }
-            d.nb = gK < 32 ? (int)gK : 32;
-            ge += (uint64_t)d.nb;
-            gK -= d.nb;
+        // returns false when the chain has no further step; otherwise (e0, nb, snaps) of the next one
+        auto gen = [&](uint64_t& e0, int& nb, int& snaps) -> bool {
+            e0 = ge;
+            snaps = 0;
+            nb = 0;
+            if (gdone) return false;
+            nb = gK < 32 ? (int)gK : 32;
+            ge += (uint64_t)nb;
+            gK -= nb;
             if (gK == 0) {
-                d.snaps = 1;
+                snaps = 1;
                 for (;;) {
                     if (++gk >= T) { gdone = true; break; }
                     gK = kcounts[gk - 1];
                     if (gK > 0) break;
-                    ++d.snaps;
+                    ++snaps;
                 }
             }
             return true;
         };
 
-        // ---- pipeline registers ----
-        // stage 1 (row gather in flight)
-        uint32_t s1_a = 0, s1_r2 = 0, s1_r3 = 0, s1_meta = 0, s1_same = 0;
-        int2 s1_row = make_int2(0, 1);
-        // stage 2 (column gather in flight)
-        uint32_t s2_a = 0, s2_r3 = 0, s2_meta = 0, s2_nbr = 0, s2_same = 0;
-        StepDesc d1, d2;
+        // ---- stage registers, one set per in-flight step (indices are compile-time after unrolling) ----
+        uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_same[3], q_nbr[3];
+        int2 q_row[3];
+        int q_nb[3], q_snaps[3];
+        bool q_valid[3];
 
-        auto issue1 = [&](const StepDesc& d) {
-            const uint4 r = sp_native_draw(A.seed, chain, 0u, d.e0 + (uint64_t)lane);
+        auto issue1 = [&](int s, uint64_t e0) {
+            const uint64_t e = e0 + (uint64_t)lane;
+            const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
             const bool noise = r.x < noise_thr;
             const uint32_t idx = __umulhi(r.y, n);
             uint32_t a = idx;
-            if (!noise && A.alias_tab) {  // sampling.py:117-122 with integer thresholds
+            if (ALIAS) {  // sampling.py:117-122 with integer thresholds; noise events pick uniformly
                 const uint2 at = __ldg(A.alias_tab + idx);
-                if (!sp_thr_accept(r.y * n, at.x)) a = at.y;
+                a = (noise | sp_thr_accept(r.y * n, at.x)) ? idx : at.y;
             }
-            s1_a = a;
-            s1_r2 = r.z;
-            s1_r3 = r.w;
-            // MATCH.ANY is slow: it is issued here, two steps before its result is first looked at
-            s1_same = __match_any_sync(FULL, a);
-            s1_meta = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
-            if (CSR) s1_row = __ldg(A.row + a);
+            q_a[s] = a;
+            q_r2[s] = r.z;
+            q_r3[s] = r.w;
+            q_meta[s] = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
+            q_same[s] = __match_any_sync(FULL, a);
+            if (CSR) q_row[s] = __ldg(A.row + a);  // every lane gathers (no divergence); noise lanes ignore it
         };
-        auto issue2 = [&]() {
-            s2_a = s1_a;
-            s2_r3 = s1_r3;
-            s2_meta = s1_meta;
-            s2_same = s1_same;
-            uint32_t nbr = s1_a;
-            if (!(s1_meta & 1u)) {
-                if (CSR) {
-                    nbr = (uint32_t)__ldg(A.col + s1_row.x + __umulhi(s1_r2, (uint32_t)s1_row.y));
-                } else {
-                    nbr = __umulhi(s1_r2, n - 1);
-                    nbr += (nbr >= s1_a);
-                }
+        auto issue2 = [&](int s) {
+            uint32_t nbr;
+            if (CSR) {
+                nbr = (uint32_t)__ldg(A.col + q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y));
+            } else {
+                nbr = __umulhi(q_r2[s], n - 1);
+                nbr += (nbr >= q_a[s]);
             }
-            s2_nbr = nbr;
+            q_nbr[s] = nbr;
         };
 
-        bool v1 = gen(d1);
-        if (v1) issue1(d1);
-        bool v2 = v1;
-        d2 = d1;
-        if (v2) issue2();
-        v1 = gen(d1);
-        if (v1) issue1(d1);
-
-        while (v2) {
-            // current step = stage 2 contents
-            const uint32_t a = s2_a, nbr = s2_nbr, r3 = s2_r3, meta = s2_meta, same = s2_same;
-            const StepDesc dc = d2;
-            // advance the pipeline: next step's column gather, the one after's Philox + row gather
-            v2 = v1;
-            d2 = d1;
-            if (v2) issue2();
-            v1 = gen(d1);
-            if (v1) issue1(d1);
-
-            const bool noise = meta & 1u;
-            const uint32_t nw_noise = meta >> 8;
-            const int nb = dc.nb;
-
-            // ---- stage 3: dependency mask of this step ----
-            uint32_t dep = 0;
-            bool suspect;
-            {
-                if (bloom_log2) {
-                    const uint32_t ha = (a * 2654435761u) >> (32 - bloom_log2);
-                    atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
-                    __syncwarp();
-                    bool hit = same != (1u << lane);
-                    if (!noise) {
-                        const uint32_t hn = (nbr * 2654435761u) >> (32 - bloom_log2);
-                        hit |= (bloom[hn >> 5] >> (hn & 31)) & 1u;
-                    }
-                    suspect = __any_sync(FULL, hit);
-                    bloom[ha >> 5] = 0u;  // clear (same value from every lane sharing the word)
-                } else {
-                    suspect = true;
-                }
-                if (suspect) {
-#pragma unroll
-                    for (int jl = 0; jl < 32; ++jl) {
-                        const uint32_t aj = __shfl_sync(FULL, a, jl);
-                        dep |= (uint32_t)((aj == a) | (aj == nbr)) << jl;
-                    }
-                    dep &= lane_lt;
-                }
-            }
-
-            // ---- commit ----
-            const uint32_t wa = P::word(a), sa = P::shift(a);
-            const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
-            const uint32_t tbase = noise ? (uint32_t)MM : 0u;
-            bool pending = lane < nb;
-            for (;;) {
-                const uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
-                const uint32_t nw = noise ? nw_noise : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                const uint32_t th = THR_SMEM ? thr[tbase + m * M + nw] : __ldg(thr + tbase + m * M + nw);
-                const bool acc = pending && sp_thr_accept(r3, th);
-                const uint32_t wmask = __ballot_sync(FULL, acc);
-                const uint32_t hmask = suspect ? __ballot_sync(FULL, pending && (dep & wmask) != 0u) : 0u;
-                const int first = hmask ? (__ffs(hmask) - 1) : 32;
-                const bool commit = acc && lane < first;
-                if (commit) {
-                    atomicXor(state + wa, (m ^ nw) << sa);
-                    if (REGCNT) {
-                        dpack += (1u << (8 * nw)) - (1u << (8 * m));
-                    } else {
-                        atomicAdd(&cnt_mem[m], -1);
-                        atomicAdd(&cnt_mem[nw], 1);
-                    }
-                }
-                acc_total += __popc(hmask ? __ballot_sync(FULL, commit) : wmask);
-                pending = pending && lane >= first;
-                if (!SMEM) __threadfence_block();
-                __syncwarp();
-                if (first == 32) break;
-                ++extra_rounds;
-            }
-            ++step_total;
-            ev_total += nb;
-            if (REGCNT && ++dsteps >= 120) fold_counts();
-            for (int q = 0; q < dc.snaps; ++q) snapshot();
+        {
+            uint64_t e0;
+            q_valid[0] = gen(e0, q_nb[0], q_snaps[0]);
+            if (q_valid[0]) { issue1(0, e0); issue2(0); }
+            q_valid[1] = gen(e0, q_nb[1], q_snaps[1]);
+            if (q_valid[1]) issue1(1, e0);
+            q_valid[2] = false;
         }
+
+        bool running = true;
+        while (running) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int cur = u, nx1 = (u + 1) % 3, nx2 = (u + 2) % 3;
+                if (!q_valid[cur]) { running = false; break; }
+                // advance the pipeline: next step's column gather, the one after's Philox + row gather
+                if (q_valid[nx1]) issue2(nx1);
+                {
+                    uint64_t e0;
+                    q_valid[nx2] = gen(e0, q_nb[nx2], q_snaps[nx2]);
+                    if (q_valid[nx2]) issue1(nx2, e0);
+                }
+
+                const uint32_t a = q_a[cur], r3 = q_r3[cur], meta = q_meta[cur];
+                const bool noise = meta & 1u;
+                const uint32_t nbr = noise ? a : q_nbr[cur];
+                const int nb = q_nb[cur];
+
+                // ---- stage 3: flag lanes that may depend on another lane, exact masks for those ----
+                uint32_t dep = 0;
+                uint32_t flagged;
+                {
+                    bool hit = q_same[cur] != lane_bit;
+                    if (bloom_bits) {
+                        const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
+                        atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
+                        __syncwarp();
+                        const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
+                        hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
+                        flagged = __ballot_sync(FULL, hit);
+                        bloom[ha >> 5] = 0u;  // clear (every lane sharing the word stores the same value)
+                    } else {
+                        flagged = FULL;
+                    }
+                    for (uint32_t f = flagged; f; f &= f - 1) {  // usually zero iterations
+                        const int il = __ffs(f) - 1;
+                        const uint32_t ai = __shfl_sync(FULL, a, il), ni = __shfl_sync(FULL, nbr, il);
+                        const uint32_t touch = __ballot_sync(FULL, (a == ai) | (a == ni));
+                        if (lane == il) dep = touch & lane_lt;
+                    }
+                }
+
+                // ---- commit ----
+                const uint32_t wa = P::word(a), sa = P::shift(a);
+                const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
+                const bool active = lane < nb;
+                uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
+                uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
+                uint32_t th;
+                if (REGCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
+                else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
+                bool acc = active && sp_thr_accept(r3, th);
+                uint32_t hmask = 0;
+                if (flagged) {
+                    const uint32_t wmask = __ballot_sync(FULL, acc);
+                    hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
+                }
+                if (hmask == 0) {  // no lane reads what an earlier accepting lane writes: all commit
+                    if (acc) {
+                        atomicXor(state + wa, (m ^ nw) << sa);
+                        ++my_acc;
+                        if (REGCNT) {
+                            dpack += (1u << (8 * nw)) - (1u << (8 * m));
+                        } else {
+                            atomicAdd(&cnt_mem[m], -1);
+                            atomicAdd(&cnt_mem[nw], 1);
+                        }
+                    }
+                    if (!SMEM) __threadfence_block();
+                    __syncwarp();
+                } else {  // rare: commit up to the first hazard, re-evaluate the rest
+                    bool pending = active;
+                    for (;;) {
+                        const int first = hmask ? (__ffs(hmask) - 1) : 32;
+                        const bool commit = acc && lane < first;
+                        if (commit) {
+                            atomicXor(state + wa, (m ^ nw) << sa);
+                            ++my_acc;
+                            if (REGCNT) {
+                                dpack += (1u << (8 * nw)) - (1u << (8 * m));
+                            } else {
+                                atomicAdd(&cnt_mem[m], -1);
+                                atomicAdd(&cnt_mem[nw], 1);
+                            }
+                        }
+                        pending = pending && lane >= first;
+                        if (!SMEM) __threadfence_block();
+                        __syncwarp();
+                        if (first == 32) break;
+                        ++n_extra;
+                        m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
+                        nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
+                        if (REGCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                        else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
+                        else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
+                        acc = pending && sp_thr_accept(r3, th);
+                        const uint32_t wmask = __ballot_sync(FULL, acc);
+                        hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
+                    }
+                }
+                ++n_steps;
+                n_events += (uint32_t)nb;
+                if (REGCNT && ++dsteps >= 120) fold_counts();
+                for (int q = 0; q < q_snaps[cur]; ++q) snapshot();
+            }
+        }
+        ev_total += n_events;
+        step_total += n_steps;
+        extra_total += n_extra;
+        acc_total += __reduce_add_sync(FULL, my_acc);
         __syncwarp();
     }
     if (lane == 0 && A.counters) {
         atomicAdd(A.counters + 0, ev_total);
         atomicAdd(A.counters + 1, acc_total);
         atomicAdd(A.counters + 2, step_total);
-        atomicAdd(A.counters + 3, extra_rounds);
+        atomicAdd(A.counters + 3, extra_total);
     }
 }
 
@@ -600,7 +638,7 @@ namespace {
 
 template <int BITS, bool SMEM, bool CSR>
 int launch_cnvm(const NativeCnvmArgs& A, int grid, int threads, size_t smem_bytes, cudaStream_t st) {
-    auto kern = cnvm_native_kernel<BITS, SMEM, CSR>;
+    auto kern = A.alias_tab ? cnvm_native_kernel<BITS, SMEM, CSR, true> : cnvm_native_kernel<BITS, SMEM, CSR, false>;
     SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     kern<<<grid, threads, smem_bytes, st>>>(A);
     SP_CUDA(cudaGetLastError());
@@ -622,7 +660,7 @@ int launch_cnvm_s(bool smem, bool csr, const NativeCnvmArgs& A, int grid, int th
 
 template <int BITS, bool SMEM, bool CSR>
 int occupancy_of(int threads, size_t smem_bytes, int* blocks) {
-    auto kern = cnvm_native_kernel<BITS, SMEM, CSR>;
+    auto kern = cnvm_native_kernel<BITS, SMEM, CSR, false>;
     SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, threads, smem_bytes));
     return SPONET_OK;
@@ -747,6 +785,10 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     A.run_begin = o->run_begin;
     A.T = (int32_t)T;
     A.seed = o->seed;
+    for (int r = 0; r < 10; ++r) {
+        A.rk[2 * r] = (uint32_t)o->seed + (uint32_t)r * 0x9E3779B9u;
+        A.rk[2 * r + 1] = (uint32_t)(o->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
 
     SP_CUDA(sc.in(x_init, (size_t)S * n, &A.x_init));
     const double* d_t;
@@ -776,7 +818,7 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     SP_CUDA(cudaGetDeviceProperties(&prop, dev));
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
-    const size_t fixed = (bits <= 4 ? (size_t)2 * M * M * 4 : 0);
+    const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)2 * M * M * 4 : 0);
     const size_t cnt_bytes = (bits >= 4) ? (size_t)M * 4 : 0;  // per-warp opinion counters
     const size_t per_warp = chain_bytes + cnt_bytes;
     int warps = 0;
@@ -795,20 +837,15 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         warps = 8;
         smem_bytes = fixed + cnt_bytes * warps;
     }
-    // Per-warp Bloom filter for the dependency pre-check: the largest power of two (<= 64 Kbit) that the
-    // shared memory left over by the chain states can hold; below 1 Kbit it is not worth having.
+    // Per-warp Bloom filter for the dependency pre-check, carved from the shared memory the chain states
+    // leave over (a chain is never given up for it).  ~N/4 bits are plenty: a step flags a lane with
+    // probability ~ 32*25/bits, against a true overlap rate of ~1000/N.  Below 1 Kbit it is not worth it.
     {
         const size_t spare = smem_max > smem_bytes + 64 ? (smem_max - smem_bytes - 64) / warps : 0;
-        int lg = 0;
-        while (lg < 16 && ((size_t)1 << (lg + 1)) / 8 <= spare) ++lg;
-        // no larger than ~N/4 bits (false-positive rate ~ 32*25/bits per step vs a true overlap rate of
-        // ~1000/N), so that small chains keep their occupancy; only spare bytes are used, a chain is
-        // never given up for a larger filter
-        int want = 10;
-        while (want < 16 && ((int64_t)1 << want) < n / 4) ++want;
-        lg = std::min(lg, want);
-        A.bloom_log2 = lg >= 10 ? lg : 0;
-        if (A.bloom_log2) smem_bytes += ((size_t)1 << A.bloom_log2) / 8 * warps;
+        size_t words = std::min<size_t>(spare / 4, 2048);
+        words = std::min<size_t>(words, std::max<size_t>(32, (size_t)n / 128));
+        A.bloom_words = words >= 32 ? (int32_t)words : 0;
+        smem_bytes += (size_t)A.bloom_words * 4 * warps;
     }
     A.warps_per_cta = warps;
     const int threads = warps * 32;
