@@ -12,7 +12,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsponet_b200.so")
+# SPONET_B200_LIB selects another build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("SPONET_B200_LIB") or os.path.join(_HERE, "libsponet_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STREAM_EXHAUSTED, ERR_UNSUPPORTED, ERR_ZERO_RATE = range(6)
 NUM_COUNTERS = 4

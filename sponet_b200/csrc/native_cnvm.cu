@@ -80,6 +80,12 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies):
 // both L2 gathers and the MATCH are in flight while a step commits.
 // ---------------------------------------------------------------------------------------------
+#ifndef SP_DUP_MODE
+#define SP_DUP_MODE 1  // 0: MATCH.ANY issued in stage 1; 1: old value of the Bloom insert (fastest, A/B on B200); 2: MATCH at step start
+#endif
+#ifndef SP_GUARDS
+#define SP_GUARDS 1  // 1: skip stage 1/2 work of steps past the end of the chain
+#endif
 template <int BITS, bool SMEM, bool CSR, bool ALIAS>
 __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         };
 
         // ---- stage registers, one set per in-flight step (indices are compile-time after unrolling) ----
-        uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_same[3], q_nbr[3];
+        uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3], q_same[3];
         int2 q_row[3];
         int q_nb[3], q_snaps[3];
         bool q_valid[3];
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             q_r2[s] = r.z;
             q_r3[s] = r.w;
             q_meta[s] = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
-            q_same[s] = __match_any_sync(FULL, a);
+            if (SP_DUP_MODE == 0) q_same[s] = __match_any_sync(FULL, a);
             if (CSR) q_row[s] = __ldg(A.row + a);  // every lane gathers (no divergence); noise lanes ignore it
         };
         auto issue2 = [&](int s) {
@@ -299,10 +305,13 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         {
             uint64_t e0;
             q_valid[0] = gen(e0, q_nb[0], q_snaps[0]);
-            if (q_valid[0]) { issue1(0, e0); issue2(0); }
+            issue1(0, e0);
+            issue2(0);
             q_valid[1] = gen(e0, q_nb[1], q_snaps[1]);
-            if (q_valid[1]) issue1(1, e0);
+            issue1(1, e0);
             q_valid[2] = false;
+            q_a[2] = q_r2[2] = q_r3[2] = q_meta[2] = q_same[2] = 0u;
+            q_row[2] = make_int2(0, 1);
         }
 
         bool running = true;
@@ -311,12 +320,18 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             for (int u = 0; u < 3; ++u) {
                 const int cur = u, nx1 = (u + 1) % 3, nx2 = (u + 2) % 3;
                 if (!q_valid[cur]) { running = false; break; }
+                // MATCH.ANY (lanes with the same agent) is slow: issued first, consumed in stage 3 after the
+                // next steps' Philox / gather work has been issued
+                uint32_t same = lane_bit;
+                if (SP_DUP_MODE == 2) same = __match_any_sync(FULL, q_a[cur]);
+                if (SP_DUP_MODE == 0) same = q_same[cur];
                 // advance the pipeline: next step's column gather, the one after's Philox + row gather
-                if (q_valid[nx1]) issue2(nx1);
+                // (issued unconditionally: past the end of the chain these are idle steps with nb = 0)
+                if (!SP_GUARDS || q_valid[nx1]) issue2(nx1);
                 {
                     uint64_t e0;
                     q_valid[nx2] = gen(e0, q_nb[nx2], q_snaps[nx2]);
-                    if (q_valid[nx2]) issue1(nx2, e0);
+                    if (!SP_GUARDS || q_valid[nx2]) issue1(nx2, e0);
                 }
 
                 const uint32_t a = q_a[cur], r3 = q_r3[cur], meta = q_meta[cur];
@@ -325,27 +340,39 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 const int nb = q_nb[cur];
 
                 // ---- stage 3: flag lanes that may depend on another lane, exact masks for those ----
+                // Every lane inserts its agent into the warp's Bloom filter.  A lane is flagged when the bit
+                // of its agent was already set (an equal agent in this step, or a hash collision; the
+                // MATCH.ANY alternative costs ~20 % on B200) or when the bit of its neighbour is set (the
+                // neighbour may be another lane's agent).  Flagged lanes get exact masks from two ballots;
+                // lanes sharing the flagged lane's agent get theirs too, because the order of the atomic
+                // inserts says nothing about the lane order.
                 uint32_t dep = 0;
                 uint32_t flagged;
-                {
-                    bool hit = q_same[cur] != lane_bit;
-                    if (bloom_bits) {
-                        const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
-                        atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
-                        __syncwarp();
-                        const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
-                        hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
-                        flagged = __ballot_sync(FULL, hit);
-                        bloom[ha >> 5] = 0u;  // clear (every lane sharing the word stores the same value)
+                if (bloom_bits) {
+                    const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
+                    bool hit;
+                    if (SP_DUP_MODE == 1) {
+                        const uint32_t bit = 1u << (ha & 31);
+                        hit = atomicOr(bloom + (ha >> 5), bit) & bit;
                     } else {
-                        flagged = FULL;
+                        atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
+                        hit = same != lane_bit;
                     }
-                    for (uint32_t f = flagged; f; f &= f - 1) {  // usually zero iterations
-                        const int il = __ffs(f) - 1;
-                        const uint32_t ai = __shfl_sync(FULL, a, il), ni = __shfl_sync(FULL, nbr, il);
-                        const uint32_t touch = __ballot_sync(FULL, (a == ai) | (a == ni));
-                        if (lane == il) dep = touch & lane_lt;
-                    }
+                    __syncwarp();
+                    const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
+                    hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
+                    flagged = __ballot_sync(FULL, hit);
+                    bloom[ha >> 5] = 0u;  // clear (every lane sharing the word stores the same value)
+                } else {
+                    flagged = FULL;
+                }
+                for (uint32_t f = flagged; f; f &= f - 1) {  // usually zero iterations
+                    const int il = __ffs(f) - 1;
+                    const uint32_t ai = __shfl_sync(FULL, a, il), ni = __shfl_sync(FULL, nbr, il);
+                    const uint32_t same_a = __ballot_sync(FULL, a == ai);
+                    const uint32_t is_nbr = __ballot_sync(FULL, a == ni);
+                    if (a == ai) dep |= same_a & lane_lt;
+                    if (lane == il) dep |= is_nbr & lane_lt;
                 }
 
                 // ---- commit ----
