@@ -161,6 +161,8 @@ typedef struct {
      * overriding the in-kernel Poisson(dt / next_event_rate) sampler (tests, host-side schedules) */
     const int64_t* event_counts;
     int32_t force_global_state; /* debug/tests: keep chain state in global memory                   */
+    int32_t warps_per_chain;    /* 0 = auto, 1 = one warp per chain, 2 = two warps alternating steps   */
+                                /* (CNVM agent-level kernel, shared-memory states only)             */
 } sponet_native_opts;
 
 /* counters: [0] candidate events executed, [1] accepted changes, [2] warp steps, [3] extra commit

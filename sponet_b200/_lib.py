@@ -66,6 +66,7 @@ class sponet_native_opts(C.Structure):
         ("run_end", C.c_int64),
         ("event_counts", C.c_void_p),
         ("force_global_state", C.c_int32),
+        ("warps_per_chain", C.c_int32),
     ]
 
 

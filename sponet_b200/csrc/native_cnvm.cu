@@ -66,45 +66,81 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // agent-level kernel
 //
 // Per warp step (32 consecutive candidate events of one chain) the work is split into
-//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued;
-//            MATCH.ANY on the agents issued (slow instruction, result needed two steps later)
+//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued
 //   stage 2  neighbour slot from the row; column gather issued
 //   stage 3  dependency mask: which EARLIER lanes touch an agent this lane reads.  Agents and
-//            neighbours never depend on the chain state, so this is known before the commit:
-//            the MATCH result flags equal agents, a per-warp Bloom filter in shared memory flags
-//            neighbours that may equal another lane's agent; only flagged lanes (none in most
-//            steps) get an exact mask, built with two shuffles and a ballot per flagged lane
+//            neighbours never depend on the chain state, so this is known before the commit: a
+//            per-warp Bloom filter in shared memory flags lanes whose agent or neighbour may equal
+//            another lane's agent; only flagged lanes (none in most steps) get an exact mask,
+//            built with two shuffles and two ballots per flagged lane
 //   commit   read x[a], x[nbr]; accept; hazard = dep & ballot(accepting lanes); lanes before the
 //            first hazard write (atomicXor on the packed word), the rest re-evaluate
 // Stages 1 and 2 of the NEXT two steps are issued before the commit of the current one (software
-// pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies):
-// both L2 gathers and the MATCH are in flight while a step commits.
+// pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies).
+//
+// PAIR mode (large chains: only ~9 fit in an SM's shared memory, i.e. 2.25 warps per scheduler):
+// TWO warps serve one chain and take alternate steps.  Stages 1-3 of a warp's next steps overlap
+// the other warp's commit; the commits themselves stay strictly ordered through a pair of
+// mbarriers (arrive = release after the writes, try_wait = acquire before the reads).
 // ---------------------------------------------------------------------------------------------
-#ifndef SP_DUP_MODE
-#define SP_DUP_MODE 1  // 0: MATCH.ANY issued in stage 1; 1: old value of the Bloom insert (fastest, A/B on B200); 2: MATCH at step start
-#endif
 #ifndef SP_GUARDS
 #define SP_GUARDS 1  // 1: skip stage 1/2 work of steps past the end of the chain
 #endif
-template <int BITS, bool SMEM, bool CSR, bool ALIAS>
-__global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
+#ifndef SP_PAIR_ARRIVE_ONE
+#define SP_PAIR_ARRIVE_ONE 0  // PAIR hand-over: 1 = __syncwarp + one arriving lane, 0 = every lane arrives
+#endif
+#ifndef SP_PAIR_MAX_SLOTS
+// A/B on B200 (H workload): 9 slots = 18 warps = 576 threads caps the kernel at 96 registers and spills
+// (4.0e10 events/s); 8 slots = 512 threads keeps 118 registers (6.3e10 vs 5.9e10 for 9 single warps).
+#define SP_PAIR_MAX_SLOTS 8
+#endif
+
+__device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SP_DONE;\n"
+        "bra SP_WAIT;\n"
+        "SP_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void sp_pair_sync(int id) {  // named barrier shared by the two warps of a chain
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+template <int BITS, bool SMEM, bool CSR, bool ALIAS, bool PAIR>
+__global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
-    constexpr bool REGCNT = (BITS <= 2);    // M <= 4: opinion counts live in registers
+    constexpr bool PACKCNT = (BITS <= 2);   // M <= 4: count deltas packed per lane, folded lazily
     constexpr bool THR_SMEM = (BITS <= 4);  // M <= 16: threshold tables staged in shared memory
     constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = PAIR ? (warp >> 1) : warp;  // chain slot of this warp within the CTA
+    const int role = PAIR ? (warp & 1) : 0;      // PAIR: which of the alternating steps this warp takes
+    const int slots = PAIR ? (A.warps_per_cta >> 1) : A.warps_per_cta;
     const int M = A.M, MM = M * M;
     const uint32_t n = (uint32_t)A.n;
     const uint32_t noise_thr = A.noise_thr;
     const uint32_t lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
 
-    // shared layout: [thr] [counts W*M (if !REGCNT)] [bloom W*bloom_words] [states W*words (if SMEM)]
+    // shared layout: [thr] [mbarriers slots*2 (PAIR)] [counts slots*M] [bloom warps*bloom_words]
+    //                [states slots*words (if SMEM)]
     // thr: M <= 4 -> 32 entries indexed (noise << 4 | m << 2 | nw); M <= 16 -> 2*MM entries
     uint32_t* sp = smem;
     const uint32_t* thr = A.thr;
-    if (REGCNT) {
+    if (PACKCNT) {
         for (int i = threadIdx.x; i < 32; i += blockDim.x) {
             const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
             sp[i] = (m < M && w < M) ? A.thr[nz * MM + m * M + w] : 0u;
@@ -114,28 +150,33 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     } else if (THR_SMEM) {
         for (int i = threadIdx.x; i < 2 * MM; i += blockDim.x) sp[i] = A.thr[i];
         thr = sp;
-        sp += 2 * MM;
+        sp += (2 * MM + 1) & ~1;
     }
-    int32_t* cnt_mem = nullptr;
-    if (!REGCNT) {
-        cnt_mem = (int32_t*)sp + warp * M;
-        sp += A.warps_per_cta * M;
+    uint32_t bar_mine = 0, bar_other = 0;
+    if (PAIR) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(sp) + (uint32_t)slot * 16u;
+        bar_mine = base + (uint32_t)role * 8u;
+        bar_other = base + (uint32_t)(role ^ 1) * 8u;
+        if (lane == 0) sp_mbar_init(bar_mine, SP_PAIR_ARRIVE_ONE ? 1u : 32u);
+        sp += (size_t)slots * 4;
     }
+    int32_t* cnt_mem = (int32_t*)sp + slot * M;
+    sp += (size_t)slots * M;
     const uint32_t bloom_bits = (uint32_t)A.bloom_words * 32u;  // per warp; 0 = no filter (all lanes flagged)
     uint32_t* bloom = sp + (size_t)warp * A.bloom_words;
     for (int i = threadIdx.x; i < A.warps_per_cta * A.bloom_words; i += blockDim.x) sp[i] = 0u;
     sp += (size_t)A.warps_per_cta * A.bloom_words;
     uint32_t* state;
-    if (SMEM) state = sp + (size_t)warp * A.words;
-    else state = A.gstate + ((size_t)blockIdx.x * A.warps_per_cta + warp) * A.words;
+    if (SMEM) state = sp + (size_t)slot * A.words;
+    else state = A.gstate + ((size_t)blockIdx.x * slots + slot) * A.words;
     __syncthreads();
 
-    const int64_t total_warps = (int64_t)gridDim.x * A.warps_per_cta;
     const int64_t num_chains = A.S * A.nrun;
     unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_total = 0;
+    uint32_t other_done = 0;  // PAIR: completions of the partner warp consumed so far (mbarrier phase)
     const int T = A.T;
 
-    for (int64_t cl = (int64_t)blockIdx.x * A.warps_per_cta + warp; cl < num_chains; cl += total_warps) {
+    for (int64_t cl = (int64_t)blockIdx.x * slots + slot; cl < num_chains; cl += (int64_t)gridDim.x * slots) {
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
@@ -143,47 +184,56 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
 
         // ---- load + pack the initial state, count opinions ----
-        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (!REGCNT) {
+        if (role == 0)
             for (int v = lane; v < M; v += 32) cnt_mem[v] = 0;
-            __syncwarp();
-        }
-        for (int w = lane; w < A.words; w += 32) {
-            uint32_t packed = 0;
-            const uint32_t base = (uint32_t)w * P::APW;
+        if (PAIR) sp_pair_sync(slot + 1);
+        else __syncwarp();
+        {
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            for (int w = role * 32 + lane; w < A.words; w += (PAIR ? 64 : 32)) {
+                uint32_t packed = 0;
+                const uint32_t base = (uint32_t)w * P::APW;
 #pragma unroll 4
-            for (int q = 0; q < P::APW; ++q) {
-                const uint32_t a = base + q;
-                if (a < n) {
-                    const uint32_t v = x0[a];
-                    packed |= v << (q * BITS);
-                    if (REGCNT) {
-                        c0 += (v == 0);
-                        c1 += (v == 1);
-                        c2 += (v == 2);
-                        c3 += (v == 3);
-                    } else {
-                        atomicAdd(&cnt_mem[v], 1);
+                for (int q = 0; q < P::APW; ++q) {
+                    const uint32_t a = base + q;
+                    if (a < n) {
+                        const uint32_t v = x0[a];
+                        packed |= v << (q * BITS);
+                        if (PACKCNT) {
+                            c0 += (v == 0);
+                            c1 += (v == 1);
+                            c2 += (v == 2);
+                            c3 += (v == 3);
+                        } else {
+                            atomicAdd(&cnt_mem[v], 1);
+                        }
                     }
                 }
+                state[w] = packed;
             }
-            state[w] = packed;
-        }
-        if (REGCNT) {
-            c0 = __reduce_add_sync(FULL, c0);
-            c1 = __reduce_add_sync(FULL, c1);
-            c2 = __reduce_add_sync(FULL, c2);
-            c3 = __reduce_add_sync(FULL, c3);
+            if (PACKCNT) {
+                c0 = __reduce_add_sync(FULL, c0);
+                c1 = __reduce_add_sync(FULL, c1);
+                c2 = __reduce_add_sync(FULL, c2);
+                c3 = __reduce_add_sync(FULL, c3);
+                if (lane == 0) {
+                    atomicAdd(&cnt_mem[0], c0);
+                    if (M > 1) atomicAdd(&cnt_mem[1], c1);
+                    if (M > 2) atomicAdd(&cnt_mem[2], c2);
+                    if (M > 3) atomicAdd(&cnt_mem[3], c3);
+                }
+            }
         }
         if (!SMEM) __threadfence_block();
-        __syncwarp();
+        if (PAIR) sp_pair_sync(slot + 1);
+        else __syncwarp();
 
-        // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into
-        // c0..c3 before any field can leave [-127, 127]; 32-bit per-lane statistics folded with them.
+        // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into the
+        // shared counters before any field can leave [-127, 127]; 32-bit per-lane statistics with them.
         uint32_t dpack = 0, my_acc = 0, n_steps = 0, n_events = 0, n_extra = 0;
         int dsteps = 0;
         auto fold_counts = [&]() {
-            if (REGCNT) {
+            if (PACKCNT) {
                 uint32_t t = dpack;
                 const int d0 = (int)(int8_t)(t & 0xFF);
                 t = (uint32_t)(((int)t - d0) >> 8);
@@ -192,31 +242,35 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 const int d2 = (int)(int8_t)(t & 0xFF);
                 t = (uint32_t)(((int)t - d2) >> 8);
                 const int d3 = (int)(int8_t)(t & 0xFF);
-                c0 += __reduce_add_sync(FULL, d0);
-                c1 += __reduce_add_sync(FULL, d1);
-                c2 += __reduce_add_sync(FULL, d2);
-                c3 += __reduce_add_sync(FULL, d3);
+                const int s0 = __reduce_add_sync(FULL, d0), s1 = __reduce_add_sync(FULL, d1);
+                const int s2 = __reduce_add_sync(FULL, d2), s3 = __reduce_add_sync(FULL, d3);
+                if (lane == 0) {
+                    atomicAdd(&cnt_mem[0], s0);
+                    if (M > 1) atomicAdd(&cnt_mem[1], s1);
+                    if (M > 2) atomicAdd(&cnt_mem[2], s2);
+                    if (M > 3) atomicAdd(&cnt_mem[3], s3);
+                }
                 dpack = 0;
                 dsteps = 0;
+                __syncwarp();
             }
         };
 
         int ksnap = 0;
-        auto snapshot = [&]() {
+        // emit == false only advances the snapshot index (PAIR: the partner warp writes that snapshot)
+        auto snapshot = [&](bool emit) {
+            const int k = ksnap++;
+            if (!emit) return;
             fold_counts();
             acc_total += __reduce_add_sync(FULL, my_acc);
             ev_total += n_events;
             step_total += n_steps;
             extra_total += n_extra;
             my_acc = n_events = n_steps = n_extra = 0;
-            const int k = ksnap++;
             const int64_t snap = cl * (int64_t)T + k;
             if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
-                    const int v = A.cv_idx[d];
-                    long long c;
-                    if (REGCNT) c = (v == 0) ? c0 : (v == 1) ? c1 : (v == 2) ? c2 : c3;
-                    else c = cnt_mem[v];
+                    const long long c = cnt_mem[A.cv_idx[d]];
                     if (A.out_cv)
                         A.out_cv[snap * A.D + d] = (A.cv_div == 1.0) ? (double)c : (double)c / A.cv_div;
                     if (A.out_sum) {
@@ -233,16 +287,17 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             }
         };
 
-        // ---- step generator: walks the per-interval event counts, two steps ahead of the commit ----
+        // ---- step generator: walks the per-interval event counts ahead of the commit ----
         int gk = 1;
         int64_t gK = 0;
         uint64_t ge = 0;
+        uint32_t gsteps = 0;  // steps generated so far (both warps of a pair see the same sequence)
         bool gdone = (T <= 1);
-        snapshot();  // k = 0: the initial state
+        snapshot(role == 0);  // k = 0: the initial state
         if (!gdone) {
             gK = kcounts[0];
             while (gK == 0) {  // leading empty intervals repeat the initial state
-                snapshot();
+                snapshot(role == 0);
                 if (++gk >= T) { gdone = true; break; }
                 gK = kcounts[gk - 1];
             }
@@ -253,6 +308,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             snaps = 0;
             nb = 0;
             if (gdone) return false;
+            ++gsteps;
             nb = gK < 32 ? (int)gK : 32;
             ge += (uint64_t)nb;
             gK -= nb;
@@ -268,11 +324,30 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             return true;
         };
 
-        // ---- stage registers, one set per in-flight step (indices are compile-time after unrolling) ----
-        uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3], q_same[3];
+        // ---- stage registers, one set per in-flight own step (indices are compile-time after unrolling) ----
+        uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3];
         int2 q_row[3];
         int q_nb[3], q_snaps[3];
+        int q_pre[3];   // PAIR: snapshots completed by the partner's step right before this own step
+        int q_next[3];  // PAIR: snapshots completed by the partner's step right after this own step
         bool q_valid[3];
+
+        // next OWN step into set s (PAIR: also walks over the partner's step next to it)
+        auto gen_own = [&](int s, uint64_t& e0) -> bool {
+            q_pre[s] = 0;
+            q_next[s] = 0;
+            if (!PAIR) return gen(e0, q_nb[s], q_snaps[s]);
+            uint64_t eo;
+            int nbo;
+            if (role == 0) {
+                const bool v = gen(e0, q_nb[s], q_snaps[s]);
+                gen(eo, nbo, q_next[s]);
+                return v;
+            }
+            gen(eo, nbo, q_pre[s]);
+            q_next[(s + 2) % 3] = q_pre[s];  // ... which also follows our previous own step
+            return gen(e0, q_nb[s], q_snaps[s]);
+        };
 
         auto issue1 = [&](int s, uint64_t e0) {
             const uint64_t e = e0 + (uint64_t)lane;
@@ -288,7 +363,6 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             q_r2[s] = r.z;
             q_r3[s] = r.w;
             q_meta[s] = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
-            if (SP_DUP_MODE == 0) q_same[s] = __match_any_sync(FULL, a);
             if (CSR) q_row[s] = __ldg(A.row + a);  // every lane gathers (no divergence); noise lanes ignore it
         };
         auto issue2 = [&](int s) {
@@ -304,33 +378,29 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
 
         {
             uint64_t e0;
-            q_valid[0] = gen(e0, q_nb[0], q_snaps[0]);
+            q_next[2] = 0;
+            q_valid[0] = gen_own(0, e0);
             issue1(0, e0);
             issue2(0);
-            q_valid[1] = gen(e0, q_nb[1], q_snaps[1]);
+            q_valid[1] = gen_own(1, e0);
             issue1(1, e0);
             q_valid[2] = false;
-            q_a[2] = q_r2[2] = q_r3[2] = q_meta[2] = q_same[2] = 0u;
+            q_a[2] = q_r2[2] = q_r3[2] = q_meta[2] = 0u;
             q_row[2] = make_int2(0, 1);
         }
 
+        bool first_own = true;
         bool running = true;
         while (running) {
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
                 const int cur = u, nx1 = (u + 1) % 3, nx2 = (u + 2) % 3;
                 if (!q_valid[cur]) { running = false; break; }
-                // MATCH.ANY (lanes with the same agent) is slow: issued first, consumed in stage 3 after the
-                // next steps' Philox / gather work has been issued
-                uint32_t same = lane_bit;
-                if (SP_DUP_MODE == 2) same = __match_any_sync(FULL, q_a[cur]);
-                if (SP_DUP_MODE == 0) same = q_same[cur];
-                // advance the pipeline: next step's column gather, the one after's Philox + row gather
-                // (issued unconditionally: past the end of the chain these are idle steps with nb = 0)
+                // advance the pipeline: next own step's column gather, the one after's Philox + row gather
                 if (!SP_GUARDS || q_valid[nx1]) issue2(nx1);
                 {
                     uint64_t e0;
-                    q_valid[nx2] = gen(e0, q_nb[nx2], q_snaps[nx2]);
+                    q_valid[nx2] = gen_own(nx2, e0);
                     if (!SP_GUARDS || q_valid[nx2]) issue1(nx2, e0);
                 }
 
@@ -350,14 +420,8 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 uint32_t flagged;
                 if (bloom_bits) {
                     const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
-                    bool hit;
-                    if (SP_DUP_MODE == 1) {
-                        const uint32_t bit = 1u << (ha & 31);
-                        hit = atomicOr(bloom + (ha >> 5), bit) & bit;
-                    } else {
-                        atomicOr(bloom + (ha >> 5), 1u << (ha & 31));
-                        hit = same != lane_bit;
-                    }
+                    const uint32_t bit = 1u << (ha & 31);
+                    bool hit = atomicOr(bloom + (ha >> 5), bit) & bit;
                     __syncwarp();
                     const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
                     hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
@@ -375,6 +439,17 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                     if (lane == il) dep |= is_nbr & lane_lt;
                 }
 
+                // ---- PAIR: the partner's step right before this one must have been committed ----
+                if (PAIR) {
+                    if (role == 1)
+                        for (int q = 0; q < q_pre[cur]; ++q) snapshot(false);  // written by the partner
+                    if (!(first_own && role == 0)) {
+                        sp_mbar_wait(bar_other, other_done & 1u);
+                        ++other_done;
+                    }
+                    first_own = false;
+                }
+
                 // ---- commit ----
                 const uint32_t wa = P::word(a), sa = P::shift(a);
                 const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
@@ -382,7 +457,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
                 uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
                 uint32_t th;
-                if (REGCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                if (PACKCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
                 else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
                 else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
                 bool acc = active && sp_thr_accept(r3, th);
@@ -395,7 +470,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                     if (acc) {
                         atomicXor(state + wa, (m ^ nw) << sa);
                         ++my_acc;
-                        if (REGCNT) {
+                        if (PACKCNT) {
                             dpack += (1u << (8 * nw)) - (1u << (8 * m));
                         } else {
                             atomicAdd(&cnt_mem[m], -1);
@@ -403,7 +478,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                         }
                     }
                     if (!SMEM) __threadfence_block();
-                    __syncwarp();
+                    if (!PAIR) __syncwarp();  // PAIR: the mbarrier hand-over orders the writes
                 } else {  // rare: commit up to the first hazard, re-evaluate the rest
                     bool pending = active;
                     for (;;) {
@@ -412,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                         if (commit) {
                             atomicXor(state + wa, (m ^ nw) << sa);
                             ++my_acc;
-                            if (REGCNT) {
+                            if (PACKCNT) {
                                 dpack += (1u << (8 * nw)) - (1u << (8 * m));
                             } else {
                                 atomicAdd(&cnt_mem[m], -1);
@@ -426,7 +501,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                         ++n_extra;
                         m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
                         nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                        if (REGCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                        if (PACKCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
                         else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
                         else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
                         acc = pending && sp_thr_accept(r3, th);
@@ -436,15 +511,34 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 }
                 ++n_steps;
                 n_events += (uint32_t)nb;
-                if (REGCNT && ++dsteps >= 120) fold_counts();
-                for (int q = 0; q < q_snaps[cur]; ++q) snapshot();
+                if (PACKCNT && (++dsteps >= 120 || (PAIR && q_next[cur] > 0))) fold_counts();
+                for (int q = 0; q < q_snaps[cur]; ++q) snapshot(true);
+                if (PAIR) {
+#if SP_PAIR_ARRIVE_ONE
+                    __syncwarp();
+                    if (lane == 0) sp_mbar_arrive(bar_mine);
+#else
+                    sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
+#endif
+                    // the partner's step right after this one writes its own snapshots: keep the index in step
+                    if (role == 0)
+                        for (int q = 0; q < q_next[cur]; ++q) snapshot(false);
+                }
             }
         }
         ev_total += n_events;
         step_total += n_steps;
         extra_total += n_extra;
         acc_total += __reduce_add_sync(FULL, my_acc);
-        __syncwarp();
+        if (PAIR) {
+            // both warps are done with the chain; account for partner completions nobody waited for
+            sp_pair_sync(slot + 1);
+            const uint32_t own = role == 0 ? (gsteps + 1) / 2 : gsteps / 2;
+            const uint32_t waited = own - ((role == 0 && own > 0) ? 1u : 0u);
+            other_done += (gsteps - own) - waited;
+        } else {
+            __syncwarp();
+        }
     }
     if (lane == 0 && A.counters) {
         atomicAdd(A.counters + 0, ev_total);
@@ -663,49 +757,28 @@ int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out) 
 
 namespace {
 
-template <int BITS, bool SMEM, bool CSR>
-int launch_cnvm(const NativeCnvmArgs& A, int grid, int threads, size_t smem_bytes, cudaStream_t st) {
-    auto kern = A.alias_tab ? cnvm_native_kernel<BITS, SMEM, CSR, true> : cnvm_native_kernel<BITS, SMEM, CSR, false>;
-    SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    kern<<<grid, threads, smem_bytes, st>>>(A);
-    SP_CUDA(cudaGetLastError());
-    return SPONET_OK;
-}
+// kernel selection over (BITS, SMEM, CSR, ALIAS, PAIR); PAIR exists for shared-memory states only
+typedef void (*cnvm_kernel_t)(NativeCnvmArgs);
 
-template <int BITS, bool SMEM>
-int launch_cnvm_g(bool csr, const NativeCnvmArgs& A, int grid, int threads, size_t smem_bytes, cudaStream_t st) {
-    return csr ? launch_cnvm<BITS, SMEM, true>(A, grid, threads, smem_bytes, st)
-               : launch_cnvm<BITS, SMEM, false>(A, grid, threads, smem_bytes, st);
+template <int BITS, bool SMEM, bool CSR>
+cnvm_kernel_t pick_cnvm(bool alias, bool pair) {
+    if (SMEM && pair) return alias ? cnvm_native_kernel<BITS, SMEM, CSR, true, SMEM> : cnvm_native_kernel<BITS, SMEM, CSR, false, SMEM>;
+    return alias ? cnvm_native_kernel<BITS, SMEM, CSR, true, false> : cnvm_native_kernel<BITS, SMEM, CSR, false, false>;
 }
 
 template <int BITS>
-int launch_cnvm_s(bool smem, bool csr, const NativeCnvmArgs& A, int grid, int threads, size_t smem_bytes,
-                  cudaStream_t st) {
-    return smem ? launch_cnvm_g<BITS, true>(csr, A, grid, threads, smem_bytes, st)
-                : launch_cnvm_g<BITS, false>(csr, A, grid, threads, smem_bytes, st);
+cnvm_kernel_t pick_cnvm_b(bool smem, bool csr, bool alias, bool pair) {
+    if (smem) return csr ? pick_cnvm<BITS, true, true>(alias, pair) : pick_cnvm<BITS, true, false>(alias, pair);
+    return csr ? pick_cnvm<BITS, false, true>(alias, false) : pick_cnvm<BITS, false, false>(alias, false);
 }
 
-template <int BITS, bool SMEM, bool CSR>
-int occupancy_of(int threads, size_t smem_bytes, int* blocks) {
-    auto kern = cnvm_native_kernel<BITS, SMEM, CSR, false>;
-    SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, threads, smem_bytes));
-    return SPONET_OK;
-}
-
-int occupancy_dispatch(int bits, bool smem, bool csr, int threads, size_t smem_bytes, int* blocks) {
-#define OCC(B)                                                                                     \
-    (smem ? (csr ? occupancy_of<B, true, true>(threads, smem_bytes, blocks)                        \
-                 : occupancy_of<B, true, false>(threads, smem_bytes, blocks))                      \
-          : (csr ? occupancy_of<B, false, true>(threads, smem_bytes, blocks)                       \
-                 : occupancy_of<B, false, false>(threads, smem_bytes, blocks)))
+cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, bool csr, bool alias, bool pair) {
     switch (bits) {
-        case 1: return OCC(1);
-        case 2: return OCC(2);
-        case 4: return OCC(4);
-        default: return OCC(8);
+        case 1: return pick_cnvm_b<1>(smem, csr, alias, pair);
+        case 2: return pick_cnvm_b<2>(smem, csr, alias, pair);
+        case 4: return pick_cnvm_b<4>(smem, csr, alias, pair);
+        default: return pick_cnvm_b<8>(smem, csr, alias, pair);
     }
-#undef OCC
 }
 
 // Threshold tables: thr[0:MM] imitation, thr[MM:2MM] noise.
@@ -839,31 +912,37 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     SP_CUDA(sc.out((unsigned long long*)counters, SPONET_NUM_COUNTERS, &A.counters, true));
 
     // ---- launch geometry ----
+    // slots = chains resident per CTA (one warp each, or two in PAIR mode); shared memory per CTA =
+    // thresholds + [mbarriers] + counters + Bloom filters + packed states.
     const int bits = M <= 2 ? 1 : M <= 4 ? 2 : M <= 16 ? 4 : 8;
     A.words = (int32_t)((n * bits + 31) / 32);
     cudaDeviceProp prop;
     SP_CUDA(cudaGetDeviceProperties(&prop, dev));
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
-    const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)2 * M * M * 4 : 0);
-    const size_t cnt_bytes = (bits >= 4) ? (size_t)M * 4 : 0;  // per-warp opinion counters
-    const size_t per_warp = chain_bytes + cnt_bytes;
-    int warps = 0;
+    const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
+    const size_t per_slot_min = (size_t)M * 4 + 16;  // counters + (possible) mbarrier pair
     bool smem_state = !o->force_global_state;
+    int slots = 0;
     if (smem_state) {
-        if (smem_max > fixed + 64) warps = (int)std::min<size_t>(16, (smem_max - fixed - 64) / per_warp);
-        if (warps < 1) smem_state = false;
+        if (smem_max > fixed + 64) slots = (int)std::min<size_t>(16, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
+        if (slots < 1) smem_state = false;
     }
-    size_t smem_bytes;
+    bool pair = false;
     if (smem_state) {
-        // no more warps than there are chains to run on this many SMs
+        // Large chains leave only a few warps per SM: give each chain two warps that alternate steps.
+        const bool auto_pair = slots <= 9 && chain_bytes >= 8192 && num_chains >= 2 * (int64_t)prop.multiProcessorCount;
+        pair = o->warps_per_chain == 2 || (o->warps_per_chain == 0 && auto_pair);
+        if (pair && slots > SP_PAIR_MAX_SLOTS) slots = SP_PAIR_MAX_SLOTS;  // the PAIR kernels' launch bound
+        // no more slots than there are chains to run on this many SMs
         const int64_t need = (num_chains + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-        warps = (int)std::max<int64_t>(1, std::min<int64_t>(warps, need));
-        smem_bytes = fixed + per_warp * warps;
+        slots = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
     } else {
-        warps = 8;
-        smem_bytes = fixed + cnt_bytes * warps;
+        slots = 8;
     }
+    const int warps = slots * (pair ? 2 : 1);
+    size_t smem_bytes = fixed + (pair ? (size_t)slots * 16 : 0) + (size_t)slots * M * 4 +
+                        (smem_state ? (size_t)slots * chain_bytes : 0);
     // Per-warp Bloom filter for the dependency pre-check, carved from the shared memory the chain states
     // leave over (a chain is never given up for it).  ~N/4 bits are plenty: a step flags a lane with
     // probability ~ 32*25/bits, against a true overlap rate of ~1000/N.  Below 1 Kbit it is not worth it.
@@ -876,21 +955,19 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     }
     A.warps_per_cta = warps;
     const int threads = warps * 32;
+    const bool csr = g != nullptr;
+    cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, csr, A.alias_tab != nullptr, pair);
+    SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int blocks_per_sm = 1;
-    SP_TRY(occupancy_dispatch(bits, smem_state, g != nullptr, threads, smem_bytes, &blocks_per_sm));
-    SP_REQUIRE(blocks_per_sm >= 1, "cnvm_run: kernel does not fit on an SM (smem %zu B)", smem_bytes);
-    const int64_t ctas_needed = (num_chains + warps - 1) / warps;
+    SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem_bytes));
+    SP_REQUIRE(blocks_per_sm >= 1, "cnvm_run: kernel does not fit on an SM (smem %zu B, %d threads)", smem_bytes, threads);
+    const int64_t ctas_needed = (num_chains + slots - 1) / slots;
     const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)prop.multiProcessorCount * blocks_per_sm);
     if (!smem_state) {
-        SP_CUDA(sc.alloc((void**)&A.gstate, (size_t)grid * warps * chain_bytes));
+        SP_CUDA(sc.alloc((void**)&A.gstate, (size_t)grid * slots * chain_bytes));
     }
-    const bool csr = g != nullptr;
-    switch (bits) {
-        case 1: SP_TRY(launch_cnvm_s<1>(smem_state, csr, A, grid, threads, smem_bytes, sc.stream)); break;
-        case 2: SP_TRY(launch_cnvm_s<2>(smem_state, csr, A, grid, threads, smem_bytes, sc.stream)); break;
-        case 4: SP_TRY(launch_cnvm_s<4>(smem_state, csr, A, grid, threads, smem_bytes, sc.stream)); break;
-        default: SP_TRY(launch_cnvm_s<8>(smem_state, csr, A, grid, threads, smem_bytes, sc.stream)); break;
-    }
+    kern<<<grid, threads, smem_bytes, sc.stream>>>(A);
+    SP_CUDA(cudaGetLastError());
     SP_CUDA(sc.finish());
     return SPONET_OK;
 }

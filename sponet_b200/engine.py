@@ -173,6 +173,7 @@ def run_native(
     counters=None,
     force_global_state: bool = False,
     counts_init=None,
+    warps_per_chain: int = 0,
 ):
     """One C-ABI call of the native ensemble path.
 
@@ -191,7 +192,8 @@ def run_native(
     out_x = _alloc((S, nrun, T, num_agents), np.uint8, like) if want_x else None
     out_cv = _alloc((S, nrun, T, D), np.float64, like) if want_cv else None
     opts = _lib.sponet_native_opts(
-        seed & (2**64 - 1), num_runs_total, run_begin, run_end, _lib.ptr(event_counts), int(force_global_state)
+        seed & (2**64 - 1), num_runs_total, run_begin, run_end, _lib.ptr(event_counts), int(force_global_state),
+        int(warps_per_chain),
     )
     sum_p = sumsq_p = None
     if sums is not None:

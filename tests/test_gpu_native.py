@@ -183,3 +183,90 @@ def test_cntm_native_matches_sequential_oracle(oracle, kind, n, force_global):
             ev_total += ev
             acc_total += acc
     assert int(counters[0]) == ev_total and int(counters[1]) == acc_total
+
+
+@pytest.mark.parametrize("n,M,alpha", [(40000, 3, 1.0), (40000, 3, 0.5), (70000, 2, 1.0)])
+def test_cnvm_pair_mode_matches_single_warp_and_oracle(oracle, n, M, alpha):
+    """Two warps per chain (alternating steps, mbarrier hand-over) must give exactly what one warp per
+    chain gives -- and one chain is checked against the sequential oracle."""
+    import networkx as nx
+
+    from sponet_b200 import CNVM, CNVMParameters, engine
+
+    g = nx.fast_gnp_random_graph(n, 8 / (n - 1), seed=3)
+    for v in list(nx.isolates(g)):
+        g.add_edge(v, (v + 1) % n)
+    r, rt = (R3, RT3) if M == 3 else (1.0, 0.05)
+    params = CNVMParameters(num_opinions=M, network=g, r=r, r_tilde=rt, alpha=alpha)
+    model = CNVM(params)
+    S, R = 1, 700  # more chains than resident slots: several chains per warp pair
+    x0 = np.random.default_rng(1).integers(0, M, (S, n)).astype(np.uint8)
+    t_eval = np.array([0.0, 0.004, 0.004001, 0.02, 0.05])  # includes a near-empty interval
+    struct, keep = model._struct()
+    spec = (np.arange(M, dtype=np.int32), 1.0)
+    out = {}
+    for wpc in (1, 2):
+        counters = np.zeros(4, dtype=np.uint64)
+        sums = (np.zeros((S, t_eval.size, M), dtype=np.int64), np.zeros((S, t_eval.size, M), dtype=np.int64))
+        _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0, t_eval, 555, R, 0, R, cv_spec=spec,
+                                  want_cv=True, sums=sums, counters=counters, warps_per_chain=wpc)
+        out[wpc] = (cv, sums, counters)
+    np.testing.assert_array_equal(out[1][0], out[2][0])
+    np.testing.assert_array_equal(out[1][1][0], out[2][1][0])
+    np.testing.assert_array_equal(out[1][1][1], out[2][1][1])
+    np.testing.assert_array_equal(out[1][2][:2], out[2][2][:2])  # events, accepted
+    # full states of a few chains in pair mode vs the oracle
+    xs, cv = engine.run_native("cnvm", model._graph(), n, struct, x0, t_eval, 555, R, 3, 6, cv_spec=spec,
+                               want_x=True, want_cv=True, warps_per_chain=2)
+    rate, noise_p = model.event_rates()
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    da = np.asarray(model.degree_alpha, dtype=float)
+    if np.all(da == da[0]):
+        alias_thr = alias = None
+    else:
+        prob, alias = oracle.build_alias_table(da)
+        alias_thr = oracle.prob_to_thr(prob)
+    for i in range(3, 6):
+        counts = oracle.native_event_counts(555, i, 1, t_eval, rate)[0]
+        ox, oc, _, _ = oracle.cnvm_native(x0[0], M, rp, col, int(oracle.prob_to_thr(noise_p)),
+                                          oracle.prob_to_thr(params.prob_imit), oracle.prob_to_thr(params.prob_noise),
+                                          alias_thr, alias, counts, 555, i)
+        np.testing.assert_array_equal(xs[0, i - 3], ox)
+        np.testing.assert_array_equal(cv[0, i - 3], oc.astype(float))
+    del keep
+
+
+def test_headline_size_pair_vs_single_and_conservation():
+    """Full-size workload H (ER N=1e5, nnz 998 782): the two-warps-per-chain schedule (what bench.py runs)
+    against one warp per chain -- identical CV trajectories, moment sums and counters -- plus the
+    size-independent properties: counts sum to N at every output time, snapshot 0 is the initial
+    histogram, events executed = sum of the interval schedule."""
+    from sponet_b200 import CNVM, _lib, engine, workloads
+
+    params, x0, rate = workloads.headline_cnvm(100_000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    n, R, T = 100_000, 1500, 6
+    t_eval = np.linspace(0, 0.5, T)
+    spec = (np.arange(3, dtype=np.int32), 1.0)
+    res = {}
+    for wpc in (1, 2):
+        counters = np.zeros(4, dtype=np.uint64)
+        sums = (np.zeros((1, T, 3), dtype=np.int64), np.zeros((1, T, 3), dtype=np.int64))
+        _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0[None, :], t_eval, 99, R, 0, R, cv_spec=spec,
+                                  want_cv=True, sums=sums, counters=counters, warps_per_chain=wpc)
+        res[wpc] = (cv[0], sums, counters)
+    np.testing.assert_array_equal(res[1][0], res[2][0])
+    np.testing.assert_array_equal(res[1][1][0], res[2][1][0])
+    np.testing.assert_array_equal(res[1][1][1], res[2][1][1])
+    np.testing.assert_array_equal(res[1][2][:2], res[2][2][:2])
+    cv, sums, counters = res[2]
+    assert (cv.sum(-1) == n).all()
+    np.testing.assert_array_equal(cv[:, 0], np.broadcast_to(np.bincount(x0, minlength=3), (R, 3)))
+    np.testing.assert_array_equal(sums[0][0], cv.sum(0).astype(np.int64))
+    np.testing.assert_array_equal(sums[1][0], (cv.astype(np.int64) ** 2).sum(0))
+    sched = np.empty((R, T - 1), dtype=np.int64)
+    _lib.check(_lib.lib().sponet_native_event_counts(99, 0, R, _lib.ptr(t_eval), T, 1.0 / rate, _lib.ptr(sched), None))
+    assert int(counters[0]) == int(sched.sum())
+    assert abs(sched.sum() / (R * 0.5 * rate) - 1) < 1e-3  # Poisson totals
+    del keep

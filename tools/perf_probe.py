@@ -1,5 +1,6 @@
 """Quick device-timed throughput probe of the native kernels (development aid, not the bench)."""
 import argparse
+import os
 import time
 
 import numpy as np
@@ -41,7 +42,8 @@ for rep in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     _, cv = engine.run_native(kind, graph, params.num_agents, struct, d_x0, t_eval, 1234 + rep, a.runs, 0, a.runs,
-                              cv_spec=spec, want_cv=True, counters=counters, force_global_state=a.global_state)
+                              cv_spec=spec, want_cv=True, counters=counters, force_global_state=a.global_state,
+                              **({'warps_per_chain': int(os.environ.get('SP_WPC', '0'))} if kind == 'cnvm' else {}))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     c = counters.cpu().numpy()
