@@ -214,6 +214,19 @@ int sponet_native_event_counts(uint64_t seed, int64_t chain_begin, int64_t num_c
 int sponet_opinion_shares(const uint8_t* x, int64_t S, int64_t num_agents, int32_t num_opinions,
                           const double* weights, double* out, void* cuda_stream);
 
+/* sponet/collective_variables.py:259-305 Interfaces: number of edges whose endpoints disagree, per
+ * snapshot (2-opinion states).  x uint8 [S, n]; out float64 [S]. */
+int sponet_interfaces(const sponet_graph* g, const uint8_t* x, int64_t S, double* out, void* cuda_stream);
+
+/* sponet/collective_variables.py:308-397 Propensities (2 opinions): out[s, m] = sum over agents j in
+ * state m of r[m,n] * d(j,n) / degree_alpha[j] + r_tilde[m,n], n = 1 - m.  NOTE degree_alpha here is
+ * d_j^alpha (collective_variables.py:355-358), not the d_j^(1-alpha) of the event loop.  g == NULL:
+ * complete graph with the scalar complete_degree_alpha = (N-1)^alpha.  r, r_tilde: [2*2] HOST arrays.
+ * x uint8 [S, n]; out float64 [S, 2]. */
+int sponet_propensities(const sponet_graph* g, int64_t num_agents, const uint8_t* x, int64_t S,
+                        const double* degree_alpha, double complete_degree_alpha, const double* r,
+                        const double* r_tilde, double* out, void* cuda_stream);
+
 /* sum and sum of squares over the run axis: x [R, L] float64 -> sum[L], sumsq[L]
  * (sponet/sample_moments.py:107-108), fixed-order reduction. */
 int sponet_moments(const double* x, int64_t R, int64_t L, double* sum, double* sumsq, void* cuda_stream);

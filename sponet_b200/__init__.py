@@ -11,6 +11,7 @@ from .collective_variables import (
     CollectiveVariable,
     CompositeCollectiveVariable,
     DegreeWeightedOpinionShares,
+    Interfaces,
     OpinionShares,
     OpinionSharesByDegree,
 )
@@ -22,7 +23,7 @@ from .steady_state import estimate_steady_state
 
 __all__ = [
     "CNTM", "CNTMParameters", "CNVM", "CNVMParameters", "CollectiveVariable",
-    "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "OpinionShares",
+    "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "Interfaces", "OpinionShares",
     "OpinionSharesByDegree", "Parameters", "load_params", "save_params", "sample_many_runs",
     "sample_moments", "estimate_steady_state", "set_default_mode",
 ]

@@ -94,6 +94,8 @@ _SIGNATURES = {
     "sponet_native_event_counts": (C.c_int, [_u64, _i64, _i64, _vp, _i64, _f64, _vp, _vp]),
     "sponet_opinion_shares": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "sponet_moments": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "sponet_interfaces": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "sponet_propensities": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -168,3 +168,75 @@ class CompositeCollectiveVariable:
 
             out = torch.cat([p if hasattr(p, "data_ptr") else torch.as_tensor(p, device=xs.device) for p in parts], dim=1)
         return out[0] if was_1d else out
+
+
+def _host_states(x):
+    xs, was_1d = _as_2d(x)
+    if not isinstance(xs, np.ndarray):
+        xs = xs.cpu().numpy()
+    return np.ascontiguousarray(xs), was_1d
+
+
+class Interfaces:
+    """Number of edges between an agent of opinion 0 and one of opinion 1 (collective_variables.py:259-305).
+
+    Only for two opinions.  ``normalize`` divides by the number of edges.  The count runs on the GPU
+    over the CSR of ``network`` (``sponet_interfaces``).
+    """
+
+    def __init__(self, network, normalize: bool = False):
+        from .engine import GraphCache
+        from .utils import calculate_neighbor_list
+
+        self.dimension = 1
+        self.normalize = normalize
+        self.network = network
+        self._neighbor_list = calculate_neighbor_list(network)
+        self._graphs = GraphCache()
+
+    def __call__(self, x):
+        xs, was_1d = _host_states(x)
+        if xs.size and np.max(xs) > 1:
+            raise ValueError("Interfaces can only be used for 2 opinions.")
+        xs = xs.astype(np.uint8, copy=False)
+        out = np.empty((xs.shape[0], 1), dtype=np.float64)
+        g = self._graphs.get(self._neighbor_list)
+        _lib.check(_lib.lib().sponet_interfaces(g.handle, _lib.ptr(xs), xs.shape[0], _lib.ptr(out), None))
+        if self.normalize:
+            out /= self.network.number_of_edges()
+        return out[0] if was_1d else out
+
+
+class Propensities:
+    """Cumulative transition rates (prop_01, prop_10) of a 2-opinion CNVM (collective_variables.py:308-397)."""
+
+    def __init__(self, params, normalize: bool = False):
+        from .engine import GraphCache
+
+        self.dimension = 2
+        self.params = params
+        self.normalize = normalize
+        self._graphs = GraphCache()
+
+    def __call__(self, x):
+        xs, was_1d = _host_states(x)
+        if xs.size and np.max(xs) > 1:
+            raise ValueError("Propensities can only be used for 2 opinions.")
+        xs = xs.astype(np.uint8, copy=False)
+        p = self.params
+        r = np.ascontiguousarray(p.r, dtype=np.float64)
+        rt = np.ascontiguousarray(p.r_tilde, dtype=np.float64)
+        out = np.empty((xs.shape[0], 2), dtype=np.float64)
+        if p.network is None:
+            da = float((p.num_agents - 1) ** p.alpha)
+            rc = _lib.lib().sponet_propensities(None, p.num_agents, _lib.ptr(xs), xs.shape[0], None, da, _lib.ptr(r),
+                                                _lib.ptr(rt), _lib.ptr(out), None)
+        else:
+            das = np.ascontiguousarray(np.array([len(nb) for nb in p.network]) ** p.alpha, dtype=np.float64)
+            g = self._graphs.get(p.network)
+            rc = _lib.lib().sponet_propensities(g.handle, p.num_agents, _lib.ptr(xs), xs.shape[0], _lib.ptr(das), 0.0,
+                                                _lib.ptr(r), _lib.ptr(rt), _lib.ptr(out), None)
+        _lib.check(rc)
+        if self.normalize:
+            out /= p.num_agents
+        return out[0] if was_1d else out

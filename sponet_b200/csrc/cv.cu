@@ -72,7 +72,124 @@ __global__ void moments_kernel(const double* __restrict__ x, int64_t R, int64_t 
     sumsq[l] = q;
 }
 
+// One CTA per snapshot, threads stride over the directed CSR entries; every undirected edge is seen from
+// both ends, so the count of differing pairs is halved (exact: the total is even).
+__global__ void __launch_bounds__(CV_THREADS) interfaces_kernel(const uint8_t* __restrict__ x, int64_t n,
+                                                                const int32_t* __restrict__ row_ptr,
+                                                                const int32_t* __restrict__ col,
+                                                                double* __restrict__ out) {
+    __shared__ unsigned long long part[CV_THREADS / 32];
+    const int64_t s = blockIdx.x;
+    const uint8_t* xs = x + s * n;
+    unsigned long long cnt = 0;
+    for (int64_t i = threadIdx.x; i < n; i += CV_THREADS) {
+        const uint8_t xi = xs[i];
+        for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) cnt += (xs[col[e]] != xi);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < CV_THREADS / 32; ++w) t += part[w];
+        out[s] = (double)(t / 2);
+    }
+}
+
+// sponet/collective_variables.py:370-397: for every agent j in state m (n = 1 - m)
+//   out[s, m] += r[m,n] * #{neighbours of j in state n} / degree_alpha[j] + r_tilde[m,n]
+// (complete graph: the neighbour count is the global count of n, degree_alpha a scalar).
+// Thread-strided partial sums folded with a fixed tree (the reference sums sequentially over j).
+__global__ void __launch_bounds__(CV_THREADS) propensities_kernel(const uint8_t* __restrict__ x, int64_t n,
+                                                                  const int32_t* __restrict__ row_ptr,
+                                                                  const int32_t* __restrict__ col,
+                                                                  const double* __restrict__ degree_alpha,
+                                                                  double complete_degree_alpha, double r01,
+                                                                  double r10, double rt01, double rt10,
+                                                                  double* __restrict__ out) {
+    __shared__ double acc[2][CV_THREADS];
+    __shared__ unsigned long long ones_s;
+    const int64_t s = blockIdx.x;
+    const uint8_t* xs = x + s * n;
+    const int t = threadIdx.x;
+    if (!row_ptr) {  // complete graph: global count of ones first
+        if (t == 0) ones_s = 0;
+        __syncthreads();
+        unsigned long long c = 0;
+        for (int64_t i = t; i < n; i += CV_THREADS) c += xs[i];
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if ((t & 31) == 0) atomicAdd(&ones_s, c);
+        __syncthreads();
+    }
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t j = t; j < n; j += CV_THREADS) {
+        const uint8_t m = xs[j];
+        const uint8_t other = 1 - m;
+        double cnt, da;
+        if (row_ptr) {
+            int c = 0;
+            for (int32_t e = row_ptr[j]; e < row_ptr[j + 1]; ++e) c += (xs[col[e]] == other);
+            cnt = (double)c;
+            da = degree_alpha[j];
+        } else {
+            cnt = (double)(other ? ones_s : (unsigned long long)n - ones_s);
+            da = complete_degree_alpha;
+        }
+        if (m == 0) a0 += r01 * cnt / da + rt01;
+        else a1 += r10 * cnt / da + rt10;
+    }
+    acc[0][t] = a0;
+    acc[1][t] = a1;
+    __syncthreads();
+    for (int stride = CV_THREADS / 2; stride > 0; stride >>= 1) {
+        if (t < stride) {
+            acc[0][t] += acc[0][t + stride];
+            acc[1][t] += acc[1][t + stride];
+        }
+        __syncthreads();
+    }
+    if (t < 2) out[s * 2 + t] = acc[t][0];
+}
+
 }  // namespace
+
+extern "C" int sponet_interfaces(const sponet_graph* g, const uint8_t* x, int64_t S, double* out,
+                                 void* cuda_stream) {
+    SP_REQUIRE(g && x && out && S >= 0, "interfaces: bad arguments");
+    if (S == 0) return SPONET_OK;
+    SP_REQUIRE(S < ((int64_t)1 << 31), "interfaces: too many snapshots for one launch");
+    SpScratch sc((cudaStream_t)cuda_stream);
+    const uint8_t* d_x;
+    double* d_out;
+    SP_CUDA(sc.in(x, (size_t)S * g->n, &d_x));
+    SP_CUDA(sc.out(out, (size_t)S, &d_out));
+    interfaces_kernel<<<(unsigned)S, CV_THREADS, 0, sc.stream>>>(d_x, g->n, g->d_row_ptr, g->d_col, d_out);
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(sc.finish());
+    return SPONET_OK;
+}
+
+extern "C" int sponet_propensities(const sponet_graph* g, int64_t num_agents, const uint8_t* x, int64_t S,
+                                   const double* degree_alpha, double complete_degree_alpha,
+                                   const double* r, const double* r_tilde, double* out, void* cuda_stream) {
+    SP_REQUIRE(x && out && r && r_tilde && S >= 0 && num_agents >= 1, "propensities: bad arguments");
+    SP_REQUIRE(!g || (g->n == num_agents && degree_alpha), "propensities: graph / degree_alpha mismatch");
+    if (S == 0) return SPONET_OK;
+    SP_REQUIRE(S < ((int64_t)1 << 31), "propensities: too many snapshots for one launch");
+    SpScratch sc((cudaStream_t)cuda_stream);
+    const uint8_t* d_x;
+    const double* d_da = nullptr;
+    double* d_out;
+    SP_CUDA(sc.in(x, (size_t)S * num_agents, &d_x));
+    if (g) SP_CUDA(sc.in(degree_alpha, (size_t)num_agents, &d_da));
+    SP_CUDA(sc.out(out, (size_t)S * 2, &d_out));
+    propensities_kernel<<<(unsigned)S, CV_THREADS, 0, sc.stream>>>(
+        d_x, num_agents, g ? g->d_row_ptr : nullptr, g ? g->d_col : nullptr, d_da, complete_degree_alpha,
+        r[1], r[2], r_tilde[1], r_tilde[2], d_out);
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(sc.finish());
+    return SPONET_OK;
+}
 
 extern "C" int sponet_opinion_shares(const uint8_t* x, int64_t S, int64_t n, int32_t M,
                                      const double* weights, double* out, void* cuda_stream) {

@@ -229,3 +229,38 @@ def test_sample_moments_and_steady_state():
     p2 = CNVMParameters(num_opinions=2, num_agents=100, r=1, r_tilde=0.2)
     est = estimate_steady_state(p2, OpinionShares(2, normalize=True), tol_abs=0.05, rng=np.random.default_rng(3), verbose=False)
     assert est.shape == (2,) and abs(est.sum() - 1) < 1e-12 and abs(est[0] - 0.5) < 0.2
+
+
+def test_interfaces_and_propensities_known_answers():
+    """values from the reference's own Interfaces / Propensities classes."""
+    import networkx as nx
+
+    from sponet_b200 import CNVMParameters, Interfaces
+    from sponet_b200.collective_variables import Propensities
+
+    g = load_golden("cv2_known_answers")
+    rp, col, x = g["row_ptr"], g["col"], g["x"]
+    nl = [np.ascontiguousarray(col[rp[i]:rp[i + 1]]) for i in range(120)]
+    net = nx.Graph()
+    net.add_nodes_from(range(120))
+    net.add_edges_from((i, int(j)) for i in range(120) for j in nl[i] if i < j)
+    assert net.number_of_edges() == int(g["num_edges"])
+    np.testing.assert_array_equal(Interfaces(net)(x), g["interfaces"])  # integer counts: exact
+    np.testing.assert_array_equal(Interfaces(net, True)(x), g["interfaces_norm"])
+    np.testing.assert_array_equal(Interfaces(net)(x[0]), g["interfaces_1d"])
+    with pytest.raises(ValueError, match="2 opinions"):
+        Interfaces(net)(x + 1)
+    for alpha in (1.0, 0.5, 0.0):
+        p = CNVMParameters(num_opinions=2, network=nl, r=g["r"], r_tilde=g["r_tilde"], alpha=alpha)
+        # float sums in a fixed tree order vs the reference's sequential order: 1e-13 relative
+        np.testing.assert_allclose(Propensities(p)(x), g[f"prop_net_a{alpha}"], rtol=1e-13)
+        np.testing.assert_allclose(Propensities(p, True)(x), g[f"prop_net_norm_a{alpha}"], rtol=1e-13)
+        pc = CNVMParameters(num_opinions=2, num_agents=120, r=g["r"], r_tilde=g["r_tilde"], alpha=alpha)
+        np.testing.assert_allclose(Propensities(pc)(x), g[f"prop_complete_a{alpha}"], rtol=1e-13)
+    # usable as collective variable of the ensemble driver (evaluated from device-resident slabs)
+    from sponet_b200 import sample_many_runs
+
+    p = CNVMParameters(num_opinions=2, network=nl, r=1.0, r_tilde=0.02)
+    _, c = sample_many_runs(p, x[0], 1.0, 3, 4, collective_variable=Interfaces(net), rng=np.random.default_rng(0))
+    _, xs = sample_many_runs(p, x[0], 1.0, 3, 4, rng=np.random.default_rng(0))
+    np.testing.assert_array_equal(c, Interfaces(net)(xs.reshape(-1, 120)).reshape(4, 3, 1))
