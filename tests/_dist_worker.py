@@ -1,0 +1,55 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU (torchrun), NCCL.  Checks that the sharded
+ensemble equals the single-GPU ensemble bit for bit and that the all-reduced moments match."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from sponet_b200 import CNVMParameters, OpinionShares, sample_many_runs, sample_moments  # noqa: E402
+from sponet_b200 import multiprocessing as smp  # noqa: E402
+from sponet_b200 import workloads  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    params, x0, _ = workloads.headline_cnvm(3000)
+    cv = OpinionShares(3, normalize=True)
+    R, T = 37, 6
+
+    # sharded over the ranks, gathered: every rank holds the full result
+    _, c_dist = sample_many_runs(params, x0, 2.0, T, R, collective_variable=cv, rng=np.random.default_rng(5))
+    _, x_dist = sample_many_runs(params, x0, 1.0, 3, 5, rng=np.random.default_rng(6))
+    _, m_dist, v_dist, n_dist = sample_moments(params, x0, 2.0, T, 64, rel_tol=1e9, collective_variable=cv,
+                                               rng=np.random.default_rng(7))
+
+    # the same calls on ONE GPU (sharding switched off locally)
+    real = smp._dist
+    smp._dist = lambda: (0, 1)
+    import sponet_b200.sample_moments as sm
+
+    sm._dist = smp._dist
+    _, c_one = sample_many_runs(params, x0, 2.0, T, R, collective_variable=cv, rng=np.random.default_rng(5))
+    _, x_one = sample_many_runs(params, x0, 1.0, 3, 5, rng=np.random.default_rng(6))
+    _, m_one, v_one, n_one = sample_moments(params, x0, 2.0, T, 64, rel_tol=1e9, collective_variable=cv,
+                                            rng=np.random.default_rng(7))
+    smp._dist = real
+    sm._dist = real
+
+    assert c_dist.shape == (R, T, 3) and np.array_equal(c_dist, c_one), "sharded CV ensemble differs"
+    assert np.array_equal(x_dist, x_one), "sharded state ensemble differs"
+    assert n_dist == n_one == 64
+    assert np.array_equal(m_dist, m_one) and np.array_equal(v_dist, v_one), "all-reduced moments differ"
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST_OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
