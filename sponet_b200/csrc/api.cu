@@ -106,11 +106,30 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     }
     for (int64_t e = 0; e < nnz; ++e)
         SP_REQUIRE(col[e] >= 0 && col[e] < n, "graph_create: neighbour index %d out of range", col[e]);
+    // padded copy: rows aligned to 16 bytes
+    std::vector<int2> row4(n);
+    int64_t n4 = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        row4[i] = make_int2((int)n4, row[i].y);
+        n4 += (row[i].y + 3) / 4;
+    }
+    SP_REQUIRE(n4 < ((int64_t)1 << 31), "graph_create: network too large");
+    std::vector<int4> col4((size_t)std::max<int64_t>(n4, 1), make_int4(-1, -1, -1, -1));
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t* dst = reinterpret_cast<int32_t*>(col4.data() + row4[i].x);
+        for (int32_t k = 0; k < row[i].y; ++k) dst[k] = col[row[i].x + k];
+    }
     sponet_graph* g = new sponet_graph();
+    g->n_col4 = n4;
     g->n = n;
     g->nnz = nnz;
     g->min_degree = dmin;
     g->max_degree = dmax;
+    g->d_row_ptr = nullptr;
+    g->d_row = nullptr;
+    g->d_col = nullptr;
+    g->d_row4 = nullptr;
+    g->d_col4 = nullptr;
     cudaError_t e = cudaGetDevice(&g->device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row_ptr, (n + 1) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row, n * sizeof(int2));
@@ -118,10 +137,16 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     if (e == cudaSuccess) e = cudaMemcpy(g->d_row_ptr, row_ptr, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_row, row.data(), n * sizeof(int2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && nnz) e = cudaMemcpy(g->d_col, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row4, n * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col4, col4.size() * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_row4, row4.data(), n * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_col4, col4.data(), col4.size() * sizeof(int4), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(g->d_row_ptr);
         cudaFree(g->d_row);
         cudaFree(g->d_col);
+        cudaFree(g->d_row4);
+        cudaFree(g->d_col4);
         delete g;
         cudaGetLastError();
         return sponet_fail(SPONET_ERR_CUDA, "graph_create: %s", cudaGetErrorString(e));
@@ -138,6 +163,8 @@ extern "C" int sponet_graph_destroy(sponet_graph* g) {
     cudaFree(g->d_row_ptr);
     cudaFree(g->d_row);
     cudaFree(g->d_col);
+    cudaFree(g->d_row4);
+    cudaFree(g->d_col4);
     if (cur != g->device) cudaSetDevice(cur);
     delete g;
     return SPONET_OK;

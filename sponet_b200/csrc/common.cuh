@@ -47,6 +47,11 @@ struct sponet_graph {
     int32_t* d_row_ptr;  // [n+1]
     int2* d_row;         // [n] (begin, degree): one 8-byte gather per agent instead of two
     int32_t* d_col;      // [nnz]
+    // Row-scanning kernels (CNTM) read whole rows: a second copy with every row padded to a multiple
+    // of four entries (-1 sentinels) so that a lane fetches four neighbours per 16-byte load.
+    int2* d_row4;        // [n] (first int4 index, degree)
+    int4* d_col4;        // [sum_i ceil(deg_i / 4)]
+    int64_t n_col4;
 };
 
 // ---------------------------------------------------------------------------------------------

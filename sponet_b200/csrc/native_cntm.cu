@@ -1,16 +1,19 @@
-// NATIVE mode, CNTM (noisy threshold model): one warp per chain, state as 1 bit per agent in shared
-// memory.  Each warp step handles 32 consecutive candidate events:
-//   phase 1 (parallel, state-independent): lane l draws event l (Philox), fetches its agent's CSR
-//            row descriptor and turns both thresholds into integer "minimum opposite-neighbour
-//            counts" with the reference's own float64 division (cntm/model.py:204-207);
-//   phase 2 (parallel): the first 32 neighbour ids of all 32 rows are gathered, one coalesced
-//            row segment per event, into registers -- 32 independent loads in flight per lane;
-//   phase 3 (sequential over the 32 events, because every event may read any earlier flip): the
-//            warp ballots the neighbour bits from shared memory, compares the popcount with the
-//            precomputed minimum and flips the agent's bit.  Rows longer than 32 (BA hubs) stream
-//            the rest of the row inline.
-// The sequential statement this must reproduce bit for bit is oracle/oracle_native.inc
-// (oracle_cntm_native).
+// NATIVE mode, CNTM (noisy threshold model): one warp per chain, 1 bit per agent in shared memory,
+// 32 consecutive candidate events per warp step -- the same scheme as the CNVM kernel
+// (native_cnvm.cu), with a row SCAN where the voter model has a single neighbour gather:
+//   stage 1  Philox draw -> agent, noise flag, noise bit; row descriptor gather issued
+//   stage 2  the first two 16-byte segments of the agent's (padded) neighbour row gathered
+//   scan     every lane walks its own row: neighbour bits from shared memory, popcount of the
+//            opposite opinion, compared with the precomputed minimum count for (threshold, degree)
+//            -- the reference's float64 `count / deg >= threshold` (cntm/model.py:204-207) turned into
+//            an exact integer table on the host.  The same pass probes the warp's Bloom filter with
+//            every neighbour id: a hit means the neighbour may be ANOTHER lane's agent in this step
+//   commit   dependency masks only for flagged lanes (exact, by re-walking the flagged lane's row);
+//            hazard = dep & ballot(lanes that flip); lanes before the first hazard flip their bit
+//            (atomicXor), the rest re-scan against the updated state
+// Stages 1 and 2 of the next two steps are issued before the current scan (pipeline of depth 2,
+// unrolled three ways).  The sequential statement this must reproduce bit for bit is
+// oracle/oracle_native.inc (oracle_cntm_native).
 #include <algorithm>
 
 #include "common.cuh"
@@ -25,15 +28,15 @@ namespace {
 
 struct NativeCntmArgs {
     int32_t n;
-    const int2* row;
-    const int32_t* col;
+    const int2* row4;  // (first int4 index, degree)
+    const int4* col4;  // rows padded to multiples of four, -1 sentinels
     uint32_t noise_thr;
-    double threshold_01, threshold_10;
+    const int32_t* need01;  // [max_degree + 1] minimum count of ones for a 0 -> 1 flip (INT_MAX = never)
+    const int32_t* need10;  // [max_degree + 1] minimum count of zeros for a 1 -> 0 flip
     const uint8_t* x_init;
     const int64_t* counts;
     int64_t S, nrun, R_total, run_begin;
     int32_t T;
-    uint64_t seed;
     uint8_t* out_x;
     double* out_cv;
     unsigned long long* out_sum;
@@ -45,18 +48,9 @@ struct NativeCntmArgs {
     uint32_t* gstate;
     int32_t words;
     int32_t warps_per_cta;
+    int32_t bloom_words;
+    uint32_t rk[20];
 };
-
-// smallest c in [0, deg] with (double)c / (double)deg >= thr  (deg + 1 when there is none)
-__device__ __forceinline__ int min_count(double thr, int deg) {
-    if (deg <= 0) return 0x7fffffff;
-    if (!(thr > 0.0)) return (0.0 >= thr) ? 0 : 0x7fffffff;  // thr <= 0 -> always; NaN -> never
-    double g = ceil(thr * (double)deg);
-    int c = g > (double)deg + 1.0 ? deg + 1 : (int)g;
-    while (c > 0 && __ddiv_rn((double)(c - 1), (double)deg) >= thr) --c;
-    while (c <= deg && !(__ddiv_rn((double)c, (double)deg) >= thr)) ++c;
-    return c;
-}
 
 template <bool SMEM>
 __device__ __forceinline__ uint32_t st_load(const uint32_t* p) {
@@ -66,21 +60,36 @@ __device__ __forceinline__ uint32_t st_load(const uint32_t* p) {
 
 template <bool SMEM>
 __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
+    constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = (uint32_t)A.n;
-    uint32_t* state = SMEM ? smem + (size_t)warp * A.words
+    const uint32_t noise_thr = A.noise_thr;
+    const uint32_t lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
+
+    // shared layout: [bloom W*bloom_words] [states W*words (if SMEM)]
+    uint32_t* sp = smem;
+    const uint32_t bloom_bits = (uint32_t)A.bloom_words * 32u;
+    uint32_t* bloom = sp + (size_t)warp * A.bloom_words;
+    for (int i = threadIdx.x; i < A.warps_per_cta * A.bloom_words; i += blockDim.x) sp[i] = 0u;
+    sp += (size_t)A.warps_per_cta * A.bloom_words;
+    uint32_t* state = SMEM ? sp + (size_t)warp * A.words
                            : A.gstate + ((size_t)blockIdx.x * A.warps_per_cta + warp) * A.words;
+    __syncthreads();
+
     const int64_t total_warps = (int64_t)gridDim.x * A.warps_per_cta;
     const int64_t num_chains = A.S * A.nrun;
     const int T = A.T;
-    unsigned long long ev_total = 0, acc_total = 0, step_total = 0;
+    unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_total = 0;
 
     for (int64_t cl = (int64_t)blockIdx.x * A.warps_per_cta + warp; cl < num_chains; cl += total_warps) {
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
+        const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;
         const uint8_t* x0 = A.x_init + j * (int64_t)n;
-        int c1 = 0;
+        const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
+
+        int c1 = 0;  // number of ones (warp-uniform, exact at snapshots)
         for (int w = lane; w < A.words; w += 32) {
             uint32_t packed = 0;
             const uint32_t base = (uint32_t)w * 32;
@@ -92,90 +101,22 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
             c1 += __popc(packed);
             state[w] = packed;
         }
-        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c1 = __reduce_add_sync(FULL, c1);
         if (!SMEM) __threadfence_block();
         __syncwarp();
 
-        uint64_t e_base = 0;
-        for (int k = 0; k < T; ++k) {
-            if (k > 0) {
-                int64_t K = A.counts[cl * (int64_t)(T - 1) + (k - 1)];
-                while (K > 0) {
-                    const int nb = K < 32 ? (int)K : 32;
-                    // ---- phase 1 ----
-                    const uint4 r = sp_native_draw(A.seed, chain, 0u, e_base + (uint64_t)lane);
-                    const uint32_t my_a = __umulhi(r.y, n);
-                    const bool my_noise = r.x < A.noise_thr;
-                    const uint32_t my_bit = r.z >> 31;
-                    int2 my_row = make_int2(0, 0);
-                    int my_need01 = 0x7fffffff, my_need10 = 0x7fffffff;
-                    if (!my_noise && lane < nb) {
-                        my_row = __ldg(A.row + my_a);
-                        my_need01 = min_count(A.threshold_01, my_row.y);
-                        my_need10 = min_count(A.threshold_10, my_row.y);
-                    }
-                    // ---- phase 2: gather the first 32 neighbours of every event's row ----
-                    uint32_t nbv[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int beg = __shfl_sync(0xffffffffu, my_row.x, e);
-                        const int deg = __shfl_sync(0xffffffffu, my_row.y, e);
-                        nbv[e] = (lane < deg) ? (uint32_t)__ldg(A.col + beg + lane) : 0xFFFFFFFFu;
-                    }
-                    // ---- phase 3: apply the events in order ----
-                    int flips = 0;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        if (e < nb) {  // warp-uniform
-                            const uint32_t a = __shfl_sync(0xffffffffu, my_a, e);
-                            const uint32_t info = __shfl_sync(
-                                0xffffffffu, (uint32_t)my_noise | (my_bit << 1), e);
-                            const uint32_t wa = a >> 5, ba = a & 31;
-                            const uint32_t xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
-                            uint32_t nw = xa;
-                            if (info & 1u) {
-                                nw = info >> 1;
-                            } else {
-                                const int deg = __shfl_sync(0xffffffffu, my_row.y, e);
-                                if (deg > 0) {
-                                    const uint32_t other = xa ^ 1u;
-                                    const uint32_t v = nbv[e];
-                                    bool hit = false;
-                                    if (v != 0xFFFFFFFFu)
-                                        hit = ((st_load<SMEM>(state + (v >> 5)) >> (v & 31)) & 1u) == other;
-                                    int cnt = __popc(__ballot_sync(0xffffffffu, hit));
-                                    if (deg > 32) {  // hub row: stream the remainder
-                                        const int beg = __shfl_sync(0xffffffffu, my_row.x, e);
-                                        for (int off = 32; off < deg; off += 32) {
-                                            bool h2 = false;
-                                            if (off + lane < deg) {
-                                                const uint32_t u = (uint32_t)__ldg(A.col + beg + off + lane);
-                                                h2 = ((st_load<SMEM>(state + (u >> 5)) >> (u & 31)) & 1u) == other;
-                                            }
-                                            cnt += __popc(__ballot_sync(0xffffffffu, h2));
-                                        }
-                                    }
-                                    const int need = __shfl_sync(0xffffffffu, xa ? my_need10 : my_need01, e);
-                                    if (cnt >= need) nw = other;
-                                }
-                            }
-                            if (nw != xa) {  // warp-uniform
-                                if (lane == 0) state[wa] = st_load<SMEM>(state + wa) ^ (1u << ba);
-                                c1 += (int)nw - (int)xa;
-                                ++flips;
-                                if (!SMEM) __threadfence_block();
-                            }
-                            __syncwarp();
-                        }
-                    }
-                    acc_total += flips;
-                    ++step_total;
-                    ev_total += nb;
-                    e_base += nb;
-                    K -= nb;
-                }
-            }
-            // ---- snapshot k ----
+        int my_delta = 0;  // per-lane change of the number of ones since the last snapshot
+        uint32_t my_acc = 0, n_steps = 0, n_events = 0, n_extra = 0;
+        int ksnap = 0;
+        auto snapshot = [&]() {
+            c1 += __reduce_add_sync(FULL, my_delta);
+            acc_total += __reduce_add_sync(FULL, my_acc);
+            ev_total += n_events;
+            step_total += n_steps;
+            extra_total += n_extra;
+            my_delta = 0;
+            my_acc = n_events = n_steps = n_extra = 0;
+            const int k = ksnap++;
             const int64_t snap = cl * (int64_t)T + k;
             if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
@@ -194,14 +135,223 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
                 for (uint32_t a = lane; a < n; a += 32)
                     dst[a] = (uint8_t)((st_load<SMEM>(state + (a >> 5)) >> (a & 31)) & 1u);
             }
+        };
+
+        // ---- step generator (same as the CNVM kernel) ----
+        int gk = 1;
+        int64_t gK = 0;
+        uint64_t ge = 0;
+        bool gdone = (T <= 1);
+        snapshot();
+        if (!gdone) {
+            gK = kcounts[0];
+            while (gK == 0) {
+                snapshot();
+                if (++gk >= T) { gdone = true; break; }
+                gK = kcounts[gk - 1];
+            }
         }
+        auto gen = [&](uint64_t& e0, int& nb, int& snaps) -> bool {
+            e0 = ge;
+            snaps = 0;
+            nb = 0;
+            if (gdone) return false;
+            nb = gK < 32 ? (int)gK : 32;
+            ge += (uint64_t)nb;
+            gK -= nb;
+            if (gK == 0) {
+                snaps = 1;
+                for (;;) {
+                    if (++gk >= T) { gdone = true; break; }
+                    gK = kcounts[gk - 1];
+                    if (gK > 0) break;
+                    ++snaps;
+                }
+            }
+            return true;
+        };
+
+        uint32_t q_a[3], q_meta[3];
+        int2 q_row[3];
+        int4 q_c0[3], q_c1[3];
+        int q_nb[3], q_snaps[3];
+        bool q_valid[3];
+        const int4 none = make_int4(-1, -1, -1, -1);
+
+        auto issue1 = [&](int s, uint64_t e0) {
+            const uint64_t e = e0 + (uint64_t)lane;
+            const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
+            const uint32_t a = __umulhi(r.y, n);
+            q_a[s] = a;
+            q_meta[s] = (uint32_t)(r.x < noise_thr) | ((r.z >> 31) << 1);  // bit 0 noise, bit 1 the noise opinion
+            q_row[s] = __ldg(A.row4 + a);
+        };
+        auto issue2 = [&](int s) {
+            const int chunks = (q_row[s].y + 3) >> 2;
+            q_c0[s] = chunks > 0 ? __ldg(A.col4 + q_row[s].x) : none;
+            q_c1[s] = chunks > 1 ? __ldg(A.col4 + q_row[s].x + 1) : none;
+        };
+
+        {
+            uint64_t e0;
+            q_valid[0] = gen(e0, q_nb[0], q_snaps[0]);
+            issue1(0, e0);
+            issue2(0);
+            q_valid[1] = gen(e0, q_nb[1], q_snaps[1]);
+            issue1(1, e0);
+            q_valid[2] = false;
+            q_a[2] = q_meta[2] = 0u;
+            q_row[2] = make_int2(0, 0);
+        }
+
+        bool running = true;
+        while (running) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int cur = u, nx1 = (u + 1) % 3, nx2 = (u + 2) % 3;
+                if (!q_valid[cur]) { running = false; break; }
+                if (q_valid[nx1]) issue2(nx1);
+                {
+                    uint64_t e0;
+                    q_valid[nx2] = gen(e0, q_nb[nx2], q_snaps[nx2]);
+                    if (q_valid[nx2]) issue1(nx2, e0);
+                }
+
+                const uint32_t a = q_a[cur], meta = q_meta[cur];
+                const bool noise = meta & 1u;
+                const int2 row = q_row[cur];
+                const int deg = noise ? 0 : row.y;  // a noise event reads no neighbour
+                const int chunks = (deg + 3) >> 2;
+                const int nb = q_nb[cur];
+                const bool active = lane < nb;
+                const uint32_t wa = a >> 5, ba = a & 31;
+
+                // opposite-opinion count over the lane's row; PROBE also tests the Bloom filter
+                uint32_t xa, nw;
+                bool hit = false;
+                auto scan = [&](bool probe) {
+                    xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
+                    const uint32_t other = xa ^ 1u;
+                    int cnt = 0;
+                    auto one = [&](int v) {
+                        const bool ok = v >= 0;
+                        const uint32_t vv = ok ? (uint32_t)v : 0u;
+                        const uint32_t bitv = (st_load<SMEM>(state + (vv >> 5)) >> (vv & 31)) & 1u;
+                        cnt += (int)(ok & (bitv == other));
+                        if (probe && bloom_bits) {
+                            const uint32_t h = __umulhi(vv * 2654435761u, bloom_bits);
+                            hit |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
+                        }
+                    };
+                    auto four = [&](const int4& v) { one(v.x); one(v.y); one(v.z); one(v.w); };
+                    if (chunks > 0) four(q_c0[cur]);
+                    if (chunks > 1) four(q_c1[cur]);
+                    for (int c = 2; c < chunks; ++c) four(__ldg(A.col4 + row.x + c));
+                    if (noise) {
+                        nw = meta >> 1;
+                    } else {
+                        const int need = deg > 0 ? __ldg((xa ? A.need10 : A.need01) + deg) : 0x7fffffff;
+                        nw = cnt >= need ? other : xa;
+                    }
+                };
+
+                // ---- Bloom insert of the agents, first scan with probes ----
+                uint32_t flagged;
+                if (bloom_bits) {
+                    const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
+                    const uint32_t bit = 1u << (ha & 31);
+                    hit = atomicOr(bloom + (ha >> 5), bit) & bit;  // an equal agent (or a collision)
+                    __syncwarp();
+                    scan(true);
+                    flagged = __ballot_sync(FULL, hit);
+                    bloom[ha >> 5] = 0u;
+                } else {
+                    scan(false);
+                    flagged = FULL;
+                }
+                // exact masks for flagged lanes: earlier lanes whose agent is this lane's agent or one of
+                // its neighbours (the flagged lane's row is re-walked by the whole warp)
+                uint32_t dep = 0;
+                for (uint32_t f = flagged; f; f &= f - 1) {
+                    const int il = __ffs(f) - 1;
+                    const uint32_t ai = __shfl_sync(FULL, a, il);
+                    const int rx = __shfl_sync(FULL, row.x, il), ch = __shfl_sync(FULL, chunks, il);
+                    const uint32_t same_a = __ballot_sync(FULL, a == ai);
+                    uint32_t touch = same_a;
+                    for (int c = 0; c < ch; ++c) {
+                        const int4 v = __ldg(A.col4 + rx + c);
+                        touch |= __ballot_sync(FULL, ((int)a == v.x) | ((int)a == v.y) | ((int)a == v.z) | ((int)a == v.w));
+                    }
+                    if (a == ai) dep |= same_a & lane_lt;
+                    if (lane == il) dep |= touch & lane_lt;
+                }
+
+                // ---- commit ----
+                bool chg = active && nw != xa;
+                uint32_t hmask = 0;
+                if (flagged) {
+                    const uint32_t wmask = __ballot_sync(FULL, chg);
+                    hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
+                }
+                if (hmask == 0) {
+                    if (chg) {
+                        atomicXor(state + wa, 1u << ba);
+                        my_delta += (int)nw - (int)xa;
+                        ++my_acc;
+                    }
+                    if (!SMEM) __threadfence_block();
+                    __syncwarp();
+                } else {
+                    bool pending = active;
+                    for (;;) {
+                        const int first = hmask ? (__ffs(hmask) - 1) : 32;
+                        const bool commit = chg && lane < first;
+                        if (commit) {
+                            atomicXor(state + wa, 1u << ba);
+                            my_delta += (int)nw - (int)xa;
+                            ++my_acc;
+                        }
+                        pending = pending && lane >= first;
+                        if (!SMEM) __threadfence_block();
+                        __syncwarp();
+                        if (first == 32) break;
+                        ++n_extra;
+                        scan(false);  // every lane re-scans (cheap relative to how rare this is)
+                        chg = pending && nw != xa;
+                        const uint32_t wmask = __ballot_sync(FULL, chg);
+                        hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
+                    }
+                }
+                ++n_steps;
+                n_events += (uint32_t)nb;
+                for (int q = 0; q < q_snaps[cur]; ++q) snapshot();
+            }
+        }
+        c1 += __reduce_add_sync(FULL, my_delta);
+        acc_total += __reduce_add_sync(FULL, my_acc);
+        ev_total += n_events;
+        step_total += n_steps;
+        extra_total += n_extra;
         __syncwarp();
     }
     if (lane == 0 && A.counters) {
         atomicAdd(A.counters + 0, ev_total);
         atomicAdd(A.counters + 1, acc_total);
         atomicAdd(A.counters + 2, step_total);
+        atomicAdd(A.counters + 3, extra_total);
     }
+}
+
+// smallest c in [0, deg] with (double)c / (double)deg >= thr  (INT_MAX when there is none): the
+// reference's `share_other_opinion >= threshold` with share = count / len(neighbors), made integer.
+int32_t min_count(double thr, int deg) {
+    if (deg <= 0) return 0x7fffffff;
+    if (!(thr > 0.0)) return (0.0 >= thr) ? 0 : 0x7fffffff;  // thr <= 0 -> always; NaN -> never
+    double g = std::ceil(thr * (double)deg);
+    int c = g > (double)deg + 1.0 ? deg + 1 : (int)g;
+    while (c > 0 && (double)(c - 1) / (double)deg >= thr) --c;
+    while (c <= deg && !((double)c / (double)deg >= thr)) ++c;
+    return c > deg ? 0x7fffffff : c;
 }
 
 template <bool SMEM>
@@ -242,11 +392,22 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     SpScratch sc((cudaStream_t)cuda_stream);
     NativeCntmArgs A{};
     A.n = (int32_t)n;
-    A.row = g->d_row;
-    A.col = g->d_col;
+    A.row4 = g->d_row4;
+    A.col4 = g->d_col4;
     A.noise_thr = sp_prob_to_thr(p->noise_prob);
-    A.threshold_01 = p->threshold_01;
-    A.threshold_10 = p->threshold_10;
+    {
+        std::vector<int32_t> need((size_t)2 * (g->max_degree + 1));
+        for (int d = 0; d <= g->max_degree; ++d) {
+            need[d] = min_count(p->threshold_01, d);
+            need[g->max_degree + 1 + d] = min_count(p->threshold_10, d);
+        }
+        int32_t* d_need;
+        SP_CUDA(sc.alloc((void**)&d_need, need.size() * sizeof(int32_t)));
+        SP_CUDA(cudaMemcpyAsync(d_need, need.data(), need.size() * sizeof(int32_t), cudaMemcpyHostToDevice, sc.stream));
+        SP_CUDA(cudaStreamSynchronize(sc.stream));
+        A.need01 = d_need;
+        A.need10 = d_need + g->max_degree + 1;
+    }
     SpCvDev cvd;
     SP_TRY(sp_stage_cv(sc, cv, 2, &cvd));
     A.D = cvd.D;
@@ -257,7 +418,10 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.R_total = o->num_runs_total;
     A.run_begin = o->run_begin;
     A.T = (int32_t)T;
-    A.seed = o->seed;
+    for (int r = 0; r < 10; ++r) {
+        A.rk[2 * r] = (uint32_t)o->seed + (uint32_t)r * 0x9E3779B9u;
+        A.rk[2 * r + 1] = (uint32_t)(o->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     SP_CUDA(sc.in(x_init, (size_t)S * n, &A.x_init));
     const double* d_t;
     SP_CUDA(sc.in(t_eval, (size_t)T, &d_t));
@@ -281,11 +445,12 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.words = (int32_t)((n + 31) / 32);
     cudaDeviceProp prop;
     SP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
     bool smem_state = !o->force_global_state;
     int warps = 0;
     if (smem_state) {
-        warps = (int)std::min<size_t>(16, (prop.sharedMemPerBlockOptin - 64) / chain_bytes);
+        warps = (int)std::min<size_t>(16, (smem_max - 64) / chain_bytes);
         if (warps < 1) smem_state = false;
     }
     size_t smem_bytes = 0;
@@ -295,6 +460,14 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
         smem_bytes = chain_bytes * warps;
     } else {
         warps = 8;
+    }
+    {   // Bloom filter per warp from the spare shared memory: a lane probes ~deg neighbours per step, so
+        // the flag rate is ~32 * <deg> / bits; up to 64 Kbit, no more than ~N/2 bits for small chains
+        const size_t spare = smem_max > smem_bytes + 64 ? (smem_max - smem_bytes - 64) / warps : 0;
+        size_t words = std::min<size_t>(spare / 4, 2048);
+        words = std::min<size_t>(words, std::max<size_t>(64, (size_t)n / 64));
+        A.bloom_words = words >= 32 ? (int32_t)words : 0;
+        smem_bytes += (size_t)A.bloom_words * 4 * warps;
     }
     A.warps_per_cta = warps;
     const int threads = warps * 32;

@@ -58,3 +58,23 @@ def ba_cntm(num_agents: int = 100_000, m: int = 5, seed: int = 1):
     params = CNTMParameters(network=g, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5)
     x_init = np.random.default_rng(0).integers(0, 2, num_agents).astype(np.uint8)
     return params, x_init, num_agents * (params.r + params.r_tilde)
+
+
+def sis_ws(num_agents: int = 1_000_000, infection_rate: float = 1.0, seed: int = 7):
+    """Config 4: SIS written as a CNVM (examples/SIS_model.py:77-80,108-112) on a Watts-Strogatz ring
+    (k = 10, p = 0.1): r = [[0, lambda], [0, 0]], r_tilde = [[0, 0], [1, 0]], 30 % infected initially."""
+    import networkx as nx
+
+    from .cnvm import CNVMParameters
+    from .utils import calculate_neighbor_list
+
+    g = nx.connected_watts_strogatz_graph(num_agents, 10, 0.1, seed=seed) if num_agents <= 20_000 else \
+        nx.watts_strogatz_graph(num_agents, 10, 0.1, seed=seed)  # k = 10 ring + rewiring never isolates a node
+    r = np.array([[0.0, infection_rate], [0.0, 0.0]])
+    rt = np.array([[0.0, 0.0], [1.0, 0.0]])
+    params = CNVMParameters(num_opinions=2, network=calculate_neighbor_list(g), r=r, r_tilde=rt, alpha=1.0)
+    x_init = np.zeros(num_agents, dtype=np.uint8)
+    x_init[: int(0.3 * num_agents)] = 1
+    np.random.default_rng(0).shuffle(x_init)
+    rate = params.r_imit * num_agents + params.r_noise * num_agents
+    return params, x_init, rate

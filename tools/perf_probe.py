@@ -24,6 +24,10 @@ if a.model == "cnvm":
     params, x0, rate = workloads.headline_cnvm(a.n)
     model = CNVM(params); kind = "cnvm"; M = 3
     struct, keep = model._struct()
+elif a.model == "sis":
+    params, x0, rate = workloads.sis_ws(a.n)
+    model = CNVM(params); kind = "cnvm"; M = 2
+    struct, keep = model._struct()
 elif a.model == "complete":
     params, x0, rate = workloads.complete_cnvm(a.n)
     model = CNVM(params); kind = "cnvm"; M = 2
