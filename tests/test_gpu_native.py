@@ -270,3 +270,57 @@ def test_headline_size_pair_vs_single_and_conservation():
     assert int(counters[0]) == int(sched.sum())
     assert abs(sched.sum() / (R * 0.5 * rate) - 1) < 1e-3  # Poisson totals
     del keep
+
+
+def test_config4_sis_ws_1e6_pair_vs_single():
+    """BASELINE config 4 shape: SIS-as-CNVM on a Watts-Strogatz ring with N = 1e6 (one chain per SM,
+    125 KB of packed state in shared memory).  Pair schedule == single schedule, and the infected share
+    follows the SIS drift."""
+    from sponet_b200 import CNVM, engine, workloads
+
+    n = 1_000_000
+    params, x0, rate = workloads.sis_ws(n, infection_rate=1.0)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    R, T = 200, 3
+    t_eval = np.linspace(0, 0.2, T)
+    spec = (np.array([1], dtype=np.int32), float(n))
+    res = {}
+    for wpc in (1, 2):
+        counters = np.zeros(4, dtype=np.uint64)
+        _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0[None, :], t_eval, 11, R, 0, R, cv_spec=spec,
+                                  want_cv=True, counters=counters, warps_per_chain=wpc)
+        res[wpc] = (cv[0], counters)
+    np.testing.assert_array_equal(res[1][0], res[2][0])
+    np.testing.assert_array_equal(res[1][1][:2], res[2][1][:2])
+    cv = res[2][0]
+    assert np.allclose(cv[:, 0, 0], 0.3)
+    # SIS: infection along edges at rate lambda * (infected neighbours / degree), recovery at rate 1:
+    # d rho/dt = lambda rho (1 - rho) - rho = -0.09 at rho = 0.3, lambda = 1 -> the share decays
+    assert (cv[:, -1, 0] < 0.3).all() and (cv[:, -1, 0] > 0.27).all()
+    assert cv[:, -1, 0].std() < 2e-3  # N = 1e6: runs agree to ~1e-3
+    del keep
+
+
+def test_config3_cntm_ba_1e5_properties():
+    """BASELINE config 3 shape: CNTM on Barabasi-Albert N = 1e5, m = 5.  Shared-memory state == global
+    state results; counts conserved; snapshot 0 is the initial histogram."""
+    from sponet_b200 import CNTM, engine, workloads
+
+    params, x0, rate = workloads.ba_cntm(100_000)
+    model = CNTM(params)
+    R, T = 600, 4
+    t_eval = np.linspace(0, 0.3, T)
+    spec = (np.array([0, 1], dtype=np.int32), 1.0)
+    res = []
+    for force_global in (False, True):
+        counters = np.zeros(4, dtype=np.uint64)
+        _, cv = engine.run_native("cntm", model._graph(), 100_000, model._struct(), x0[None, :], t_eval, 5, R, 0, R,
+                                  cv_spec=spec, want_cv=True, counters=counters, force_global_state=force_global)
+        res.append((cv[0], counters))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1][:2], res[1][1][:2])
+    cv = res[0][0]
+    assert (cv.sum(-1) == 100_000).all()
+    np.testing.assert_array_equal(cv[:, 0], np.broadcast_to(np.bincount(x0, minlength=2), (R, 2)))
+    assert abs(int(res[0][1][0]) / (R * 0.3 * rate) - 1) < 2e-3
