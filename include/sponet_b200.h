@@ -161,7 +161,7 @@ typedef struct {
      * overriding the in-kernel Poisson(dt / next_event_rate) sampler (tests, host-side schedules) */
     const int64_t* event_counts;
     int32_t force_global_state; /* debug/tests: keep chain state in global memory                   */
-    int32_t warps_per_chain;    /* 0 = auto, 1 = one warp per chain, 2 = two warps alternating steps   */
+    int32_t warps_per_chain;    /* 0 = auto, W >= 1: W warps take a chain's steps round-robin (W <= 16) */
                                 /* (CNVM agent-level kernel, shared-memory states only)             */
 } sponet_native_opts;
 

@@ -44,6 +44,7 @@ struct NativeCnvmArgs {
     uint32_t* gstate;  // global chain states (fallback), [total_warps, words]
     int32_t words;     // 32-bit words per chain
     int32_t warps_per_cta;
+    int32_t warps_per_chain;  // RING kernels: warps serving one chain
     int32_t bloom_words;  // per-warp Bloom filter size in 32-bit words (0 = disabled)
     uint32_t rk[20];      // Philox4x32-10 round keys of the seed: (k0 + r*W0, k1 + r*W1), r = 0..9
 };
@@ -78,22 +79,19 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // Stages 1 and 2 of the NEXT two steps are issued before the commit of the current one (software
 // pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies).
 //
-// PAIR mode (large chains: only ~9 fit in an SM's shared memory, i.e. 2.25 warps per scheduler):
-// TWO warps serve one chain and take alternate steps.  Stages 1-3 of a warp's next steps overlap
-// the other warp's commit; the commits themselves stay strictly ordered through a pair of
-// mbarriers (arrive = release after the writes, try_wait = acquire before the reads).
+// RING mode (large chains: only a few fit in an SM's shared memory, i.e. ~2 warps per scheduler):
+// W warps serve one chain and take its steps round-robin (step s belongs to warp s mod W).  Stages
+// 1-3 of a warp's next steps overlap the other warps' commits; the commits themselves stay strictly
+// ordered through a ring of mbarriers, one per warp (arrive = release after the writes, try_wait on
+// the predecessor = acquire before the reads).
 // ---------------------------------------------------------------------------------------------
 #ifndef SP_GUARDS
 #define SP_GUARDS 1  // 1: skip stage 1/2 work of steps past the end of the chain
 #endif
-#ifndef SP_PAIR_ARRIVE_ONE
-#define SP_PAIR_ARRIVE_ONE 0  // PAIR hand-over: 1 = __syncwarp + one arriving lane, 0 = every lane arrives
-#endif
-#ifndef SP_PAIR_MAX_SLOTS
-// A/B on B200 (H workload): 9 slots = 18 warps = 576 threads caps the kernel at 96 registers and spills
-// (4.0e10 events/s); 8 slots = 512 threads keeps 118 registers (6.3e10 vs 5.9e10 for 9 single warps).
-#define SP_PAIR_MAX_SLOTS 8
-#endif
+// A/B on B200 (H workload): 9 chains x 2 warps = 576 threads caps the kernel at 96 registers and spills
+// (4.0e10 events/s); 8 x 2 = 512 threads keeps 118 registers (6.3e10, vs 5.9e10 for 9 single warps).
+// Whether every lane or one lane arrives on the mbarrier makes no measurable difference.
+#define SP_RING_MAX_THREADS 512
 
 __device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -114,12 +112,12 @@ __device__ __forceinline__ void sp_mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void sp_pair_sync(int id) {  // named barrier shared by the two warps of a chain
-    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+__device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named barrier of one chain's warps
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int BITS, bool SMEM, bool CSR, bool ALIAS, bool PAIR>
-__global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
+template <int BITS, bool SMEM, bool CSR, bool ALIAS, bool RING>
+__global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
     constexpr bool PACKCNT = (BITS <= 2);   // M <= 4: count deltas packed per lane, folded lazily
     constexpr bool THR_SMEM = (BITS <= 4);  // M <= 16: threshold tables staged in shared memory
@@ -127,15 +125,16 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = PAIR ? (warp >> 1) : warp;  // chain slot of this warp within the CTA
-    const int role = PAIR ? (warp & 1) : 0;      // PAIR: which of the alternating steps this warp takes
-    const int slots = PAIR ? (A.warps_per_cta >> 1) : A.warps_per_cta;
+    const int W = RING ? A.warps_per_chain : 1;  // warps serving one chain
+    const int slot = RING ? warp / W : warp;     // chain slot of this warp within the CTA
+    const int role = RING ? warp % W : 0;        // RING: this warp takes the steps s with s % W == role
+    const int slots = A.warps_per_cta / W;
     const int M = A.M, MM = M * M;
     const uint32_t n = (uint32_t)A.n;
     const uint32_t noise_thr = A.noise_thr;
     const uint32_t lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
 
-    // shared layout: [thr] [mbarriers slots*2 (PAIR)] [counts slots*M] [bloom warps*bloom_words]
+    // shared layout: [thr] [mbarriers, one per warp (RING)] [counts slots*M] [bloom warps*bloom_words]
     //                [states slots*words (if SMEM)]
     // thr: M <= 4 -> 32 entries indexed (noise << 4 | m << 2 | nw); M <= 16 -> 2*MM entries
     uint32_t* sp = smem;
@@ -152,13 +151,13 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
         thr = sp;
         sp += (2 * MM + 1) & ~1;
     }
-    uint32_t bar_mine = 0, bar_other = 0;
-    if (PAIR) {
-        const uint32_t base = (uint32_t)__cvta_generic_to_shared(sp) + (uint32_t)slot * 16u;
+    uint32_t bar_mine = 0, bar_pred = 0;
+    if (RING) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(sp) + (uint32_t)(slot * W) * 8u;
         bar_mine = base + (uint32_t)role * 8u;
-        bar_other = base + (uint32_t)(role ^ 1) * 8u;
-        if (lane == 0) sp_mbar_init(bar_mine, SP_PAIR_ARRIVE_ONE ? 1u : 32u);
-        sp += (size_t)slots * 4;
+        bar_pred = base + (uint32_t)((role + W - 1) % W) * 8u;
+        if (lane == 0) sp_mbar_init(bar_mine, 32u);
+        sp += (size_t)A.warps_per_cta * 2;
     }
     int32_t* cnt_mem = (int32_t*)sp + slot * M;
     sp += (size_t)slots * M;
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
 
     const int64_t num_chains = A.S * A.nrun;
     unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_total = 0;
-    uint32_t other_done = 0;  // PAIR: completions of the partner warp consumed so far (mbarrier phase)
+    uint32_t pred_base = 0;  // RING: steps the predecessor warp completed in earlier chains (mbarrier phase)
     const int T = A.T;
 
     for (int64_t cl = (int64_t)blockIdx.x * slots + slot; cl < num_chains; cl += (int64_t)gridDim.x * slots) {
@@ -186,11 +185,11 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
         // ---- load + pack the initial state, count opinions ----
         if (role == 0)
             for (int v = lane; v < M; v += 32) cnt_mem[v] = 0;
-        if (PAIR) sp_pair_sync(slot + 1);
+        if (RING) sp_ring_sync(slot + 1, 32 * W);
         else __syncwarp();
         {
             int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            for (int w = role * 32 + lane; w < A.words; w += (PAIR ? 64 : 32)) {
+            for (int w = role * 32 + lane; w < A.words; w += 32 * W) {
                 uint32_t packed = 0;
                 const uint32_t base = (uint32_t)w * P::APW;
 #pragma unroll 4
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
             }
         }
         if (!SMEM) __threadfence_block();
-        if (PAIR) sp_pair_sync(slot + 1);
+        if (RING) sp_ring_sync(slot + 1, 32 * W);
         else __syncwarp();
 
         // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into the
@@ -256,11 +255,8 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
             }
         };
 
-        int ksnap = 0;
-        // emit == false only advances the snapshot index (PAIR: the partner warp writes that snapshot)
-        auto snapshot = [&](bool emit) {
-            const int k = ksnap++;
-            if (!emit) return;
+        // writes output time k (RING: only the warp that owns the completing step calls this)
+        auto snapshot = [&](int k) {
             fold_counts();
             acc_total += __reduce_add_sync(FULL, my_acc);
             ev_total += n_events;
@@ -291,13 +287,16 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
         int gk = 1;
         int64_t gK = 0;
         uint64_t ge = 0;
-        uint32_t gsteps = 0;  // steps generated so far (both warps of a pair see the same sequence)
+        uint32_t gsteps = 0;  // steps generated so far (every warp of a ring sees the same sequence)
+        int gsnaps = 0;       // output times completed by the steps generated so far
         bool gdone = (T <= 1);
-        snapshot(role == 0);  // k = 0: the initial state
+        if (role == 0) snapshot(0);  // k = 0: the initial state
+        ++gsnaps;
         if (!gdone) {
             gK = kcounts[0];
             while (gK == 0) {  // leading empty intervals repeat the initial state
-                snapshot(role == 0);
+                if (role == 0) snapshot(gsnaps);
+                ++gsnaps;
                 if (++gk >= T) { gdone = true; break; }
                 gK = kcounts[gk - 1];
             }
@@ -321,6 +320,7 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
                     ++snaps;
                 }
             }
+            gsnaps += snaps;
             return true;
         };
 
@@ -328,26 +328,30 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
         uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3];
         int2 q_row[3];
         int q_nb[3], q_snaps[3];
-        int q_pre[3];   // PAIR: snapshots completed by the partner's step right before this own step
-        int q_next[3];  // PAIR: snapshots completed by the partner's step right after this own step
+        int q_base[3];  // index of the first output time this step completes
+        int q_next[3];  // RING: output times completed by the other warps' steps before our next own step
         bool q_valid[3];
 
-        // next OWN step into set s (PAIR: also walks over the partner's step next to it)
+        // next OWN step into set s (RING: also walks over the W-1 steps of the other warps that follow it)
         auto gen_own = [&](int s, uint64_t& e0) -> bool {
-            q_pre[s] = 0;
             q_next[s] = 0;
-            if (!PAIR) return gen(e0, q_nb[s], q_snaps[s]);
-            uint64_t eo;
-            int nbo;
-            if (role == 0) {
-                const bool v = gen(e0, q_nb[s], q_snaps[s]);
-                gen(eo, nbo, q_next[s]);
-                return v;
+            q_base[s] = gsnaps;
+            const bool v = gen(e0, q_nb[s], q_snaps[s]);
+            if (RING) {
+                uint64_t eo;
+                int nbo, sno;
+                for (int w = 1; w < W; ++w) {
+                    gen(eo, nbo, sno);
+                    q_next[s] += sno;
+                }
             }
-            gen(eo, nbo, q_pre[s]);
-            q_next[(s + 2) % 3] = q_pre[s];  // ... which also follows our previous own step
-            return gen(e0, q_nb[s], q_snaps[s]);
+            return v;
         };
+        if (RING) {  // the steps before this warp's first own step belong to the warps before it
+            uint64_t eo;
+            int nbo, sno;
+            for (int w = 0; w < role; ++w) gen(eo, nbo, sno);
+        }
 
         auto issue1 = [&](int s, uint64_t e0) {
             const uint64_t e = e0 + (uint64_t)lane;
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
 
         {
             uint64_t e0;
-            q_next[2] = 0;
+            q_next[2] = q_base[2] = 0;
             q_valid[0] = gen_own(0, e0);
             issue1(0, e0);
             issue2(0);
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
             q_row[2] = make_int2(0, 1);
         }
 
-        bool first_own = true;
+        uint32_t own_done = 0;  // own steps committed in this chain
         bool running = true;
         while (running) {
 #pragma unroll
@@ -439,15 +443,12 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
                     if (lane == il) dep |= is_nbr & lane_lt;
                 }
 
-                // ---- PAIR: the partner's step right before this one must have been committed ----
-                if (PAIR) {
-                    if (role == 1)
-                        for (int q = 0; q < q_pre[cur]; ++q) snapshot(false);  // written by the partner
-                    if (!(first_own && role == 0)) {
-                        sp_mbar_wait(bar_other, other_done & 1u);
-                        ++other_done;
-                    }
-                    first_own = false;
+                // ---- RING: the step right before this one (the predecessor warp's) must be committed ----
+                if (RING) {
+                    // our k-th own step follows the predecessor's k-th (role > 0) or (k-1)-th (role 0) step
+                    if (role > 0) sp_mbar_wait(bar_pred, (pred_base + own_done) & 1u);
+                    else if (own_done > 0) sp_mbar_wait(bar_pred, (pred_base + own_done - 1u) & 1u);
+                    ++own_done;
                 }
 
                 // ---- commit ----
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
                         }
                     }
                     if (!SMEM) __threadfence_block();
-                    if (!PAIR) __syncwarp();  // PAIR: the mbarrier hand-over orders the writes
+                    if (!RING) __syncwarp();  // RING: the mbarrier hand-over orders the writes
                 } else {  // rare: commit up to the first hazard, re-evaluate the rest
                     bool pending = active;
                     for (;;) {
@@ -511,31 +512,22 @@ __global__ void __launch_bounds__(PAIR ? SP_PAIR_MAX_SLOTS * 64 : 512, 1) cnvm_n
                 }
                 ++n_steps;
                 n_events += (uint32_t)nb;
-                if (PACKCNT && (++dsteps >= 120 || (PAIR && q_next[cur] > 0))) fold_counts();
-                for (int q = 0; q < q_snaps[cur]; ++q) snapshot(true);
-                if (PAIR) {
-#if SP_PAIR_ARRIVE_ONE
-                    __syncwarp();
-                    if (lane == 0) sp_mbar_arrive(bar_mine);
-#else
-                    sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
-#endif
-                    // the partner's step right after this one writes its own snapshots: keep the index in step
-                    if (role == 0)
-                        for (int q = 0; q < q_next[cur]; ++q) snapshot(false);
-                }
+                // RING: another warp writes the next output time before our next own step -> it needs our deltas
+                if (PACKCNT && (++dsteps >= 120 || (RING && q_next[cur] > 0))) fold_counts();
+                for (int q = 0; q < q_snaps[cur]; ++q) snapshot(q_base[cur] + q);
+                if (RING) sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
             }
         }
         ev_total += n_events;
         step_total += n_steps;
         extra_total += n_extra;
         acc_total += __reduce_add_sync(FULL, my_acc);
-        if (PAIR) {
-            // both warps are done with the chain; account for partner completions nobody waited for
-            sp_pair_sync(slot + 1);
-            const uint32_t own = role == 0 ? (gsteps + 1) / 2 : gsteps / 2;
-            const uint32_t waited = own - ((role == 0 && own > 0) ? 1u : 0u);
-            other_done += (gsteps - own) - waited;
+        if (RING) {
+            // every warp of the ring is done with the chain; the predecessor's barrier has advanced by the
+            // number of steps it owned
+            sp_ring_sync(slot + 1, 32 * W);
+            const uint32_t pr = (uint32_t)((role + W - 1) % W);
+            pred_base += gsteps > pr ? (gsteps - pr + (uint32_t)W - 1u) / (uint32_t)W : 0u;
         } else {
             __syncwarp();
         }
@@ -757,7 +749,7 @@ int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out) 
 
 namespace {
 
-// kernel selection over (BITS, SMEM, CSR, ALIAS, PAIR); PAIR exists for shared-memory states only
+// kernel selection over (BITS, SMEM, CSR, ALIAS, RING); RING exists for shared-memory states only
 typedef void (*cnvm_kernel_t)(NativeCnvmArgs);
 
 template <int BITS, bool SMEM, bool CSR>
@@ -912,7 +904,7 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     SP_CUDA(sc.out((unsigned long long*)counters, SPONET_NUM_COUNTERS, &A.counters, true));
 
     // ---- launch geometry ----
-    // slots = chains resident per CTA (one warp each, or two in PAIR mode); shared memory per CTA =
+    // slots = chains resident per CTA (one warp each, or a ring of warps_per_chain warps); shared memory per CTA =
     // thresholds + [mbarriers] + counters + Bloom filters + packed states.
     const int bits = M <= 2 ? 1 : M <= 4 ? 2 : M <= 16 ? 4 : 8;
     A.words = (int32_t)((n * bits + 31) / 32);
@@ -921,27 +913,38 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
     const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
-    const size_t per_slot_min = (size_t)M * 4 + 16;  // counters + (possible) mbarrier pair
+    const size_t per_slot_min = (size_t)M * 4 + 16 * 8;  // counters + (possible) mbarrier ring
     bool smem_state = !o->force_global_state;
     int slots = 0;
     if (smem_state) {
         if (smem_max > fixed + 64) slots = (int)std::min<size_t>(16, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
         if (slots < 1) smem_state = false;
     }
-    bool pair = false;
+    int wpc = 1;  // warps per chain
     if (smem_state) {
-        // Large chains leave only a few warps per SM: give each chain two warps that alternate steps.
-        const bool auto_pair = slots <= 9 && chain_bytes >= 8192 && num_chains >= 2 * (int64_t)prop.multiProcessorCount;
-        pair = o->warps_per_chain == 2 || (o->warps_per_chain == 0 && auto_pair);
-        if (pair && slots > SP_PAIR_MAX_SLOTS) slots = SP_PAIR_MAX_SLOTS;  // the PAIR kernels' launch bound
         // no more slots than there are chains to run on this many SMs
         const int64_t need = (num_chains + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
         slots = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
+        // Large chains leave only a few warps per SM: give each chain several warps that take its steps
+        // round-robin (RING).  At most 512 threads per CTA (keeps 118 registers), at most 8 warps a chain.
+        const int max_warps = SP_RING_MAX_THREADS / 32;
+        if (o->warps_per_chain > 0) {
+            wpc = std::min(o->warps_per_chain, 16);
+        } else {
+            if (slots == 9 && chain_bytes >= 8192) slots = 8;  // 8 x 2 warps beat 9 x 1 (A/B on H)
+            if (slots <= 8) wpc = std::min(8, max_warps / slots);
+        }
+        while (wpc > 1 && slots * wpc > max_warps) --slots;  // explicit request: trade slots for warps
+        if (slots < 1) slots = 1;
+        if (slots * wpc > max_warps) wpc = max_warps / slots;
+        if (slots > 15) wpc = 1;  // named barriers 1..15 identify the rings
     } else {
         slots = 8;
     }
-    const int warps = slots * (pair ? 2 : 1);
-    size_t smem_bytes = fixed + (pair ? (size_t)slots * 16 : 0) + (size_t)slots * M * 4 +
+    const bool pair = wpc > 1;
+    const int warps = slots * wpc;
+    A.warps_per_chain = wpc;
+    size_t smem_bytes = fixed + (pair ? (size_t)warps * 8 : 0) + (size_t)slots * M * 4 +
                         (smem_state ? (size_t)slots * chain_bytes : 0);
     // Per-warp Bloom filter for the dependency pre-check, carved from the shared memory the chain states
     // leave over (a chain is never given up for it).  ~N/4 bits are plenty: a step flags a lane with

@@ -205,16 +205,17 @@ def test_cnvm_pair_mode_matches_single_warp_and_oracle(oracle, n, M, alpha):
     struct, keep = model._struct()
     spec = (np.arange(M, dtype=np.int32), 1.0)
     out = {}
-    for wpc in (1, 2):
+    for wpc in (1, 2, 3, 8):
         counters = np.zeros(4, dtype=np.uint64)
         sums = (np.zeros((S, t_eval.size, M), dtype=np.int64), np.zeros((S, t_eval.size, M), dtype=np.int64))
         _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0, t_eval, 555, R, 0, R, cv_spec=spec,
                                   want_cv=True, sums=sums, counters=counters, warps_per_chain=wpc)
         out[wpc] = (cv, sums, counters)
-    np.testing.assert_array_equal(out[1][0], out[2][0])
-    np.testing.assert_array_equal(out[1][1][0], out[2][1][0])
-    np.testing.assert_array_equal(out[1][1][1], out[2][1][1])
-    np.testing.assert_array_equal(out[1][2][:2], out[2][2][:2])  # events, accepted
+    for wpc in (2, 3, 8):
+        np.testing.assert_array_equal(out[1][0], out[wpc][0])
+        np.testing.assert_array_equal(out[1][1][0], out[wpc][1][0])
+        np.testing.assert_array_equal(out[1][1][1], out[wpc][1][1])
+        np.testing.assert_array_equal(out[1][2][:2], out[wpc][2][:2])  # events, accepted
     # full states of a few chains in pair mode vs the oracle
     xs, cv = engine.run_native("cnvm", model._graph(), n, struct, x0, t_eval, 555, R, 3, 6, cv_spec=spec,
                                want_x=True, want_cv=True, warps_per_chain=2)
@@ -250,17 +251,17 @@ def test_headline_size_pair_vs_single_and_conservation():
     t_eval = np.linspace(0, 0.5, T)
     spec = (np.arange(3, dtype=np.int32), 1.0)
     res = {}
-    for wpc in (1, 2):
+    for wpc in (1, 0):  # 0 = automatic choice: 8 chains x 2 warps per SM
         counters = np.zeros(4, dtype=np.uint64)
         sums = (np.zeros((1, T, 3), dtype=np.int64), np.zeros((1, T, 3), dtype=np.int64))
         _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0[None, :], t_eval, 99, R, 0, R, cv_spec=spec,
                                   want_cv=True, sums=sums, counters=counters, warps_per_chain=wpc)
         res[wpc] = (cv[0], sums, counters)
-    np.testing.assert_array_equal(res[1][0], res[2][0])
-    np.testing.assert_array_equal(res[1][1][0], res[2][1][0])
-    np.testing.assert_array_equal(res[1][1][1], res[2][1][1])
-    np.testing.assert_array_equal(res[1][2][:2], res[2][2][:2])
-    cv, sums, counters = res[2]
+    np.testing.assert_array_equal(res[1][0], res[0][0])
+    np.testing.assert_array_equal(res[1][1][0], res[0][1][0])
+    np.testing.assert_array_equal(res[1][1][1], res[0][1][1])
+    np.testing.assert_array_equal(res[1][2][:2], res[0][2][:2])
+    cv, sums, counters = res[0]
     assert (cv.sum(-1) == n).all()
     np.testing.assert_array_equal(cv[:, 0], np.broadcast_to(np.bincount(x0, minlength=3), (R, 3)))
     np.testing.assert_array_equal(sums[0][0], cv.sum(0).astype(np.int64))
@@ -286,14 +287,15 @@ def test_config4_sis_ws_1e6_pair_vs_single():
     t_eval = np.linspace(0, 0.2, T)
     spec = (np.array([1], dtype=np.int32), float(n))
     res = {}
-    for wpc in (1, 2):
+    for wpc in (1, 0, 16):  # 0 = automatic choice (a ring of 8 warps for one chain per SM)
         counters = np.zeros(4, dtype=np.uint64)
         _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0[None, :], t_eval, 11, R, 0, R, cv_spec=spec,
                                   want_cv=True, counters=counters, warps_per_chain=wpc)
         res[wpc] = (cv[0], counters)
-    np.testing.assert_array_equal(res[1][0], res[2][0])
-    np.testing.assert_array_equal(res[1][1][:2], res[2][1][:2])
-    cv = res[2][0]
+    for wpc in (0, 16):
+        np.testing.assert_array_equal(res[1][0], res[wpc][0])
+        np.testing.assert_array_equal(res[1][1][:2], res[wpc][1][:2])
+    cv = res[0][0]
     assert np.allclose(cv[:, 0, 0], 0.3)
     # SIS: infection along edges at rate lambda * (infected neighbours / degree), recovery at rate 1:
     # d rho/dt = lambda rho (1 - rho) - rho = -0.09 at rho = 0.3, lambda = 1 -> the share decays
