@@ -174,8 +174,14 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
             _, local = _native_call(model, kind, states, t_out, seed, num_runs, rb, re, cv_spec=spec, want_cv=True)
         _tick(pbar, S * (re - rb))
     elif cv is None:
-        local, _ = _native_call(model, kind, states, t_out, seed, num_runs, rb, re, want_x=True)
-        _tick(pbar, S * (re - rb))
+        # full trajectories: produced in run chunks so that the device-side staging stays bounded
+        local = np.empty((S, re - rb, T, N), dtype=np.uint8)
+        chunk = max(1, int(_SLAB_BYTES // max(1, S * T * N)))
+        for lo in range(rb, re, chunk):
+            hi = min(re, lo + chunk)
+            part, _ = _native_call(model, kind, states, t_out, seed, num_runs, lo, hi, want_x=True)
+            local[:, lo - rb : hi - rb] = part
+            _tick(pbar, S * (hi - lo))
     else:
         local = _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, pbar)
     _close(pbar)

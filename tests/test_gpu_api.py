@@ -264,3 +264,18 @@ def test_interfaces_and_propensities_known_answers():
     _, c = sample_many_runs(p, x[0], 1.0, 3, 4, collective_variable=Interfaces(net), rng=np.random.default_rng(0))
     _, xs = sample_many_runs(p, x[0], 1.0, 3, 4, rng=np.random.default_rng(0))
     np.testing.assert_array_equal(c, Interfaces(net)(xs.reshape(-1, 120)).reshape(4, 3, 1))
+
+
+def test_full_trajectories_are_chunk_invariant(monkeypatch):
+    """cv=None output is produced in run chunks (bounded device staging): same result for any chunk size."""
+    import networkx as nx
+
+    from sponet_b200 import CNVMParameters, sample_many_runs
+    from sponet_b200 import multiprocessing as smp
+
+    params = CNVMParameters(num_opinions=3, network=nx.barabasi_albert_graph(100, 2, seed=1), r=R3, r_tilde=RT3)
+    states = np.random.default_rng(0).integers(0, 3, (2, 100))
+    _, a = sample_many_runs(params, states, 1.0, 4, 7, rng=np.random.default_rng(3))
+    monkeypatch.setattr(smp, "_SLAB_BYTES", 2 * 4 * 100 * 3)  # three runs per chunk
+    _, b = sample_many_runs(params, states, 1.0, 4, 7, rng=np.random.default_rng(3))
+    np.testing.assert_array_equal(a, b)
