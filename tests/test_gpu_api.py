@@ -279,3 +279,64 @@ def test_full_trajectories_are_chunk_invariant(monkeypatch):
     monkeypatch.setattr(smp, "_SLAB_BYTES", 2 * 4 * 100 * 3)  # three runs per chunk
     _, b = sample_many_runs(params, states, 1.0, 4, 7, rng=np.random.default_rng(3))
     np.testing.assert_array_equal(a, b)
+
+
+class _RingGenerator:
+    """Minimal stand-in for a sponet NetworkGenerator: `num_agents` + `__call__() -> nx.Graph`
+    (sponet/network_generator.py protocol).  Each call returns a differently rewired ring."""
+
+    def __init__(self, n, seed):
+        self.num_agents = n
+        self.rng = np.random.default_rng(seed)
+        self.calls = 0
+
+    def __call__(self):
+        import networkx as nx
+
+        self.calls += 1
+        return nx.connected_watts_strogatz_graph(self.num_agents, 4, 0.3, seed=int(self.rng.integers(1 << 30)))
+
+
+def test_network_generator_resamples_per_run():
+    """CNVMParameters(network_generator=...): a new network per simulate() call and per run of
+    sample_many_runs (sponet/cnvm/model.py:95-96, sponet/multiprocessing.py:36)."""
+    from sponet_b200 import CNVM, CNVMParameters, OpinionShares, sample_many_runs
+
+    gen = _RingGenerator(60, seed=1)
+    params = CNVMParameters(num_opinions=2, network_generator=gen, r=1.0, r_tilde=0.05)
+    assert params.num_agents == 60 and params.network is None
+    model = CNVM(params)
+    x0 = np.random.default_rng(0).integers(0, 2, 60)
+    t, x = model.simulate(2.0, x0, 5, rng=np.random.default_rng(1))
+    assert gen.calls == 1 and x.shape == (5, 60) and len(params.network) == 60
+    first = [nb.copy() for nb in params.network]
+    model.simulate(2.0, x0, 5, rng=np.random.default_rng(1))
+    assert gen.calls == 2 and any(not np.array_equal(a, b) for a, b in zip(first, params.network))
+    with pytest.raises(ValueError, match="NetworkGenerator"):
+        params.set_network(None)
+    _, c = sample_many_runs(params, x0, 1.0, 3, 4, collective_variable=OpinionShares(2), rng=np.random.default_rng(2))
+    assert c.shape == (4, 3, 2) and gen.calls == 6 and (c.sum(-1) == 60).all()
+
+
+def test_update_rates_and_cntm_drivers():
+    import networkx as nx
+
+    from sponet_b200 import (CNTMParameters, CNVM, CNVMParameters, OpinionShares, estimate_steady_state,
+                             sample_many_runs, sample_moments)
+
+    params = CNVMParameters(num_opinions=2, num_agents=80, r=1.0, r_tilde=0.0)
+    model = CNVM(params)
+    model.update_rates(r_tilde=0.5)
+    assert params.r_noise == 1.0 and params.r_imit == 1.0
+    x0 = np.zeros(80, dtype=int)
+    _, x = model.simulate(20.0, x0, 3, rng=np.random.default_rng(0))
+    assert x[-1].sum() > 0  # noise now creates opinion 1 out of consensus
+    p = CNTMParameters(nx.erdos_renyi_graph(90, 0.1, seed=2), 1.0, 0.3, 0.5, 0.5)
+    s0 = np.random.default_rng(1).integers(0, 2, 90)
+    _, a = sample_many_runs(p, s0, 2.0, 4, 3, n_jobs=2, rng=np.random.default_rng(4), mode="replay")
+    assert a.shape == (3, 4, 90) and a.dtype == np.uint8
+    t, mean, var, n = sample_moments(p, s0, 2.0, 4, 200, rel_tol=0.2, collective_variable=OpinionShares(2, True),
+                                     rng=np.random.default_rng(5))
+    assert mean.shape == (4, 2) and np.allclose(mean.sum(1), 1.0) and n >= 200
+    est = estimate_steady_state(p, OpinionShares(2, normalize=True), tol_abs=0.1, rng=np.random.default_rng(6), verbose=False)
+    assert est.shape == (2,) and abs(est.sum() - 1) < 1e-12
