@@ -145,12 +145,24 @@ int sponet_cntm_replay_all(const sponet_graph* g, const sponet_cntm_params* para
  * DESIGN.md section 3 gives the sampling scheme; oracle/oracle_native.inc states it sequentially.
  * ------------------------------------------------------------------------------------------- */
 
-/* In-kernel collective variable = OpinionShares (sponet/collective_variables.py:63-124 without
- * weights): out[d] = count[idx[d]] / divisor.  divisor 1.0 = counts, num_agents = normalize=True. */
+/* In-kernel collective variable: the OpinionShares family (sponet/collective_variables.py:63-220).
+ * The kernel keeps an integer table count[class * M + opinion] = sum of agent_weight over the agents
+ * of that class holding that opinion, updated on every accepted event, and emits
+ *     out[d] = count[idx[d]] / (divisors ? divisors[d] : divisor).
+ *   OpinionShares(normalize, idx_to_return)       num_classes 1, no weights, divisor 1 or N
+ *   OpinionShares(weights = integers) /
+ *   DegreeWeightedOpinionShares                    agent_weight = weights / degrees, divisor sum|w|
+ *   OpinionSharesByDegree                          agent_class = rank of the degree, divisors = class sizes
+ * agent_class / agent_weight are served by the CNVM agent-level kernel only; float (non-integer)
+ * weights are not in-kernel (use out_x + sponet_opinion_shares). */
 typedef struct {
-    int32_t dimension;  /* D = len(idx_to_return)                       */
-    const int32_t* idx; /* [D] HOST pointer, opinion indices to return  */
+    int32_t dimension;           /* D                                                           */
+    const int32_t* idx;          /* [D] HOST: indices into the table, class * M + opinion       */
     double divisor;
+    int32_t num_classes;         /* 0 or 1: a single class                                      */
+    const int32_t* agent_class;  /* [n] HOST, NULL = class 0                                    */
+    const int32_t* agent_weight; /* [n] HOST integer weights (may be negative), NULL = 1        */
+    const double* divisors;      /* [D] HOST per-output divisors, NULL = `divisor` for all      */
 } sponet_shares_cv;
 
 typedef struct {

@@ -55,7 +55,15 @@ class sponet_replay_work(C.Structure):
 
 
 class sponet_shares_cv(C.Structure):
-    _fields_ = [("dimension", C.c_int32), ("idx", C.c_void_p), ("divisor", C.c_double)]
+    _fields_ = [
+        ("dimension", C.c_int32),
+        ("idx", C.c_void_p),
+        ("divisor", C.c_double),
+        ("num_classes", C.c_int32),
+        ("agent_class", C.c_void_p),
+        ("agent_weight", C.c_void_p),
+        ("divisors", C.c_void_p),
+    ]
 
 
 class sponet_native_opts(C.Structure):

@@ -106,10 +106,16 @@ class OpinionShares:
 
     # -- what the simulation kernels need to compute this CV on the fly -----------------------
     def _kernel_spec(self, num_agents: int):
-        """(idx int32[D], divisor) when the CV is an unweighted histogram, else None."""
-        if self.weights is not None:
-            return None
-        return self.idx_to_return.astype(np.int32), float(num_agents) if self.normalize else 1.0
+        """KernelCV when the CV is an integer-weighted histogram (exact in-kernel), else None."""
+        from .engine import KernelCV
+
+        idx = self.idx_to_return.astype(np.int32)
+        if self.weights is None:
+            return KernelCV(idx, float(num_agents) if self.normalize else 1.0)
+        w = np.asarray(self.weights, dtype=np.float64)
+        if w.shape != (num_agents,) or not np.all(w == np.round(w)) or np.sum(np.abs(w)) >= 2**31:
+            return None  # float weights: evaluated from stored states (sponet_opinion_shares)
+        return KernelCV(idx, float(self.normalization) if self.normalize else 1.0, agent_weight=w.astype(np.int32))
 
 
 class DegreeWeightedOpinionShares(OpinionShares):
@@ -130,6 +136,21 @@ class OpinionSharesByDegree:
         self.normalize = normalize
         self.idx_to_return = _select(idx_to_return, num_opinions)
         self.dimension = len(self.idx_to_return) * self.degrees.shape[0]
+
+    def _kernel_spec(self, num_agents: int):
+        """One class per distinct degree; out = counts[class, opinion] (/ class size when normalised)."""
+        from .engine import KernelCV
+
+        if self.degrees_of_nodes.shape != (num_agents,):
+            return None
+        M, C = self.num_opinions, self.degrees.shape[0]
+        cls = np.searchsorted(self.degrees, self.degrees_of_nodes).astype(np.int32)
+        idx = (np.arange(C)[:, None] * M + self.idx_to_return[None, :]).ravel()
+        divisors = None
+        if self.normalize:
+            sizes = np.bincount(cls, minlength=C).astype(np.float64)
+            divisors = np.repeat(sizes, len(self.idx_to_return))
+        return KernelCV(idx, 1.0, divisors=divisors, num_classes=C, agent_class=cls)
 
     def __call__(self, x):
         xs, was_1d = _as_2d(x)
@@ -157,6 +178,28 @@ class CompositeCollectiveVariable:
     def __init__(self, collective_variables: list[CollectiveVariable]):
         self.collective_variables = collective_variables
         self.dimension = sum(cv.dimension for cv in collective_variables)
+
+    def _kernel_spec(self, num_agents: int):
+        """Concatenation is in-kernel when every part reads the same (class, weight) table."""
+        from .engine import KernelCV
+
+        specs = [cv._kernel_spec(num_agents) if hasattr(cv, "_kernel_spec") else None for cv in self.collective_variables]
+        if not specs or any(sp is None for sp in specs):
+            return None
+
+        def same(a, b):
+            return (a is None and b is None) or (a is not None and b is not None and np.array_equal(a, b))
+
+        first = specs[0]
+        for sp in specs[1:]:
+            if sp.num_classes != first.num_classes or not same(sp.agent_class, first.agent_class) or not same(
+                sp.agent_weight, first.agent_weight
+            ):
+                return None
+        return KernelCV(
+            np.concatenate([sp.idx for sp in specs]), 1.0, divisors=np.concatenate([sp.divisor_vector() for sp in specs]),
+            num_classes=first.num_classes, agent_class=first.agent_class, agent_weight=first.agent_weight,
+        )
 
     def __call__(self, x):
         xs, was_1d = _as_2d(x)

@@ -195,4 +195,7 @@ struct SpCvDev {
     int32_t D;
     const int32_t* d_idx;  // device [D]
     double divisor;
+    const double* d_divisors;  // device [D] or nullptr
+    int32_t num_classes;       // >= 1
+    const int2* d_cw;          // device [n] (class, weight) or nullptr
 };

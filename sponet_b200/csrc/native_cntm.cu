@@ -22,7 +22,7 @@ int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, 
                            int64_t nrun, int64_t R_total, int64_t run_begin, const double* d_t_eval,
                            int T, double next_event_rate, int64_t* d_counts);
 int sp_validate_native_common(const double* t_eval, int64_t T, const sponet_native_opts* o, int64_t S);
-int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out);
+int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, int64_t n);
 
 namespace {
 
@@ -409,7 +409,9 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
         A.need10 = d_need + g->max_degree + 1;
     }
     SpCvDev cvd;
-    SP_TRY(sp_stage_cv(sc, cv, 2, &cvd));
+    SP_TRY(sp_stage_cv(sc, cv, 2, &cvd, 0));
+    if (cvd.d_divisors)
+        return sponet_fail(SPONET_ERR_UNSUPPORTED, "cntm_run: per-output divisors are not supported");
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
     A.cv_div = cvd.divisor;

@@ -40,6 +40,9 @@ struct NativeCnvmArgs {
     int32_t D;
     const int32_t* cv_idx;
     double cv_div;
+    const double* cv_divs;  // per-output divisors (nullptr = cv_div)
+    const int2* cw;         // per-agent (class, weight) of a grouped / weighted CV (nullptr = plain counts)
+    int32_t cnt_stride;     // counters per chain: num_classes * M
     unsigned long long* counters;
     uint32_t* gstate;  // global chain states (fallback), [total_warps, words]
     int32_t words;     // 32-bit words per chain
@@ -119,7 +122,10 @@ __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named ba
 template <int BITS, bool SMEM, bool CSR, bool ALIAS, bool RING>
 __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
-    constexpr bool PACKCNT = (BITS <= 2);   // M <= 4: count deltas packed per lane, folded lazily
+    constexpr bool THR4 = (BITS <= 2);      // M <= 4: threshold table padded to 4 x 4 per branch
+    // M <= 4 and plain counts: count deltas packed per lane, folded lazily; a grouped / weighted CV
+    // (A.cw) updates its table with shared-memory atomics on every accepted event instead
+    const bool PACKCNT = THR4 && A.cw == nullptr;
     constexpr bool THR_SMEM = (BITS <= 4);  // M <= 16: threshold tables staged in shared memory
     constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     // thr: M <= 4 -> 32 entries indexed (noise << 4 | m << 2 | nw); M <= 16 -> 2*MM entries
     uint32_t* sp = smem;
     const uint32_t* thr = A.thr;
-    if (PACKCNT) {
+    if (THR4) {
         for (int i = threadIdx.x; i < 32; i += blockDim.x) {
             const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
             sp[i] = (m < M && w < M) ? A.thr[nz * MM + m * M + w] : 0u;
@@ -159,8 +165,8 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         if (lane == 0) sp_mbar_init(bar_mine, 32u);
         sp += (size_t)A.warps_per_cta * 2;
     }
-    int32_t* cnt_mem = (int32_t*)sp + slot * M;
-    sp += (size_t)slots * M;
+    int32_t* cnt_mem = (int32_t*)sp + slot * A.cnt_stride;
+    sp += (size_t)slots * A.cnt_stride;
     const uint32_t bloom_bits = (uint32_t)A.bloom_words * 32u;  // per warp; 0 = no filter (all lanes flagged)
     uint32_t* bloom = sp + (size_t)warp * A.bloom_words;
     for (int i = threadIdx.x; i < A.warps_per_cta * A.bloom_words; i += blockDim.x) sp[i] = 0u;
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
 
         // ---- load + pack the initial state, count opinions ----
         if (role == 0)
-            for (int v = lane; v < M; v += 32) cnt_mem[v] = 0;
+            for (int v = lane; v < A.cnt_stride; v += 32) cnt_mem[v] = 0;
         if (RING) sp_ring_sync(slot + 1, 32 * W);
         else __syncwarp();
         {
@@ -203,6 +209,9 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                             c1 += (v == 1);
                             c2 += (v == 2);
                             c3 += (v == 3);
+                        } else if (A.cw) {
+                            const int2 cw = __ldg(A.cw + a);
+                            atomicAdd(&cnt_mem[cw.x * M + v], cw.y);
                         } else {
                             atomicAdd(&cnt_mem[v], 1);
                         }
@@ -255,6 +264,17 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             }
         };
 
+        // an agent of (class, weight) moves from opinion m to opinion nw: table update with shared atomics
+        auto count_move = [&](uint32_t agent, uint32_t m, uint32_t nw) {
+            int base = 0, w = 1;
+            if (A.cw) {  // gathered only for accepted events (rare path: grouped / weighted CVs)
+                const int2 cw = __ldg(A.cw + agent);
+                base = cw.x * M;
+                w = cw.y;
+            }
+            atomicAdd(&cnt_mem[base + (int)m], -w);
+            atomicAdd(&cnt_mem[base + (int)nw], w);
+        };
         // writes output time k (RING: only the warp that owns the completing step calls this)
         auto snapshot = [&](int k) {
             fold_counts();
@@ -267,8 +287,10 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
                     const long long c = cnt_mem[A.cv_idx[d]];
-                    if (A.out_cv)
-                        A.out_cv[snap * A.D + d] = (A.cv_div == 1.0) ? (double)c : (double)c / A.cv_div;
+                    if (A.out_cv) {
+                        const double dv = A.cv_divs ? A.cv_divs[d] : A.cv_div;
+                        A.out_cv[snap * A.D + d] = (dv == 1.0) ? (double)c : (double)c / dv;
+                    }
                     if (A.out_sum) {
                         const int64_t o = (j * (int64_t)T + k) * A.D + d;
                         atomicAdd(A.out_sum + o, (unsigned long long)c);
@@ -458,7 +480,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                 uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
                 uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
                 uint32_t th;
-                if (PACKCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
                 else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
                 else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
                 bool acc = active && sp_thr_accept(r3, th);
@@ -474,8 +496,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                         if (PACKCNT) {
                             dpack += (1u << (8 * nw)) - (1u << (8 * m));
                         } else {
-                            atomicAdd(&cnt_mem[m], -1);
-                            atomicAdd(&cnt_mem[nw], 1);
+                            count_move(a, m, nw);
                         }
                     }
                     if (!SMEM) __threadfence_block();
@@ -491,8 +512,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                             if (PACKCNT) {
                                 dpack += (1u << (8 * nw)) - (1u << (8 * m));
                             } else {
-                                atomicAdd(&cnt_mem[m], -1);
-                                atomicAdd(&cnt_mem[nw], 1);
+                                count_move(a, m, nw);
                             }
                         }
                         pending = pending && lane >= first;
@@ -502,7 +522,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                         ++n_extra;
                         m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
                         nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                        if (PACKCNT) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                        if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
                         else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
                         else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
                         acc = pending && sp_thr_accept(r3, th);
@@ -727,23 +747,53 @@ int sp_validate_native_common(const double* t_eval, int64_t T, const sponet_nati
     return SPONET_OK;
 }
 
-// Stages the in-kernel CV descriptor.  cv == NULL with moment outputs is an error.
-int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out) {
+// Stages the in-kernel CV descriptor.  `n` > 0 allows the per-agent class / weight arrays (CNVM agent-level
+// kernel); kernels that only keep plain opinion counts pass n = 0.
+int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, int64_t n) {
     out->D = 0;
     out->d_idx = nullptr;
     out->divisor = 1.0;
+    out->d_divisors = nullptr;
+    out->num_classes = 1;
+    out->d_cw = nullptr;
     if (!cv) return SPONET_OK;
     SP_REQUIRE(cv->dimension >= 1 && cv->idx, "cv: dimension/idx invalid");
-    SP_REQUIRE(cv->divisor != 0.0, "cv: divisor must be non-zero");
+    SP_REQUIRE(cv->divisors || cv->divisor != 0.0, "cv: divisor must be non-zero");
+    const int C = cv->num_classes > 1 ? cv->num_classes : 1;
+    const bool grouped = cv->agent_class || cv->agent_weight || C > 1;
+    if (grouped && n <= 0)
+        return sponet_fail(SPONET_ERR_UNSUPPORTED, "cv: agent classes / weights are served by the CNVM agent-level kernel only");
+    SP_REQUIRE((int64_t)C * M <= 16384, "cv: too many classes (%d x %d opinions)", C, M);
     for (int d = 0; d < cv->dimension; ++d)
-        SP_REQUIRE(cv->idx[d] >= 0 && cv->idx[d] < M, "cv: opinion index %d out of range", cv->idx[d]);
+        SP_REQUIRE(cv->idx[d] >= 0 && cv->idx[d] < C * M, "cv: table index %d out of range", cv->idx[d]);
     int32_t* d_idx;
     SP_CUDA(sc.alloc((void**)&d_idx, cv->dimension * sizeof(int32_t)));
     SP_CUDA(cudaMemcpyAsync(d_idx, cv->idx, cv->dimension * sizeof(int32_t), cudaMemcpyHostToDevice, sc.stream));
+    if (cv->divisors) {
+        for (int d = 0; d < cv->dimension; ++d) SP_REQUIRE(cv->divisors[d] != 0.0, "cv: divisors must be non-zero");
+        double* d_div;
+        SP_CUDA(sc.alloc((void**)&d_div, cv->dimension * sizeof(double)));
+        SP_CUDA(cudaMemcpyAsync(d_div, cv->divisors, cv->dimension * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
+        out->d_divisors = d_div;
+    }
+    if (grouped) {
+        std::vector<int2> cw((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t c = cv->agent_class ? cv->agent_class[i] : 0;
+            SP_REQUIRE(c >= 0 && c < C, "cv: agent_class[%lld] = %d out of range", (long long)i, c);
+            cw[i] = make_int2(c, cv->agent_weight ? cv->agent_weight[i] : 1);
+        }
+        int2* d_cw;
+        SP_CUDA(sc.alloc((void**)&d_cw, (size_t)n * sizeof(int2)));
+        SP_CUDA(cudaMemcpyAsync(d_cw, cw.data(), (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, sc.stream));
+        SP_CUDA(cudaStreamSynchronize(sc.stream));
+        out->d_cw = d_cw;
+    }
     SP_CUDA(cudaStreamSynchronize(sc.stream));
     out->D = cv->dimension;
     out->d_idx = d_idx;
     out->divisor = cv->divisor;
+    out->num_classes = C;
     return SPONET_OK;
 }
 
@@ -867,10 +917,13 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     A.noise_thr = sp_prob_to_thr(noise_probability);
     SP_TRY(stage_thresholds(sc, p, &A.thr));
     SpCvDev cvd;
-    SP_TRY(sp_stage_cv(sc, cv, M, &cvd));
+    SP_TRY(sp_stage_cv(sc, cv, M, &cvd, n));
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
     A.cv_div = cvd.divisor;
+    A.cv_divs = cvd.d_divisors;
+    A.cw = cvd.d_cw;
+    A.cnt_stride = cvd.num_classes * M;
     A.S = S;
     A.nrun = nrun;
     A.R_total = o->num_runs_total;
@@ -913,7 +966,8 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
     const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
-    const size_t per_slot_min = (size_t)M * 4 + 16 * 8;  // counters + (possible) mbarrier ring
+    const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
+    const size_t per_slot_min = cnt_bytes + 16 * 8;              // counters + (possible) mbarrier ring
     bool smem_state = !o->force_global_state;
     int slots = 0;
     if (smem_state) {
@@ -944,7 +998,7 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     const bool pair = wpc > 1;
     const int warps = slots * wpc;
     A.warps_per_chain = wpc;
-    size_t smem_bytes = fixed + (pair ? (size_t)warps * 8 : 0) + (size_t)slots * M * 4 +
+    size_t smem_bytes = fixed + (pair ? (size_t)warps * 8 : 0) + (size_t)slots * cnt_bytes +
                         (smem_state ? (size_t)slots * chain_bytes : 0);
     // Per-warp Bloom filter for the dependency pre-check, carved from the shared memory the chain states
     // leave over (a chain is never given up for it).  ~N/4 bits are plenty: a step flags a lane with
@@ -1011,7 +1065,9 @@ extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_
     A.noise_thr = sp_prob_to_thr(noise_probability);
     SP_TRY(stage_thresholds(sc, p, &A.thr));
     SpCvDev cvd;
-    SP_TRY(sp_stage_cv(sc, cv, M, &cvd));
+    SP_TRY(sp_stage_cv(sc, cv, M, &cvd, 0));
+    if (cvd.d_divisors)
+        return sponet_fail(SPONET_ERR_UNSUPPORTED, "count-only path: per-output divisors are not supported");
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
     A.cv_div = cvd.divisor;

@@ -128,12 +128,46 @@ def cnvm_event_rates(params, degree_alpha, complete: bool) -> tuple[float, float
     return ner.value, npr.value
 
 
+class KernelCV:
+    """What the simulation kernels need to evaluate a CV of the OpinionShares family on the fly
+    (sponet_shares_cv): out[d] = count[idx[d]] / divisor(s), count = integer table [class * M + opinion]."""
+
+    def __init__(self, idx, divisor=1.0, divisors=None, num_classes=1, agent_class=None, agent_weight=None):
+        self.idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self.divisor = float(divisor)
+        self.divisors = None if divisors is None else np.ascontiguousarray(divisors, dtype=np.float64)
+        self.num_classes = int(num_classes)
+        self.agent_class = None if agent_class is None else np.ascontiguousarray(agent_class, dtype=np.int32)
+        self.agent_weight = None if agent_weight is None else np.ascontiguousarray(agent_weight, dtype=np.int32)
+
+    @property
+    def grouped(self) -> bool:
+        return self.agent_class is not None or self.agent_weight is not None
+
+    @property
+    def dimension(self) -> int:
+        return int(self.idx.size)
+
+    def divisor_vector(self) -> np.ndarray:
+        return self.divisors if self.divisors is not None else np.full(self.idx.size, self.divisor)
+
+
+def as_kernel_cv(spec) -> "KernelCV | None":
+    if spec is None or isinstance(spec, KernelCV):
+        return spec
+    idx, divisor = spec  # legacy (idx, divisor) tuples
+    return KernelCV(idx, divisor)
+
+
 def cv_struct(spec):
+    spec = as_kernel_cv(spec)
     if spec is None:
         return None, None
-    idx, divisor = spec
-    idx = np.ascontiguousarray(idx, dtype=np.int32)
-    return _lib.sponet_shares_cv(int(idx.size), _lib.ptr(idx), float(divisor)), idx
+    s = _lib.sponet_shares_cv(
+        spec.dimension, _lib.ptr(spec.idx), spec.divisor, spec.num_classes, _lib.ptr(spec.agent_class),
+        _lib.ptr(spec.agent_weight), _lib.ptr(spec.divisors),
+    )
+    return s, spec
 
 
 def draw_seed(rng: Generator) -> int:
@@ -188,7 +222,7 @@ def run_native(
     like = counts_init if kind == "cnvm_counts" else x_init
     S = like.shape[0]
     cvs, cv_keep = cv_struct(cv_spec)
-    D = 0 if cv_spec is None else cv_keep.size
+    D = 0 if cv_spec is None else cv_keep.dimension
     out_x = _alloc((S, nrun, T, num_agents), np.uint8, like) if want_x else None
     out_cv = _alloc((S, nrun, T, D), np.float64, like) if want_cv else None
     opts = _lib.sponet_native_opts(

@@ -135,9 +135,10 @@ def sample_many_runs(
 # native
 # ---------------------------------------------------------------------------------------------
 def _kernel_cv_spec(cv, num_agents):
-    if isinstance(cv, OpinionShares):
-        return cv._kernel_spec(num_agents)
-    return None
+    """KernelCV if the simulation kernels can evaluate `cv` on the fly (OpinionShares family with
+    integer weights, by-degree groups, composites over one table), else None."""
+    fn = getattr(cv, "_kernel_spec", None)
+    return fn(num_agents) if fn is not None else None
 
 
 def _native_call(model, kind, x_init, t_out, seed, R_total, rb, re, **kw):
@@ -163,8 +164,10 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
     pbar = _progress(progress_bar, S * (re - rb))
 
     spec = _kernel_cv_spec(cv, N)
+    if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
+        spec = None  # grouped / weighted tables are kept by the CNVM agent-level kernel only
     if spec is not None:
-        if kind == "cnvm" and model.is_complete and p.num_opinions <= 16:
+        if kind == "cnvm" and model.is_complete and p.num_opinions <= 16 and not spec.grouped and spec.divisors is None:
             counts0 = np.stack([np.bincount(s, minlength=p.num_opinions) for s in states]).astype(np.int64)
             struct, keep = model._struct()
             _, local = engine.run_native("cnvm_counts", None, N, struct, None, t_out, seed, num_runs, rb, re,

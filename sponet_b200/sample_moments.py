@@ -48,6 +48,8 @@ def batch_moment_sums(model, kind, state, t_grid, batch_size, cv, rng) -> tuple[
     N, T = p.num_agents, t_grid.size
     rank, world = _dist()
     spec = _kernel_cv_spec(cv, N) if p.num_opinions <= 256 else None
+    if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
+        spec = None
     if spec is not None and engine.resolve_mode(None) == "native":
         from .multiprocessing import _broadcast_seed
 
@@ -56,12 +58,13 @@ def batch_moment_sums(model, kind, state, t_grid, batch_size, cv, rng) -> tuple[
             seed = _broadcast_seed(seed)
         b = np.concatenate(([0], np.cumsum(_split_runs(batch_size, world))))
         rb, re = int(b[rank]), int(b[rank + 1])
-        idx, divisor = spec
-        sums = (np.zeros((1, T, idx.size), dtype=np.int64), np.zeros((1, T, idx.size), dtype=np.int64))
+        divisor = spec.divisor_vector()
+        plain = not spec.grouped and spec.divisors is None
+        sums = (np.zeros((1, T, spec.dimension), dtype=np.int64), np.zeros((1, T, spec.dimension), dtype=np.int64))
         x0 = np.ascontiguousarray(np.asarray(state, dtype=np.uint8)[None, :])
         if kind == "cnvm":
             struct, keep = model._struct()
-            if model.is_complete and p.num_opinions <= 16:
+            if model.is_complete and p.num_opinions <= 16 and plain:
                 c0 = np.bincount(x0[0], minlength=p.num_opinions).astype(np.int64)[None, :]
                 engine.run_native("cnvm_counts", None, N, struct, None, t_grid, seed, batch_size, rb, re,
                                   cv_spec=spec, sums=sums, counts_init=c0)

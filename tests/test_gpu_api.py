@@ -340,3 +340,57 @@ def test_update_rates_and_cntm_drivers():
     assert mean.shape == (4, 2) and np.allclose(mean.sum(1), 1.0) and n >= 200
     est = estimate_steady_state(p, OpinionShares(2, normalize=True), tol_abs=0.1, rng=np.random.default_rng(6), verbose=False)
     assert est.shape == (2,) and abs(est.sum() - 1) < 1e-12
+
+
+def test_grouped_and_weighted_cvs_are_evaluated_in_kernel():
+    """DegreeWeightedOpinionShares, OpinionSharesByDegree, integer-weighted OpinionShares and composites
+    over one table are kept by the simulation kernel (integer tables, exact); the result must equal the
+    CV evaluated on the stored states of the same chains, bit for bit -- also with a ring of warps."""
+    import networkx as nx
+
+    from sponet_b200 import (CNVM, CNVMParameters, CompositeCollectiveVariable, DegreeWeightedOpinionShares,
+                             OpinionShares, OpinionSharesByDegree, engine, sample_many_runs, sample_moments)
+    from sponet_b200.multiprocessing import _kernel_cv_spec
+
+    g = nx.barabasi_albert_graph(300, 3, seed=2)
+    params = CNVMParameters(num_opinions=3, network=g, r=R3, r_tilde=RT3, alpha=0.5)
+    x0 = np.random.default_rng(0).integers(0, 3, 300)
+    wi = np.random.default_rng(1).integers(-3, 8, 300)
+    cvs = [
+        DegreeWeightedOpinionShares(3, g),
+        DegreeWeightedOpinionShares(3, g, normalize=True, idx_to_return=[2, 0]),
+        OpinionSharesByDegree(3, g),
+        OpinionSharesByDegree(3, g, normalize=True, idx_to_return=1),
+        OpinionShares(3, weights=wi, normalize=True),
+        CompositeCollectiveVariable([OpinionShares(3), OpinionShares(3, normalize=True, idx_to_return=1)]),
+        CompositeCollectiveVariable([OpinionSharesByDegree(3, g), OpinionSharesByDegree(3, g, True, [0])]),
+    ]
+    _, xs = sample_many_runs(params, x0, 2.0, 4, 6, rng=np.random.default_rng(9))
+    for cv in cvs:
+        assert _kernel_cv_spec(cv, 300) is not None, type(cv).__name__
+        _, c = sample_many_runs(params, x0, 2.0, 4, 6, collective_variable=cv, rng=np.random.default_rng(9))
+        assert c.shape == (6, 4, cv.dimension)
+        np.testing.assert_array_equal(c, cv(xs.reshape(-1, 300)).reshape(c.shape))
+    # float weights and mixed tables are NOT in-kernel (evaluated from device-resident slabs instead)
+    assert _kernel_cv_spec(OpinionShares(3, weights=np.random.default_rng(2).random(300)), 300) is None
+    assert _kernel_cv_spec(CompositeCollectiveVariable([OpinionShares(3), DegreeWeightedOpinionShares(3, g)]), 300) is None
+    # moments of a grouped CV: fused integer sums == moments of the per-run values
+    cv = OpinionSharesByDegree(3, g, normalize=True)
+    _, c = sample_many_runs(params, x0, 2.0, 4, 300, collective_variable=cv, rng=np.random.default_rng(4))
+    _, m, v, n = sample_moments(params, x0, 2.0, 4, 300, rel_tol=1e9, collective_variable=cv, rng=np.random.default_rng(4))
+    np.testing.assert_allclose(m, c.mean(0), rtol=1e-12)
+    np.testing.assert_allclose(v, c.var(0), rtol=1e-8, atol=1e-14)
+    # ring of warps + grouped table (larger chain so that the ring is used)
+    n_big = 40000
+    gb = nx.fast_gnp_random_graph(n_big, 8 / n_big, seed=1)
+    for u in list(nx.isolates(gb)):
+        gb.add_edge(u, (u + 1) % n_big)
+    pb = CNVMParameters(num_opinions=3, network=gb, r=R3, r_tilde=RT3)
+    xb = np.random.default_rng(5).integers(0, 3, n_big).astype(np.uint8)
+    spec = _kernel_cv_spec(OpinionSharesByDegree(3, gb), n_big)
+    mb = CNVM(pb)
+    struct, keep = mb._struct()
+    outs = [engine.run_native("cnvm", mb._graph(), n_big, struct, xb[None], np.linspace(0, 0.05, 3), 3, 40, 0, 40,
+                              cv_spec=spec, want_cv=True, warps_per_chain=w)[1] for w in (1, 4)]
+    np.testing.assert_array_equal(outs[0], outs[1])
+    del keep
