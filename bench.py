@@ -312,6 +312,135 @@ def run_gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# --all-configs: every BASELINE.json configuration shape on one GPU next to the CPU arm
+# (writes gpurun_out/configs.json; summarised in profiles/r1_configs.md).  Not part of the default run.
+# ---------------------------------------------------------------------------------------------
+def _gpu_rate(kind, model, struct, graph, n, x0, t_eval, runs, spec, counts_init=None, reps=3):
+    import torch
+
+    from sponet_b200 import engine
+
+    d_x0 = None if x0 is None else torch.as_tensor(x0[None, :], device="cuda")
+    d_c0 = None if counts_init is None else torch.as_tensor(counts_init, device="cuda")
+    best = 0.0
+    for rep in range(reps):
+        counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        engine.run_native(kind, graph, n, struct, d_x0, t_eval, 100 + rep, runs, 0, runs, cv_spec=spec, want_cv=True,
+                          counters=counters, counts_init=d_c0)
+        e1.record()
+        torch.cuda.synchronize()
+        ev = float(counters[0].item())
+        best = max(best, ev / (e0.elapsed_time(e1) * 1e-3))
+    return best, ev
+
+
+def _cpu_rate(model_name, x0, t_eval, M, threads, target_s=8.0, **kw):
+    import oracle
+
+    _, ev = oracle.sample_many_runs(model_name, x0, threads, t_eval, M, num_threads=threads, seed=1, **kw)  # warm
+    t0 = time.perf_counter()
+    _, ev = oracle.sample_many_runs(model_name, x0, threads, t_eval, M, num_threads=threads, seed=2, **kw)
+    per = time.perf_counter() - t0
+    runs = max(threads, int(threads * max(1.0, target_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    _, ev = oracle.sample_many_runs(model_name, x0, runs, t_eval, M, num_threads=threads, seed=3, **kw)
+    sec = time.perf_counter() - t0
+    return ev / sec, runs, sec
+
+
+def run_all_configs():
+    import torch
+
+    import oracle  # CPU baseline leg
+    from sponet_b200 import CNTM, CNVM, OpinionShares, engine, sample_moments, workloads
+
+    threads = host_threads()
+    out = []
+
+    # config 1: CNVM M=2 complete N=1000, t_max=100, T=101 (count-only kernel; 1e5 runs to fill the GPU)
+    params, x0, rate = workloads.complete_cnvm(1000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    t_eval = np.linspace(0, 100.0, 101)
+    spec = (np.arange(2, dtype=np.int32), 1.0)
+    c0 = np.bincount(x0, minlength=2).astype(np.int64)[None, :]
+    g, _ = _gpu_rate("cnvm_counts", model, struct, None, 1000, None, t_eval, 100_000, spec, counts_init=c0)
+    g1k, _ = _gpu_rate("cnvm_counts", model, struct, None, 1000, None, t_eval, 1000, spec, counts_init=c0)
+    ga, _ = _gpu_rate("cnvm", model, struct, None, 1000, x0, t_eval, 100_000, spec)
+    c, runs, sec = _cpu_rate("cnvm_complete", x0, t_eval, 2, threads, r_imit=params.r_imit, r_noise=params.r_noise,
+                            prob_imit=params.prob_imit, prob_noise=params.prob_noise, degree_alpha=model.degree_alpha)
+    out.append(dict(config="1: CNVM M=2 complete N=1000, t_max=100, T=101", gpu_events_per_s=g,
+                    note=f"count-only kernel, 1e5 runs; 1e3 runs (as in BASELINE): {g1k:.3g}; agent-level kernel, 1e5 runs: {ga:.3g}",
+                    cpu_events_per_s=c, cpu_threads=threads, cpu_sample=f"{runs} runs, {sec:.1f} s"))
+
+    # config 2: CNVM M=3 ER N=1e4, R=1e4, T=100
+    params, x0, rate = workloads.headline_cnvm(10_000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    t_eval = np.linspace(0, 10.0, 100)
+    spec = (np.arange(3, dtype=np.int32), 1.0)
+    g, _ = _gpu_rate("cnvm", model, struct, model._graph(), 10_000, x0, t_eval, 10_000, spec)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    c, runs, sec = _cpu_rate("cnvm", x0, t_eval, 3, threads, row_ptr=rp, col=col, r_imit=params.r_imit,
+                            r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise,
+                            degree_alpha=np.ones(10_000))
+    out.append(dict(config="2: CNVM M=3 ER N=1e4 <d>=10, 1e4 realizations, 100 outputs (t_max=10)", gpu_events_per_s=g,
+                    cpu_events_per_s=c, cpu_threads=threads, cpu_sample=f"{runs} runs, {sec:.1f} s"))
+
+    # config 3: CNTM BA N=1e5 m=5, R=1e4
+    params, x0, rate = workloads.ba_cntm(100_000)
+    model = CNTM(params)
+    t_eval = np.linspace(0, 2.0, 11)
+    spec = (np.arange(2, dtype=np.int32), 1.0)
+    g, _ = _gpu_rate("cntm", model, model._struct(), model._graph(), 100_000, x0, t_eval, 10_000, spec)
+    rp, col = oracle.neighbor_list_to_csr(model.neighbor_list)
+    c, runs, sec = _cpu_rate("cntm", x0, t_eval, 2, threads, row_ptr=rp, col=col, next_event_rate=model.next_event_rate,
+                            noise_prob=model.noise_prob, threshold_01=0.5, threshold_10=0.5)
+    out.append(dict(config="3: CNTM BA N=1e5 m=5, r=1 r~=0.2 thr 0.5/0.5, 1e4 realizations (t_max=2 sample)",
+                    gpu_events_per_s=g, cpu_events_per_s=c, cpu_threads=threads, cpu_sample=f"{runs} runs, {sec:.1f} s"))
+
+    # config 4: SIS-as-CNVM WS N=1e6 (per-GPU share of 1e5 realizations: timed on 600)
+    params, x0, rate = workloads.sis_ws(1_000_000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    t_eval = np.linspace(0, 1.0, 11)
+    spec = (np.array([1], dtype=np.int32), 1e6)
+    g, _ = _gpu_rate("cnvm", model, struct, model._graph(), 1_000_000, x0, t_eval, 592, spec)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    c, runs, sec = _cpu_rate("cnvm", x0, t_eval, 2, threads, target_s=6.0, row_ptr=rp, col=col, r_imit=params.r_imit,
+                            r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise,
+                            degree_alpha=np.ones(1_000_000))
+    out.append(dict(config="4: SIS-as-CNVM WS N=1e6 k=10 p=0.1, lambda=1 (592 realizations, t_max=1 sample)",
+                    gpu_events_per_s=g, cpu_events_per_s=c, cpu_threads=threads, cpu_sample=f"{runs} runs, {sec:.1f} s"))
+
+    # config 5: one (r, r~) point of the sample_moments sweep on the H graph, fused integer moments (wall clock, host API)
+    from sponet_b200 import CNVMParameters
+
+    hp, hx0, _ = workloads.headline_cnvm(100_000)
+    p5 = CNVMParameters(num_opinions=2, network=hp.network, r=1.0, r_tilde=0.02)
+    x5 = (hx0 % 2).astype(np.uint8)
+    cv = OpinionShares(2, normalize=True)
+    sample_moments(p5, x5, 1.0, 11, 2000, rel_tol=1e9, collective_variable=cv, rng=np.random.default_rng(0))  # warm
+    t0 = time.perf_counter()
+    _, mean, var, n = sample_moments(p5, x5, 10.0, 101, 10_000, rel_tol=1e9, collective_variable=cv, rng=np.random.default_rng(1))
+    sec = time.perf_counter() - t0
+    ev = 10_000 * 10.0 * (p5.r_imit + p5.r_noise) * 100_000
+    out.append(dict(config="5: one point of the (r, r~) sweep: sample_moments, M=2, ER N=1e5, 1e4 runs, t_max=10, T=101",
+                    gpu_events_per_s=ev / sec, note=f"wall clock through sample_moments (host API), {sec:.2f} s per point",
+                    cpu_events_per_s=None))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/configs.json", "w") as fh:
+        json.dump(out, fh, indent=1)
+    for o in out:
+        print(json.dumps(o))
+    del keep
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,7 +448,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-configs", action="store_true", help="measure every BASELINE config shape (one GPU)")
     args = ap.parse_args()
+    if args.all_configs:
+        run_all_configs()
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return

@@ -38,6 +38,16 @@ from .utils import t_eval_to_ndarray
 
 # device memory budget for snapshot slabs when a CV has to be evaluated from stored states
 _SLAB_BYTES = int(os.environ.get("SPONET_B200_SLAB_BYTES", 2 << 30))
+# Complete graphs with a counts-only CV: the thread-per-chain count kernel needs tens of thousands of
+# chains to fill a B200; below that the warp-per-chain agent-level kernel is faster.  The choice
+# depends on the TOTAL number of chains of the call so that it does not change with the GPU count.
+_COUNT_ONLY_MIN_CHAINS = 20_000
+
+
+def use_count_only(model, kind, spec, total_chains: int) -> bool:
+    p = model.params
+    return (kind == "cnvm" and model.is_complete and p.num_opinions <= 16 and spec is not None and not spec.grouped
+            and spec.divisors is None and total_chains >= _COUNT_ONLY_MIN_CHAINS)
 
 
 def _split_runs(num_runs: int, num_chunks: int) -> np.ndarray:
@@ -167,7 +177,7 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
     if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
         spec = None  # grouped / weighted tables are kept by the CNVM agent-level kernel only
     if spec is not None:
-        if kind == "cnvm" and model.is_complete and p.num_opinions <= 16 and not spec.grouped and spec.divisors is None:
+        if use_count_only(model, kind, spec, S * num_runs):
             counts0 = np.stack([np.bincount(s, minlength=p.num_opinions) for s in states]).astype(np.int64)
             struct, keep = model._struct()
             _, local = engine.run_native("cnvm_counts", None, N, struct, None, t_out, seed, num_runs, rb, re,

@@ -23,7 +23,7 @@ from numpy.typing import ArrayLike, NDArray
 
 from . import _lib, engine
 from .collective_variables import CollectiveVariable
-from .multiprocessing import _dist, _kernel_cv_spec, _make_model, _split_runs, sample_many_runs
+from .multiprocessing import _dist, _kernel_cv_spec, _make_model, _split_runs, sample_many_runs, use_count_only
 from .parameters import Parameters
 
 
@@ -64,7 +64,7 @@ def batch_moment_sums(model, kind, state, t_grid, batch_size, cv, rng) -> tuple[
         x0 = np.ascontiguousarray(np.asarray(state, dtype=np.uint8)[None, :])
         if kind == "cnvm":
             struct, keep = model._struct()
-            if model.is_complete and p.num_opinions <= 16 and plain:
+            if plain and use_count_only(model, kind, spec, batch_size):
                 c0 = np.bincount(x0[0], minlength=p.num_opinions).astype(np.int64)[None, :]
                 engine.run_native("cnvm_counts", None, N, struct, None, t_grid, seed, batch_size, rb, re,
                                   cv_spec=spec, sums=sums, counts_init=c0)
