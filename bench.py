@@ -62,16 +62,21 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_capture() -> dict:
+    """Numbers of the committed ncu capture of the dominant kernel (profiles/traffic.json), or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
             with open(p) as fh:
-                return json.load(fh).get("cnvm_native_kernel_dram_bytes_per_launch")
+                return json.load(fh)
         except Exception:
             pass
-    return None
+    return {}
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    return ncu_capture().get("cnvm_native_kernel_dram_bytes_per_launch")
 
 
 class ClockSampler:
@@ -89,7 +94,8 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", os.environ.get("SPONET_BENCH_SMI_MS", "200")], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -295,7 +301,9 @@ def run_gpu_arm(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bytes_per_event,
-                         "kernel": "cnvm_native_kernel<2,smem,csr>", "note": "chain states live in shared memory and the CSR in L2, so DRAM traffic is far below the algorithmic bytes by design; the kernel is issue/latency bound (DESIGN.md section 5)"},
+                         "kernel": "cnvm_native_kernel<2,smem,csr,noalias,ring>",
+                         "ncu": {k: v for k, v in ncu_capture().items() if k.endswith("_pct") or k.startswith("warp_")},
+                         "note": "chain states live in shared memory and the CSR in L2, so DRAM traffic is far below the algorithmic bytes by design; the kernel is issue/latency bound (DESIGN.md section 5)"},
             "wall_s_timed_region": wall,
         }
         if world == 1 and not args.no_cpu_baseline:
