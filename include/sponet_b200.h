@@ -68,6 +68,18 @@ int sponet_graph_destroy(sponet_graph* g);
 int sponet_graph_info(const sponet_graph* g, int64_t* num_agents, int64_t* nnz, int32_t* min_degree,
                       int32_t* max_degree, int* device);
 
+/* Neighbour sampler table of native mode.  For networks with 1 <= degree <= 64 and at most 2^20 agents
+ * whose table fits 64 MiB, graph_create also builds L = 2^log2_slots >= max_degree slots per agent:
+ * neighbour k of a d-neighbour row owns the slot interval [k L / d, (k+1) L / d).  Entry (agent, slot j)
+ * = word0 | word1 << 32 with word0 = primary id | (thr >> 12) << 20, word1 = alias id | (thr & 0xFFF) << 20,
+ * primary = floor(j d / L), alias = primary + 1, thr = floor(((primary+1) L - j d) / d * 2^24) (0xFFFFFF and
+ * alias = primary when the slot lies inside one neighbour).  The CNVM kernel then draws
+ *     slot = r2 >> (32 - log2_slots), frac = ((r2 << log2_slots) >> 8), nbr = frac < thr ? primary : alias
+ * -- one 8-byte gather instead of the dependent row -> column pair; each neighbour keeps probability 1/d
+ * up to 2^-24 per slot.  *log2_slots = -1 when the graph has no table (the kernel then uses the CSR:
+ * nbr = col[begin + mulhi(r2, d)]).  `table` (HOST, [n << log2_slots]) may be NULL. */
+int sponet_graph_neighbor_table(const sponet_graph* g, int32_t* log2_slots, uint64_t* table);
+
 /* ---------------------------------------------------------------------------------------------
  * Model parameters as the reference loops receive them
  * ------------------------------------------------------------------------------------------- */

@@ -338,8 +338,38 @@ def native_poisson(seed, chain, interval, lam):
     return f(seed, chain, interval, lam)
 
 
+def build_neighbor_table(row_ptr, col):
+    """Independent numpy statement of the neighbour sampler table (include/sponet_b200.h,
+    sponet_graph_neighbor_table).  Returns (table uint64 [n << lg], lg) or (None, -1) when the graph is
+    not eligible (degree 0 or > 64, more than 2^20 agents, table above 64 MiB)."""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    deg = np.diff(row_ptr)
+    n = deg.size
+    if deg.min() < 1 or deg.max() > 64 or n > (1 << 20):
+        return None, -1
+    lg = 1
+    while (1 << lg) < deg.max():
+        lg += 1
+    L = 1 << lg
+    if n * L * 8 > (64 << 20):
+        return None, -1
+    j = np.arange(L, dtype=np.int64)[None, :]
+    d = deg[:, None]
+    k = j * d // L
+    num = (k + 1) * L - j * d
+    cont = num < d
+    base = row_ptr[:-1, None]
+    colv = np.asarray(col, dtype=np.int64)
+    id0 = colv[base + k]
+    id1 = np.where(cont, colv[np.minimum(base + k + 1, colv.size - 1)], id0)
+    thr = np.where(cont, (num << 24) // d, 0xFFFFFF)
+    w0 = id0 | ((thr >> 12) << 20)
+    w1 = id1 | ((thr & 0xFFF) << 20)
+    return (w0 | (w1 << 32)).astype(np.uint64).ravel(), lg
+
+
 def cnvm_native(x, M, row_ptr, col, noise_thr, thr_imit, thr_noise, alias_thr, alias, counts, seed, chain,
-                want_x=True):
+                want_x=True, nbtab=None, nbtab_log2=0):
     x = np.array(x, dtype=np.uint8)
     n = x.size
     counts = np.ascontiguousarray(counts, dtype=np.int64)
@@ -348,14 +378,16 @@ def cnvm_native(x, M, row_ptr, col, noise_thr, thr_imit, thr_noise, alias_thr, a
     out_c = np.empty((T, M), dtype=np.int64)
     acc = C.c_int64(0)
     f = lib().oracle_cnvm_native
-    f.argtypes = [_u8, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, _u32, _u32,
+    f.argtypes = [_u8, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, _u32, _u32,
                   C.c_void_p, C.c_void_p, _i64, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, _i64,
                   C.POINTER(C.c_int64)]
+    if nbtab is not None:
+        nbtab = np.ascontiguousarray(nbtab, dtype=np.uint64)
     ti = np.ascontiguousarray(thr_imit, dtype=np.uint32)
     tn = np.ascontiguousarray(thr_noise, dtype=np.uint32)
-    keep = [row_ptr, col, alias_thr, alias]
+    keep = [row_ptr, col, alias_thr, alias, nbtab]
     ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
-    ev = f(x, n, M, ptr(row_ptr), ptr(col), int(noise_thr), ti, tn, ptr(alias_thr), ptr(alias), counts,
+    ev = f(x, n, M, ptr(row_ptr), ptr(col), ptr(nbtab), int(nbtab_log2), int(noise_thr), ti, tn, ptr(alias_thr), ptr(alias), counts,
            T, seed, chain, ptr(out_x), out_c, C.byref(acc))
     del keep
     return out_x, out_c, ev, acc.value

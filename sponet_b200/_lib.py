@@ -92,6 +92,7 @@ _SIGNATURES = {
     "sponet_graph_create": (C.c_int, [_i64, _vp, _vp, C.POINTER(_vp)]),
     "sponet_graph_destroy": (C.c_int, [_vp]),
     "sponet_graph_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_int)]),
+    "sponet_graph_neighbor_table": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "sponet_cnvm_replay": (C.c_int, [_vp, _i64, C.POINTER(sponet_cnvm_params), _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sponet_cntm_replay": (C.c_int, [_vp, C.POINTER(sponet_cntm_params), _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sponet_cnvm_replay_all": (C.c_int, [_vp, _i64, C.POINTER(sponet_cnvm_params), _vp, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -119,7 +119,34 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
         int32_t* dst = reinterpret_cast<int32_t*>(col4.data() + row4[i].x);
         for (int32_t k = 0; k < row[i].y; ++k) dst[k] = col[row[i].x + k];
     }
+    // neighbour sampler table: agent i, slot j of L = 2^lg.  Neighbour k owns the slot interval
+    // [k L / d, (k+1) L / d); slot j belongs to its primary neighbour floor(j d / L) up to the boundary
+    // b = (primary + 1) L / d and to the next neighbour beyond it.  thr = floor(share * 2^24).
+    int lg = 1;
+    while ((1 << lg) < dmax) ++lg;
+    const bool use_tab = dmin >= 1 && dmax <= 64 && n <= (1 << 20) && ((int64_t)n << lg) * 8 <= ((int64_t)64 << 20);
+    std::vector<uint2> nbtab;
+    if (use_tab) {
+        const int64_t L = (int64_t)1 << lg;
+        nbtab.resize((size_t)(n * L));
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t d = row[i].y;
+            const int32_t* nb = col + row[i].x;
+            for (int64_t j = 0; j < L; ++j) {
+                const int64_t k = j * d / L;                 // primary neighbour of slot j
+                const int64_t num = (k + 1) * L - j * d;     // share of the slot owned by k, times d
+                uint32_t id0 = (uint32_t)nb[k], id1 = id0, thr = 0xFFFFFFu;
+                if (num < d) {                               // the slot continues into neighbour k + 1
+                    id1 = (uint32_t)nb[k + 1];
+                    thr = (uint32_t)((num << 24) / d);
+                }
+                nbtab[(size_t)(i * L + j)] = make_uint2(id0 | ((thr >> 12) << 20), id1 | ((thr & 0xFFFu) << 20));
+            }
+        }
+    }
     sponet_graph* g = new sponet_graph();
+    g->d_nbtab = nullptr;
+    g->nbtab_log2 = use_tab ? lg : 0;
     g->n_col4 = n4;
     g->n = n;
     g->nnz = nnz;
@@ -141,7 +168,10 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col4, col4.size() * sizeof(int4));
     if (e == cudaSuccess) e = cudaMemcpy(g->d_row4, row4.data(), n * sizeof(int2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_col4, col4.data(), col4.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && use_tab) e = cudaMalloc((void**)&g->d_nbtab, nbtab.size() * sizeof(uint2));
+    if (e == cudaSuccess && use_tab) e = cudaMemcpy(g->d_nbtab, nbtab.data(), nbtab.size() * sizeof(uint2), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
+        cudaFree(g->d_nbtab);
         cudaFree(g->d_row_ptr);
         cudaFree(g->d_row);
         cudaFree(g->d_col);
@@ -165,6 +195,7 @@ extern "C" int sponet_graph_destroy(sponet_graph* g) {
     cudaFree(g->d_col);
     cudaFree(g->d_row4);
     cudaFree(g->d_col4);
+    cudaFree(g->d_nbtab);
     if (cur != g->device) cudaSetDevice(cur);
     delete g;
     return SPONET_OK;
@@ -178,5 +209,19 @@ extern "C" int sponet_graph_info(const sponet_graph* g, int64_t* num_agents, int
     if (min_degree) *min_degree = g->min_degree;
     if (max_degree) *max_degree = g->max_degree;
     if (device) *device = g->device;
+    return SPONET_OK;
+}
+
+extern "C" int sponet_graph_neighbor_table(const sponet_graph* g, int32_t* log2_slots, uint64_t* table) {
+    SP_REQUIRE(g && log2_slots, "graph_neighbor_table: bad arguments");
+    *log2_slots = g->d_nbtab ? g->nbtab_log2 : -1;
+    if (g->d_nbtab && table) {
+        int cur = 0;
+        SP_CUDA(cudaGetDevice(&cur));
+        if (cur != g->device) SP_CUDA(cudaSetDevice(g->device));
+        cudaError_t e = cudaMemcpy(table, g->d_nbtab, ((size_t)g->n << g->nbtab_log2) * sizeof(uint2), cudaMemcpyDeviceToHost);
+        if (cur != g->device) cudaSetDevice(cur);
+        SP_CUDA(e);
+    }
     return SPONET_OK;
 }

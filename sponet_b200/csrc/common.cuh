@@ -52,6 +52,12 @@ struct sponet_graph {
     int2* d_row4;        // [n] (first int4 index, degree)
     int4* d_col4;        // [sum_i ceil(deg_i / 4)]
     int64_t n_col4;
+    // Neighbour sampler table (bounded-degree graphs that fit L2): 2^nbtab_log2 slots per agent, one
+    // 8-byte entry per slot = (primary id | thr_hi << 20, alias id | thr_lo << 20).  A uniformly drawn
+    // slot plus 24 further random bits select a uniformly distributed neighbour with ONE gather
+    // instead of the dependent row -> column pair (see sponet_graph_neighbor_table in the header).
+    uint2* d_nbtab;      // [n << nbtab_log2] or nullptr
+    int32_t nbtab_log2;
 };
 
 // ---------------------------------------------------------------------------------------------

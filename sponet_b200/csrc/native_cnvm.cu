@@ -25,6 +25,8 @@ struct NativeCnvmArgs {
     int32_t n, M;
     const int2* row;  // (begin, degree); nullptr = complete graph
     const int32_t* col;
+    const uint2* nbtab;  // neighbour sampler table (GRAPH == 2): [n << nbtab_log2]
+    int32_t nbtab_log2;
     uint32_t noise_thr;
     const uint2* alias_tab;  // (threshold, alias) per agent; nullptr = uniform agent weights
     const uint32_t* thr;  // [2*M*M]: imitation thresholds, then noise thresholds
@@ -119,7 +121,9 @@ __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named ba
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int BITS, bool SMEM, bool CSR, bool ALIAS, bool RING>
+// GRAPH: 0 = complete graph (no gather), 1 = CSR (row gather, then column gather), 2 = neighbour sampler
+// table (one gather; bounded-degree graphs whose table fits L2)
+template <int BITS, bool SMEM, int GRAPH, bool ALIAS, bool RING>
 __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
     constexpr bool THR4 = (BITS <= 2);      // M <= 4: threshold table padded to 4 x 4 per branch
@@ -389,12 +393,22 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             q_r2[s] = r.z;
             q_r3[s] = r.w;
             q_meta[s] = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
-            if (CSR) q_row[s] = __ldg(A.row + a);  // every lane gathers (no divergence); noise lanes ignore it
+            // every lane gathers (no divergence); noise lanes ignore the result
+            if (GRAPH == 1) q_row[s] = __ldg(A.row + a);
+            if (GRAPH == 2) {
+                const uint2 t = __ldg(A.nbtab + (((size_t)a << A.nbtab_log2) + (r.z >> (32 - A.nbtab_log2))));
+                q_row[s] = make_int2((int)t.x, (int)t.y);
+            }
         };
         auto issue2 = [&](int s) {
             uint32_t nbr;
-            if (CSR) {
+            if (GRAPH == 1) {
                 nbr = (uint32_t)__ldg(A.col + q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y));
+            } else if (GRAPH == 2) {
+                const uint32_t w0 = (uint32_t)q_row[s].x, w1 = (uint32_t)q_row[s].y;
+                const uint32_t thr = ((w0 >> 20) << 12) | (w1 >> 20);
+                const uint32_t frac = (q_r2[s] << A.nbtab_log2) >> 8;
+                nbr = (frac < thr ? w0 : w1) & 0xFFFFFu;
             } else {
                 nbr = __umulhi(q_r2[s], n - 1);
                 nbr += (nbr >= q_a[s]);
@@ -799,27 +813,33 @@ int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, 
 
 namespace {
 
-// kernel selection over (BITS, SMEM, CSR, ALIAS, RING); RING exists for shared-memory states only
+// kernel selection over (BITS, SMEM, GRAPH, ALIAS, RING); RING exists for shared-memory states only
 typedef void (*cnvm_kernel_t)(NativeCnvmArgs);
 
-template <int BITS, bool SMEM, bool CSR>
-cnvm_kernel_t pick_cnvm(bool alias, bool pair) {
-    if (SMEM && pair) return alias ? cnvm_native_kernel<BITS, SMEM, CSR, true, SMEM> : cnvm_native_kernel<BITS, SMEM, CSR, false, SMEM>;
-    return alias ? cnvm_native_kernel<BITS, SMEM, CSR, true, false> : cnvm_native_kernel<BITS, SMEM, CSR, false, false>;
+template <int BITS, bool SMEM, int GRAPH>
+cnvm_kernel_t pick_cnvm(bool alias, bool ring) {
+    if (SMEM && ring) return alias ? cnvm_native_kernel<BITS, SMEM, GRAPH, true, SMEM> : cnvm_native_kernel<BITS, SMEM, GRAPH, false, SMEM>;
+    return alias ? cnvm_native_kernel<BITS, SMEM, GRAPH, true, false> : cnvm_native_kernel<BITS, SMEM, GRAPH, false, false>;
+}
+
+template <int BITS, bool SMEM>
+cnvm_kernel_t pick_cnvm_g(int graph, bool alias, bool ring) {
+    if (graph == 2) return pick_cnvm<BITS, SMEM, 2>(alias, ring);
+    if (graph == 1) return pick_cnvm<BITS, SMEM, 1>(alias, ring);
+    return pick_cnvm<BITS, SMEM, 0>(alias, ring);
 }
 
 template <int BITS>
-cnvm_kernel_t pick_cnvm_b(bool smem, bool csr, bool alias, bool pair) {
-    if (smem) return csr ? pick_cnvm<BITS, true, true>(alias, pair) : pick_cnvm<BITS, true, false>(alias, pair);
-    return csr ? pick_cnvm<BITS, false, true>(alias, false) : pick_cnvm<BITS, false, false>(alias, false);
+cnvm_kernel_t pick_cnvm_b(bool smem, int graph, bool alias, bool ring) {
+    return smem ? pick_cnvm_g<BITS, true>(graph, alias, ring) : pick_cnvm_g<BITS, false>(graph, alias, false);
 }
 
-cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, bool csr, bool alias, bool pair) {
+cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, int graph, bool alias, bool ring) {
     switch (bits) {
-        case 1: return pick_cnvm_b<1>(smem, csr, alias, pair);
-        case 2: return pick_cnvm_b<2>(smem, csr, alias, pair);
-        case 4: return pick_cnvm_b<4>(smem, csr, alias, pair);
-        default: return pick_cnvm_b<8>(smem, csr, alias, pair);
+        case 1: return pick_cnvm_b<1>(smem, graph, alias, ring);
+        case 2: return pick_cnvm_b<2>(smem, graph, alias, ring);
+        case 4: return pick_cnvm_b<4>(smem, graph, alias, ring);
+        default: return pick_cnvm_b<8>(smem, graph, alias, ring);
     }
 }
 
@@ -910,6 +930,8 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         }
         A.row = g->d_row;
         A.col = g->d_col;
+        A.nbtab = g->d_nbtab;
+        A.nbtab_log2 = g->nbtab_log2;
     } else {
         SP_TRY(sponet_cnvm_event_rates(nullptr, n, p->degree_alpha[0], p->r_imit, p->r_noise,
                                        &next_event_rate, &noise_probability));
@@ -1012,8 +1034,8 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     }
     A.warps_per_cta = warps;
     const int threads = warps * 32;
-    const bool csr = g != nullptr;
-    cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, csr, A.alias_tab != nullptr, pair);
+    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
+    cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, graph_kind, A.alias_tab != nullptr, pair);
     SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int blocks_per_sm = 1;
     SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem_bytes));

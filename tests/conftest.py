@@ -42,3 +42,18 @@ def oracle():
 
     orc.build()
     return orc
+
+
+def library_neighbor_table(graph):
+    """(table uint64 [n << lg], lg) the library built for `graph` (an engine.GraphHandle), or (None, -1)."""
+    import ctypes as C
+
+    from sponet_b200 import _lib
+
+    lg = C.c_int32(0)
+    _lib.check(_lib.lib().sponet_graph_neighbor_table(graph.handle, C.byref(lg), None))
+    if lg.value < 0:
+        return None, -1
+    tab = np.empty(graph.num_agents << lg.value, dtype=np.uint64)
+    _lib.check(_lib.lib().sponet_graph_neighbor_table(graph.handle, C.byref(lg), tab.ctypes.data))
+    return tab, lg.value

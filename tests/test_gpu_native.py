@@ -8,7 +8,23 @@ import ctypes as C
 import numpy as np
 import pytest
 
+from conftest import library_neighbor_table
+
 pytestmark = pytest.mark.gpu
+
+
+def _nbtab(oracle, model, rp, col):
+    """The neighbour sampler table the library uses for this model's graph, cross-checked against the
+    oracle's independent construction.  (None, 0) for complete graphs / graphs without a table."""
+    if rp is None:
+        return None, 0
+    tab, lg = library_neighbor_table(model._graph())
+    exp, exp_lg = oracle.build_neighbor_table(rp, col)
+    assert lg == exp_lg
+    if tab is None:
+        return None, 0
+    np.testing.assert_array_equal(tab, exp)
+    return tab, lg
 
 R3 = np.array([[0, 1, 2], [1, 0, 1], [2, 0, 0]], dtype=float)
 RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
@@ -86,12 +102,13 @@ def test_cnvm_native_matches_sequential_oracle(oracle, kind, n, M, alpha, force_
     total_ev = total_acc = 0
     exp_sum = np.zeros((S, T, M), dtype=np.int64)
     exp_sq = np.zeros((S, T, M), dtype=np.int64)
+    nbtab, nblg = _nbtab(oracle, model, rp, col)
     for j in range(S):
         for i in range(R):
             chain = j * R + i
             counts = oracle.native_event_counts(seed, chain, 1, t_eval, rate)[0]
             ox, oc, ev, acc = oracle.cnvm_native(states[j], M, rp, col, noise_thr, thr_i, thr_n, alias_thr, alias,
-                                                 counts, seed, chain)
+                                                 counts, seed, chain, nbtab=nbtab, nbtab_log2=nblg)
             np.testing.assert_array_equal(out_x[j, i], ox, err_msg=f"states differ for chain ({j},{i})")
             np.testing.assert_array_equal(out_cv[j, i], oc.astype(float))
             exp_sum[j] += oc
@@ -227,11 +244,12 @@ def test_cnvm_pair_mode_matches_single_warp_and_oracle(oracle, n, M, alpha):
     else:
         prob, alias = oracle.build_alias_table(da)
         alias_thr = oracle.prob_to_thr(prob)
+    nbtab, nblg = _nbtab(oracle, model, rp, col)
     for i in range(3, 6):
         counts = oracle.native_event_counts(555, i, 1, t_eval, rate)[0]
         ox, oc, _, _ = oracle.cnvm_native(x0[0], M, rp, col, int(oracle.prob_to_thr(noise_p)),
                                           oracle.prob_to_thr(params.prob_imit), oracle.prob_to_thr(params.prob_noise),
-                                          alias_thr, alias, counts, 555, i)
+                                          alias_thr, alias, counts, 555, i, nbtab=nbtab, nbtab_log2=nblg)
         np.testing.assert_array_equal(xs[0, i - 3], ox)
         np.testing.assert_array_equal(cv[0, i - 3], oc.astype(float))
     del keep
@@ -326,3 +344,38 @@ def test_config3_cntm_ba_1e5_properties():
     assert (cv.sum(-1) == 100_000).all()
     np.testing.assert_array_equal(cv[:, 0], np.broadcast_to(np.bincount(x0, minlength=2), (R, 2)))
     assert abs(int(res[0][1][0]) / (R * 0.3 * rate) - 1) < 2e-3
+
+
+def test_neighbor_table_construction_and_uniformity(oracle):
+    """The table gives every neighbour probability 1/deg (up to 2^-24 per slot); graphs that are not
+    eligible (hubs above 64, isolated nodes) keep the CSR path."""
+    import networkx as nx
+
+    from sponet_b200 import engine
+    from sponet_b200.utils import calculate_neighbor_list
+
+    g = nx.fast_gnp_random_graph(400, 0.03, seed=1)
+    for v in list(nx.isolates(g)):
+        g.add_edge(v, (v + 1) % 400)
+    nl = calculate_neighbor_list(g)
+    gh = engine.GraphHandle(nl)
+    tab, lg = library_neighbor_table(gh)
+    rp, col = oracle.neighbor_list_to_csr(nl)
+    exp, exp_lg = oracle.build_neighbor_table(rp, col)
+    assert lg == exp_lg >= 1
+    np.testing.assert_array_equal(tab, exp)
+    L = 1 << lg
+    w0, w1 = (tab & 0xFFFFFFFF).astype(np.int64), (tab >> 32).astype(np.int64)
+    thr = ((w0 >> 20) << 12) | (w1 >> 20)
+    p0 = np.where((w0 & 0xFFFFF) == (w1 & 0xFFFFF), 1.0, thr / 2.0**24)
+    for a in (0, 7, 399):
+        prob = {}
+        for j in range(L):
+            e = a * L + j
+            prob[w0[e] & 0xFFFFF] = prob.get(w0[e] & 0xFFFFF, 0.0) + p0[e] / L
+            if p0[e] < 1.0:
+                prob[w1[e] & 0xFFFFF] = prob.get(w1[e] & 0xFFFFF, 0.0) + (1 - p0[e]) / L
+        assert sorted(prob) == sorted(int(v) for v in nl[a])
+        assert np.allclose(list(prob.values()), 1.0 / len(nl[a]), atol=2.0**-22)
+    star = calculate_neighbor_list(nx.star_graph(80))  # hub of degree 80
+    assert library_neighbor_table(engine.GraphHandle(star))[0] is None
