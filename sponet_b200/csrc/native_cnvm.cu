@@ -309,75 +309,9 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             }
         };
 
-        // ---- step generator: walks the per-interval event counts ahead of the commit ----
-        int gk = 1;
-        int64_t gK = 0;
-        uint64_t ge = 0;
-        uint32_t gsteps = 0;  // steps generated so far (every warp of a ring sees the same sequence)
-        int gsnaps = 0;       // output times completed by the steps generated so far
-        bool gdone = (T <= 1);
-        if (role == 0) snapshot(0);  // k = 0: the initial state
-        ++gsnaps;
-        if (!gdone) {
-            gK = kcounts[0];
-            while (gK == 0) {  // leading empty intervals repeat the initial state
-                if (role == 0) snapshot(gsnaps);
-                ++gsnaps;
-                if (++gk >= T) { gdone = true; break; }
-                gK = kcounts[gk - 1];
-            }
-        }
-        // returns false when the chain has no further step; otherwise (e0, nb, snaps) of the next one
-        auto gen = [&](uint64_t& e0, int& nb, int& snaps) -> bool {
-            e0 = ge;
-            snaps = 0;
-            nb = 0;
-            if (gdone) return false;
-            ++gsteps;
-            nb = gK < 32 ? (int)gK : 32;
-            ge += (uint64_t)nb;
-            gK -= nb;
-            if (gK == 0) {
-                snaps = 1;
-                for (;;) {
-                    if (++gk >= T) { gdone = true; break; }
-                    gK = kcounts[gk - 1];
-                    if (gK > 0) break;
-                    ++snaps;
-                }
-            }
-            gsnaps += snaps;
-            return true;
-        };
-
         // ---- stage registers, one set per in-flight own step (indices are compile-time after unrolling) ----
         uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3];
         int2 q_row[3];
-        int q_nb[3], q_snaps[3];
-        int q_base[3];  // index of the first output time this step completes
-        int q_next[3];  // RING: output times completed by the other warps' steps before our next own step
-        bool q_valid[3];
-
-        // next OWN step into set s (RING: also walks over the W-1 steps of the other warps that follow it)
-        auto gen_own = [&](int s, uint64_t& e0) -> bool {
-            q_next[s] = 0;
-            q_base[s] = gsnaps;
-            const bool v = gen(e0, q_nb[s], q_snaps[s]);
-            if (RING) {
-                uint64_t eo;
-                int nbo, sno;
-                for (int w = 1; w < W; ++w) {
-                    gen(eo, nbo, sno);
-                    q_next[s] += sno;
-                }
-            }
-            return v;
-        };
-        if (RING) {  // the steps before this warp's first own step belong to the warps before it
-            uint64_t eo;
-            int nbo, sno;
-            for (int w = 0; w < role; ++w) gen(eo, nbo, sno);
-        }
 
         auto issue1 = [&](int s, uint64_t e0) {
             const uint64_t e = e0 + (uint64_t)lane;
@@ -416,95 +350,85 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             q_nbr[s] = nbr;
         };
 
-        {
-            uint64_t e0;
-            q_next[2] = q_base[2] = 0;
-            q_valid[0] = gen_own(0, e0);
-            issue1(0, e0);
-            issue2(0);
-            q_valid[1] = gen_own(1, e0);
-            issue1(1, e0);
-            q_valid[2] = false;
-            q_a[2] = q_r2[2] = q_r3[2] = q_meta[2] = 0u;
-            q_row[2] = make_int2(0, 1);
-        }
+        uint32_t own_done = 0;  // own steps committed in this chain (RING: position in the hand-over ring)
+        // stage 3 + commit of the step held in register set `cur` (nb events)
+        auto process = [&](int cur, int nb) {
+            const uint32_t a = q_a[cur], r3 = q_r3[cur], meta = q_meta[cur];
+            const bool noise = meta & 1u;
+            const uint32_t nbr = noise ? a : q_nbr[cur];
+            
+            // ---- stage 3: flag lanes that may depend on another lane, exact masks for those ----
+            // Every lane inserts its agent into the warp's Bloom filter.  A lane is flagged when the bit
+            // of its agent was already set (an equal agent in this step, or a hash collision; the
+            // MATCH.ANY alternative costs ~20 % on B200) or when the bit of its neighbour is set (the
+            // neighbour may be another lane's agent).  Flagged lanes get exact masks from two ballots;
+            // lanes sharing the flagged lane's agent get theirs too, because the order of the atomic
+            // inserts says nothing about the lane order.
+            uint32_t dep = 0;
+            uint32_t flagged;
+            if (bloom_bits) {
+                const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
+                const uint32_t bit = 1u << (ha & 31);
+                bool hit = atomicOr(bloom + (ha >> 5), bit) & bit;
+                __syncwarp();
+                const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
+                hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
+                flagged = __ballot_sync(FULL, hit);
+                bloom[ha >> 5] = 0u;  // clear (every lane sharing the word stores the same value)
+            } else {
+                flagged = FULL;
+            }
+            for (uint32_t f = flagged; f; f &= f - 1) {  // usually zero iterations
+                const int il = __ffs(f) - 1;
+                const uint32_t ai = __shfl_sync(FULL, a, il), ni = __shfl_sync(FULL, nbr, il);
+                const uint32_t same_a = __ballot_sync(FULL, a == ai);
+                const uint32_t is_nbr = __ballot_sync(FULL, a == ni);
+                if (a == ai) dep |= same_a & lane_lt;
+                if (lane == il) dep |= is_nbr & lane_lt;
+            }
 
-        uint32_t own_done = 0;  // own steps committed in this chain
-        bool running = true;
-        while (running) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int cur = u, nx1 = (u + 1) % 3, nx2 = (u + 2) % 3;
-                if (!q_valid[cur]) { running = false; break; }
-                // advance the pipeline: next own step's column gather, the one after's Philox + row gather
-                if (!SP_GUARDS || q_valid[nx1]) issue2(nx1);
-                {
-                    uint64_t e0;
-                    q_valid[nx2] = gen_own(nx2, e0);
-                    if (!SP_GUARDS || q_valid[nx2]) issue1(nx2, e0);
-                }
+            // ---- RING: the step right before this one (the predecessor warp's) must be committed ----
+            if (RING) {
+                // our k-th own step follows the predecessor's k-th (role > 0) or (k-1)-th (role 0) step
+                if (role > 0) sp_mbar_wait(bar_pred, (pred_base + own_done) & 1u);
+                else if (own_done > 0) sp_mbar_wait(bar_pred, (pred_base + own_done - 1u) & 1u);
+                ++own_done;
+            }
 
-                const uint32_t a = q_a[cur], r3 = q_r3[cur], meta = q_meta[cur];
-                const bool noise = meta & 1u;
-                const uint32_t nbr = noise ? a : q_nbr[cur];
-                const int nb = q_nb[cur];
-
-                // ---- stage 3: flag lanes that may depend on another lane, exact masks for those ----
-                // Every lane inserts its agent into the warp's Bloom filter.  A lane is flagged when the bit
-                // of its agent was already set (an equal agent in this step, or a hash collision; the
-                // MATCH.ANY alternative costs ~20 % on B200) or when the bit of its neighbour is set (the
-                // neighbour may be another lane's agent).  Flagged lanes get exact masks from two ballots;
-                // lanes sharing the flagged lane's agent get theirs too, because the order of the atomic
-                // inserts says nothing about the lane order.
-                uint32_t dep = 0;
-                uint32_t flagged;
-                if (bloom_bits) {
-                    const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
-                    const uint32_t bit = 1u << (ha & 31);
-                    bool hit = atomicOr(bloom + (ha >> 5), bit) & bit;
-                    __syncwarp();
-                    const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
-                    hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
-                    flagged = __ballot_sync(FULL, hit);
-                    bloom[ha >> 5] = 0u;  // clear (every lane sharing the word stores the same value)
-                } else {
-                    flagged = FULL;
+            // ---- commit ----
+            const uint32_t wa = P::word(a), sa = P::shift(a);
+            const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
+            const bool active = lane < nb;
+            uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
+            uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
+            uint32_t th;
+            if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+            else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
+            else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
+            bool acc = active && sp_thr_accept(r3, th);
+            uint32_t hmask = 0;
+            if (flagged) {
+                const uint32_t wmask = __ballot_sync(FULL, acc);
+                hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
+            }
+            if (hmask == 0) {  // no lane reads what an earlier accepting lane writes: all commit
+                if (acc) {
+                    atomicXor(state + wa, (m ^ nw) << sa);
+                    ++my_acc;
+                    if (PACKCNT) {
+                        dpack += (1u << (8 * nw)) - (1u << (8 * m));
+                    } else {
+                        count_move(a, m, nw);
+                    }
                 }
-                for (uint32_t f = flagged; f; f &= f - 1) {  // usually zero iterations
-                    const int il = __ffs(f) - 1;
-                    const uint32_t ai = __shfl_sync(FULL, a, il), ni = __shfl_sync(FULL, nbr, il);
-                    const uint32_t same_a = __ballot_sync(FULL, a == ai);
-                    const uint32_t is_nbr = __ballot_sync(FULL, a == ni);
-                    if (a == ai) dep |= same_a & lane_lt;
-                    if (lane == il) dep |= is_nbr & lane_lt;
-                }
-
-                // ---- RING: the step right before this one (the predecessor warp's) must be committed ----
-                if (RING) {
-                    // our k-th own step follows the predecessor's k-th (role > 0) or (k-1)-th (role 0) step
-                    if (role > 0) sp_mbar_wait(bar_pred, (pred_base + own_done) & 1u);
-                    else if (own_done > 0) sp_mbar_wait(bar_pred, (pred_base + own_done - 1u) & 1u);
-                    ++own_done;
-                }
-
-                // ---- commit ----
-                const uint32_t wa = P::word(a), sa = P::shift(a);
-                const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
-                const bool active = lane < nb;
-                uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
-                uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                uint32_t th;
-                if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
-                else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
-                else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
-                bool acc = active && sp_thr_accept(r3, th);
-                uint32_t hmask = 0;
-                if (flagged) {
-                    const uint32_t wmask = __ballot_sync(FULL, acc);
-                    hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
-                }
-                if (hmask == 0) {  // no lane reads what an earlier accepting lane writes: all commit
-                    if (acc) {
+                if (!SMEM) __threadfence_block();
+                if (!RING) __syncwarp();  // RING: the mbarrier hand-over orders the writes
+            } else {  // rare: commit up to the first hazard, re-evaluate the rest
+                bool pending = active;
+                for (;;) {
+                    const int first = hmask ? (__ffs(hmask) - 1) : 32;
+                    const bool commit = acc && lane < first;
+                    if (commit) {
                         atomicXor(state + wa, (m ^ nw) << sa);
                         ++my_acc;
                         if (PACKCNT) {
@@ -513,43 +437,97 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                             count_move(a, m, nw);
                         }
                     }
+                    pending = pending && lane >= first;
                     if (!SMEM) __threadfence_block();
-                    if (!RING) __syncwarp();  // RING: the mbarrier hand-over orders the writes
-                } else {  // rare: commit up to the first hazard, re-evaluate the rest
-                    bool pending = active;
-                    for (;;) {
-                        const int first = hmask ? (__ffs(hmask) - 1) : 32;
-                        const bool commit = acc && lane < first;
-                        if (commit) {
-                            atomicXor(state + wa, (m ^ nw) << sa);
-                            ++my_acc;
-                            if (PACKCNT) {
-                                dpack += (1u << (8 * nw)) - (1u << (8 * m));
+                    __syncwarp();
+                    if (first == 32) break;
+                    ++n_extra;
+                    m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
+                    nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
+                    if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                    else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
+                    else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
+                    acc = pending && sp_thr_accept(r3, th);
+                    const uint32_t wmask = __ballot_sync(FULL, acc);
+                    hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
+                }
+            }
+            ++n_steps;
+            n_events += (uint32_t)nb;
+            if (PACKCNT && ++dsteps >= 120) fold_counts();
+        };
+
+        // ---- the chain: output interval by output interval ----
+        // Steps are numbered through the whole chain (RING: step s belongs to warp s mod W).  Inside an
+        // interval of K events the steps are full except the last one, so a warp only needs a counter for
+        // its own steps; the software pipeline (depth 2 over the warp's own steps) restarts per interval.
+        uint32_t s_mod = 0;   // steps of the chain so far, mod W
+        uint32_t gsteps = 0;  // steps of the chain so far
+        uint64_t E = 0;       // events of the chain so far
+        int k = 1;
+        if (role == 0) snapshot(0);  // k = 0: the initial state
+        while (k < T && kcounts[k - 1] == 0) {  // leading empty intervals repeat the initial state
+            if (role == 0) snapshot(k);
+            ++k;
+        }
+        int64_t K_left = k < T ? kcounts[k - 1] : 0;
+        while (k < T) {
+            // at most 2^30 steps at a time (32-bit step counters); the interval ends with the last chunk
+            const int64_t Kc = K_left > ((int64_t)1 << 35) ? ((int64_t)1 << 35) : K_left;
+            K_left -= Kc;
+            const bool ends = K_left == 0;
+            int k_next = k;
+            if (ends) {  // output times completed by the last step: k and the empty intervals right after it
+                k_next = k + 1;
+                while (k_next < T && kcounts[k_next - 1] == 0) ++k_next;
+            }
+            const int nsteps = (int)((Kc + 31) >> 5);
+            const int tail = (int)(Kc - 32 * (int64_t)(nsteps - 1));        // events of the last step
+            const int first = (int)((uint32_t)(role + W) - s_mod) % W;        // first own step of this chunk
+            const int n_own = nsteps > first ? (nsteps - first + W - 1) / W : 0;
+            const bool own_last = (int)((s_mod + (uint32_t)(nsteps - 1)) % (uint32_t)W) == role;
+            if (n_own > 0) {
+                const uint64_t e_stride = 32ull * (uint64_t)W;
+                uint64_t e_pre = E + 32ull * (uint64_t)first;  // first event of the next step to draw
+                issue1(0, e_pre);
+                e_pre += e_stride;
+                issue2(0);
+                if (n_own > 1) {
+                    issue1(1, e_pre);
+                    e_pre += e_stride;
+                }
+                for (int j0 = 0; j0 < n_own; j0 += 3) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int jj = j0 + u;
+                        if (jj >= n_own) break;
+                        // next own step's column gather, the one after's Philox + row gather
+                        if (jj + 1 < n_own) issue2((u + 1) % 3);
+                        if (jj + 2 < n_own) {
+                            issue1((u + 2) % 3, e_pre);
+                            e_pre += e_stride;
+                        }
+                        const bool last_of_chunk = first + jj * W == nsteps - 1;
+                        process(u, last_of_chunk ? tail : 32);
+                        if (jj == n_own - 1) {
+                            // the interval ends within the next W-1 steps: whoever owns its last step writes the
+                            // output time and needs every warp's count deltas
+                            if (ends && own_last) {
+                                for (int q = k; q < k_next; ++q) snapshot(q);
                             } else {
-                                count_move(a, m, nw);
+                                fold_counts();
                             }
                         }
-                        pending = pending && lane >= first;
-                        if (!SMEM) __threadfence_block();
-                        __syncwarp();
-                        if (first == 32) break;
-                        ++n_extra;
-                        m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
-                        nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                        if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
-                        else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
-                        else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
-                        acc = pending && sp_thr_accept(r3, th);
-                        const uint32_t wmask = __ballot_sync(FULL, acc);
-                        hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
+                        if (RING) sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
                     }
                 }
-                ++n_steps;
-                n_events += (uint32_t)nb;
-                // RING: another warp writes the next output time before our next own step -> it needs our deltas
-                if (PACKCNT && (++dsteps >= 120 || (RING && q_next[cur] > 0))) fold_counts();
-                for (int q = 0; q < q_snaps[cur]; ++q) snapshot(q_base[cur] + q);
-                if (RING) sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
+            }
+            s_mod = (s_mod + (uint32_t)nsteps) % (uint32_t)W;
+            gsteps += (uint32_t)nsteps;
+            E += (uint64_t)Kc;
+            if (ends) {
+                k = k_next;
+                K_left = k < T ? kcounts[k - 1] : 0;
             }
         }
         ev_total += n_events;
