@@ -102,14 +102,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")) -> dict:
+        """Summary of the samples taken inside [t_begin, t_end] (perf_counter clock)."""
         if self.proc is not None:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not (t_begin <= ts <= t_end):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -222,12 +225,13 @@ def run_gpu_arm(args) -> None:
         return engine.run_native("cnvm", graph, N_AGENTS, struct, d_x0, t_eval, seed, R_total, rb, re,
                                  cv_spec=spec, want_cv=True, counters=counters)
 
-    for w in range(args.warmup):
-        step(10 + w)
-    barrier()
-
+    # the sampler starts before the warm-up so that the timed steps follow the warm-up without an idle gap
+    # (an idle B200 drops its clocks within ~100 ms and the next launch pays the ramp); only the samples
+    # taken inside the timed region are reported
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for w in range(args.warmup):
+        step(10 + w)
     counters = torch.zeros(4, dtype=torch.int64, device="cuda")
     step_ms = []
     barrier()
@@ -241,8 +245,9 @@ def run_gpu_arm(args) -> None:
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
     barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    wall1 = time.perf_counter()
+    wall = wall1 - wall0
+    clocks = sampler.stop(wall0, wall1)
 
     c = counters.cpu().numpy().astype(np.float64)
     stats = torch.tensor([sum(step_ms), c[0], c[1]], dtype=torch.float64, device="cuda")

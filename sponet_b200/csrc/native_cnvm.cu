@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     constexpr bool THR4 = (BITS <= 2);      // M <= 4: threshold table padded to 4 x 4 per branch
     // M <= 4 and plain counts: count deltas packed per lane, folded lazily; a grouped / weighted CV
     // (A.cw) updates its table with shared-memory atomics on every accepted event instead
-    const bool PACKCNT = THR4 && A.cw == nullptr;
+    uint32_t packcnt_r = (THR4 && A.cw == nullptr) ? 1u : 0u;
+    asm volatile("" : "+r"(packcnt_r));  // keep the flag in a register (otherwise re-derived from the 64-bit pointer per use)
+    const bool PACKCNT = THR4 && packcnt_r != 0u;
     constexpr bool THR_SMEM = (BITS <= 4);  // M <= 16: threshold tables staged in shared memory
     constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -243,7 +245,6 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into the
         // shared counters before any field can leave [-127, 127]; 32-bit per-lane statistics with them.
         uint32_t dpack = 0, my_acc = 0, n_steps = 0, n_events = 0, n_extra = 0;
-        int dsteps = 0;
         auto fold_counts = [&]() {
             if (PACKCNT) {
                 uint32_t t = dpack;
@@ -263,7 +264,6 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                     if (M > 3) atomicAdd(&cnt_mem[3], s3);
                 }
                 dpack = 0;
-                dsteps = 0;
                 __syncwarp();
             }
         };
@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
         };
 
         uint32_t own_done = 0;  // own steps committed in this chain (RING: position in the hand-over ring)
+        const uint32_t wait_base = pred_base + (role == 0 ? 1u : 0u);
         // stage 3 + commit of the step held in register set `cur` (nb events)
         auto process = [&](int cur, int nb) {
             const uint32_t a = q_a[cur], r3 = q_r3[cur], meta = q_meta[cur];
@@ -389,9 +390,9 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
 
             // ---- RING: the step right before this one (the predecessor warp's) must be committed ----
             if (RING) {
-                // our k-th own step follows the predecessor's k-th (role > 0) or (k-1)-th (role 0) step
-                if (role > 0) sp_mbar_wait(bar_pred, (pred_base + own_done) & 1u);
-                else if (own_done > 0) sp_mbar_wait(bar_pred, (pred_base + own_done - 1u) & 1u);
+                // our k-th own step follows the predecessor's k-th (role > 0) or (k-1)-th (role 0) step; for
+                // role 0's first step that is the phase before the barrier's current one, complete by definition
+                sp_mbar_wait(bar_pred, (wait_base + own_done) & 1u);
                 ++own_done;
             }
 
@@ -454,7 +455,6 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             }
             ++n_steps;
             n_events += (uint32_t)nb;
-            if (PACKCNT && ++dsteps >= 120) fold_counts();
         };
 
         // ---- the chain: output interval by output interval ----
@@ -487,39 +487,44 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             const int n_own = nsteps > first ? (nsteps - first + W - 1) / W : 0;
             const bool own_last = (int)((s_mod + (uint32_t)(nsteps - 1)) % (uint32_t)W) == role;
             if (n_own > 0) {
+                // The pipeline always runs two own steps ahead, also past the end of the chunk: the draws of a
+                // step that does not exist are valid gathers that nobody consumes (two per chunk and warp),
+                // which keeps the loop body free of prefetch conditions.
                 const uint64_t e_stride = 32ull * (uint64_t)W;
                 uint64_t e_pre = E + 32ull * (uint64_t)first;  // first event of the next step to draw
                 issue1(0, e_pre);
                 e_pre += e_stride;
                 issue2(0);
-                if (n_own > 1) {
-                    issue1(1, e_pre);
-                    e_pre += e_stride;
-                }
-                for (int j0 = 0; j0 < n_own; j0 += 3) {
+                issue1(1, e_pre);
+                e_pre += e_stride;
+                int rem = n_own;  // own steps left in this chunk
+                while (rem > 0) {
+                    // blocks of at most 120 own steps (a multiple of the 3 register sets): the packed count
+                    // deltas of a lane move by at most 1 per step and are folded after each block
+                    const int stop = rem > 120 ? rem - 120 : 0;
+                    while (rem > stop) {
 #pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int jj = j0 + u;
-                        if (jj >= n_own) break;
-                        // next own step's column gather, the one after's Philox + row gather
-                        if (jj + 1 < n_own) issue2((u + 1) % 3);
-                        if (jj + 2 < n_own) {
-                            issue1((u + 2) % 3, e_pre);
+                        for (int u = 0; u < 3; ++u) {
+                            if (rem == stop) break;
+                            issue2((u + 1) % 3);              // next own step: column gather
+                            issue1((u + 2) % 3, e_pre);       // the one after: Philox + row gather
                             e_pre += e_stride;
-                        }
-                        const bool last_of_chunk = first + jj * W == nsteps - 1;
-                        process(u, last_of_chunk ? tail : 32);
-                        if (jj == n_own - 1) {
-                            // the interval ends within the next W-1 steps: whoever owns its last step writes the
-                            // output time and needs every warp's count deltas
-                            if (ends && own_last) {
-                                for (int q = k; q < k_next; ++q) snapshot(q);
-                            } else {
-                                fold_counts();
+                            const bool last_own = rem == 1;   // the chunk's last step, if ours, is our last one
+                            process(u, (last_own && own_last) ? tail : 32);
+                            if (last_own) {
+                                // the interval ends within the next W-1 steps: whoever owns its last step writes
+                                // the output times and needs every warp's count deltas
+                                if (ends && own_last) {
+                                    for (int q = k; q < k_next; ++q) snapshot(q);
+                                } else {
+                                    fold_counts();
+                                }
                             }
+                            if (RING) sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
+                            --rem;
                         }
-                        if (RING) sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
                     }
+                    if (rem > 0) fold_counts();
                 }
             }
             s_mod = (s_mod + (uint32_t)nsteps) % (uint32_t)W;
