@@ -96,7 +96,9 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // A/B on B200 (H workload): 9 chains x 2 warps = 576 threads caps the kernel at 96 registers and spills
 // (4.0e10 events/s); 8 x 2 = 512 threads keeps 118 registers (6.3e10, vs 5.9e10 for 9 single warps).
 // Whether every lane or one lane arrives on the mbarrier makes no measurable difference.
+#ifndef SP_RING_MAX_THREADS
 #define SP_RING_MAX_THREADS 512
+#endif
 
 __device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -117,6 +119,11 @@ __device__ __forceinline__ void sp_mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ uint32_t sp_lds(uint32_t saddr) {  // load through a 32-bit shared-window address
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named barrier of one chain's warps
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -124,7 +131,7 @@ __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named ba
 // GRAPH: 0 = complete graph (no gather), 1 = CSR (row gather, then column gather), 2 = neighbour sampler
 // table (one gather; bounded-degree graphs whose table fits L2)
 template <int BITS, bool SMEM, int GRAPH, bool ALIAS, bool RING>
-__global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
+__global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
     constexpr bool THR4 = (BITS <= 2);      // M <= 4: threshold table padded to 4 x 4 per branch
     // M <= 4 and plain counts: count deltas packed per lane, folded lazily; a grouped / weighted CV
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     // thr: M <= 4 -> 32 entries indexed (noise << 4 | m << 2 | nw); M <= 16 -> 2*MM entries
     uint32_t* sp = smem;
     const uint32_t* thr = A.thr;
+    const uint32_t thr4_saddr = (uint32_t)__cvta_generic_to_shared(smem);  // THR4: the padded table sits first
     if (THR4) {
         for (int i = threadIdx.x; i < 32; i += blockDim.x) {
             const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
@@ -330,7 +338,8 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             // every lane gathers (no divergence); noise lanes ignore the result
             if (GRAPH == 1) q_row[s] = __ldg(A.row + a);
             if (GRAPH == 2) {
-                const uint2 t = __ldg(A.nbtab + (((size_t)a << A.nbtab_log2) + (r.z >> (32 - A.nbtab_log2))));
+                // slot index (a << lg) | (top lg bits of r2) in one funnel shift; the table has < 2^26 entries
+                const uint2 t = __ldg(A.nbtab + __funnelshift_l(r.z, a, (uint32_t)A.nbtab_log2));
                 q_row[s] = make_int2((int)t.x, (int)t.y);
             }
         };
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
             uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
             uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
             uint32_t th;
-            if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+            if (THR4) th = sp_lds(thr4_saddr + ((((meta & 1u) << 4) | (m << 2) | nw) << 2));
             else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
             else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
             bool acc = active && sp_thr_accept(r3, th);
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(512, 1) cnvm_native_kernel(NativeCnvmArgs A) {
                     ++n_extra;
                     m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
                     nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                    if (THR4) th = thr[((meta & 1u) << 4) | (m << 2) | nw];
+                    if (THR4) th = sp_lds(thr4_saddr + ((((meta & 1u) << 4) | (m << 2) | nw) << 2));
                     else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
                     else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
                     acc = pending && sp_thr_accept(r3, th);
