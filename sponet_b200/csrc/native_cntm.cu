@@ -107,8 +107,7 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
 
         int my_delta = 0;  // per-lane change of the number of ones since the last snapshot
         uint32_t my_acc = 0, n_steps = 0, n_events = 0, n_extra = 0;
-        int ksnap = 0;
-        auto snapshot = [&]() {
+        auto snapshot = [&](int k) {
             c1 += __reduce_add_sync(FULL, my_delta);
             acc_total += __reduce_add_sync(FULL, my_acc);
             ev_total += n_events;
@@ -116,7 +115,6 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
             extra_total += n_extra;
             my_delta = 0;
             my_acc = n_events = n_steps = n_extra = 0;
-            const int k = ksnap++;
             const int64_t snap = cl * (int64_t)T + k;
             if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
@@ -137,45 +135,9 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
             }
         };
 
-        // ---- step generator (same as the CNVM kernel) ----
-        int gk = 1;
-        int64_t gK = 0;
-        uint64_t ge = 0;
-        bool gdone = (T <= 1);
-        snapshot();
-        if (!gdone) {
-            gK = kcounts[0];
-            while (gK == 0) {
-                snapshot();
-                if (++gk >= T) { gdone = true; break; }
-                gK = kcounts[gk - 1];
-            }
-        }
-        auto gen = [&](uint64_t& e0, int& nb, int& snaps) -> bool {
-            e0 = ge;
-            snaps = 0;
-            nb = 0;
-            if (gdone) return false;
-            nb = gK < 32 ? (int)gK : 32;
-            ge += (uint64_t)nb;
-            gK -= nb;
-            if (gK == 0) {
-                snaps = 1;
-                for (;;) {
-                    if (++gk >= T) { gdone = true; break; }
-                    gK = kcounts[gk - 1];
-                    if (gK > 0) break;
-                    ++snaps;
-                }
-            }
-            return true;
-        };
-
         uint32_t q_a[3], q_meta[3];
         int2 q_row[3];
         int4 q_c0[3], q_c1[3];
-        int q_nb[3], q_snaps[3];
-        bool q_valid[3];
         const int4 none = make_int4(-1, -1, -1, -1);
 
         auto issue1 = [&](int s, uint64_t e0) {
@@ -192,139 +154,158 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
             q_c1[s] = chunks > 1 ? __ldg(A.col4 + q_row[s].x + 1) : none;
         };
 
-        {
-            uint64_t e0;
-            q_valid[0] = gen(e0, q_nb[0], q_snaps[0]);
-            issue1(0, e0);
-            issue2(0);
-            q_valid[1] = gen(e0, q_nb[1], q_snaps[1]);
-            issue1(1, e0);
-            q_valid[2] = false;
-            q_a[2] = q_meta[2] = 0u;
-            q_row[2] = make_int2(0, 0);
-        }
+        // stage 3 + commit of the step held in register set `cur` (nb events)
+        auto process = [&](int cur, int nb) {
+            const uint32_t a = q_a[cur], meta = q_meta[cur];
+            const bool noise = meta & 1u;
+            const int2 row = q_row[cur];
+            const int deg = noise ? 0 : row.y;  // a noise event reads no neighbour
+            const int chunks = (deg + 3) >> 2;
+            const bool active = lane < nb;
+            const uint32_t wa = a >> 5, ba = a & 31;
 
-        bool running = true;
-        while (running) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int cur = u, nx1 = (u + 1) % 3, nx2 = (u + 2) % 3;
-                if (!q_valid[cur]) { running = false; break; }
-                if (q_valid[nx1]) issue2(nx1);
-                {
-                    uint64_t e0;
-                    q_valid[nx2] = gen(e0, q_nb[nx2], q_snaps[nx2]);
-                    if (q_valid[nx2]) issue1(nx2, e0);
-                }
-
-                const uint32_t a = q_a[cur], meta = q_meta[cur];
-                const bool noise = meta & 1u;
-                const int2 row = q_row[cur];
-                const int deg = noise ? 0 : row.y;  // a noise event reads no neighbour
-                const int chunks = (deg + 3) >> 2;
-                const int nb = q_nb[cur];
-                const bool active = lane < nb;
-                const uint32_t wa = a >> 5, ba = a & 31;
-
-                // opposite-opinion count over the lane's row; PROBE also tests the Bloom filter
-                uint32_t xa, nw;
-                bool hit = false;
-                auto scan = [&](bool probe) {
-                    xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
-                    const uint32_t other = xa ^ 1u;
-                    int cnt = 0;
-                    auto one = [&](int v) {
-                        const bool ok = v >= 0;
-                        const uint32_t vv = ok ? (uint32_t)v : 0u;
-                        const uint32_t bitv = (st_load<SMEM>(state + (vv >> 5)) >> (vv & 31)) & 1u;
-                        cnt += (int)(ok & (bitv == other));
-                        if (probe && bloom_bits) {
-                            const uint32_t h = __umulhi(vv * 2654435761u, bloom_bits);
-                            hit |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
-                        }
-                    };
-                    auto four = [&](const int4& v) { one(v.x); one(v.y); one(v.z); one(v.w); };
-                    if (chunks > 0) four(q_c0[cur]);
-                    if (chunks > 1) four(q_c1[cur]);
-                    for (int c = 2; c < chunks; ++c) four(__ldg(A.col4 + row.x + c));
-                    if (noise) {
-                        nw = meta >> 1;
-                    } else {
-                        const int need = deg > 0 ? __ldg((xa ? A.need10 : A.need01) + deg) : 0x7fffffff;
-                        nw = cnt >= need ? other : xa;
+            // opposite-opinion count over the lane's row; PROBE also tests the Bloom filter
+            uint32_t xa, nw;
+            bool hit = false;
+            auto scan = [&](bool probe) {
+                xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
+                const uint32_t other = xa ^ 1u;
+                int cnt = 0;
+                auto one = [&](int v) {
+                    const bool ok = v >= 0;
+                    const uint32_t vv = ok ? (uint32_t)v : 0u;
+                    const uint32_t bitv = (st_load<SMEM>(state + (vv >> 5)) >> (vv & 31)) & 1u;
+                    cnt += (int)(ok & (bitv == other));
+                    if (probe && bloom_bits) {
+                        const uint32_t h = __umulhi(vv * 2654435761u, bloom_bits);
+                        hit |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
                     }
                 };
-
-                // ---- Bloom insert of the agents, first scan with probes ----
-                uint32_t flagged;
-                if (bloom_bits) {
-                    const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
-                    const uint32_t bit = 1u << (ha & 31);
-                    hit = atomicOr(bloom + (ha >> 5), bit) & bit;  // an equal agent (or a collision)
-                    __syncwarp();
-                    scan(true);
-                    flagged = __ballot_sync(FULL, hit);
-                    bloom[ha >> 5] = 0u;
+                auto four = [&](const int4& v) { one(v.x); one(v.y); one(v.z); one(v.w); };
+                if (chunks > 0) four(q_c0[cur]);
+                if (chunks > 1) four(q_c1[cur]);
+                for (int c = 2; c < chunks; ++c) four(__ldg(A.col4 + row.x + c));
+                if (noise) {
+                    nw = meta >> 1;
                 } else {
-                    scan(false);
-                    flagged = FULL;
+                    const int need = deg > 0 ? __ldg((xa ? A.need10 : A.need01) + deg) : 0x7fffffff;
+                    nw = cnt >= need ? other : xa;
                 }
-                // exact masks for flagged lanes: earlier lanes whose agent is this lane's agent or one of
-                // its neighbours (the flagged lane's row is re-walked by the whole warp)
-                uint32_t dep = 0;
-                for (uint32_t f = flagged; f; f &= f - 1) {
-                    const int il = __ffs(f) - 1;
-                    const uint32_t ai = __shfl_sync(FULL, a, il);
-                    const int rx = __shfl_sync(FULL, row.x, il), ch = __shfl_sync(FULL, chunks, il);
-                    const uint32_t same_a = __ballot_sync(FULL, a == ai);
-                    uint32_t touch = same_a;
-                    for (int c = 0; c < ch; ++c) {
-                        const int4 v = __ldg(A.col4 + rx + c);
-                        touch |= __ballot_sync(FULL, ((int)a == v.x) | ((int)a == v.y) | ((int)a == v.z) | ((int)a == v.w));
-                    }
-                    if (a == ai) dep |= same_a & lane_lt;
-                    if (lane == il) dep |= touch & lane_lt;
-                }
+            };
 
-                // ---- commit ----
-                bool chg = active && nw != xa;
-                uint32_t hmask = 0;
-                if (flagged) {
-                    const uint32_t wmask = __ballot_sync(FULL, chg);
-                    hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
+            // ---- Bloom insert of the agents, first scan with probes ----
+            uint32_t flagged;
+            if (bloom_bits) {
+                const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
+                const uint32_t bit = 1u << (ha & 31);
+                hit = atomicOr(bloom + (ha >> 5), bit) & bit;  // an equal agent (or a collision)
+                __syncwarp();
+                scan(true);
+                flagged = __ballot_sync(FULL, hit);
+                bloom[ha >> 5] = 0u;
+            } else {
+                scan(false);
+                flagged = FULL;
+            }
+            // exact masks for flagged lanes: earlier lanes whose agent is this lane's agent or one of
+            // its neighbours (the flagged lane's row is re-walked by the whole warp)
+            uint32_t dep = 0;
+            for (uint32_t f = flagged; f; f &= f - 1) {
+                const int il = __ffs(f) - 1;
+                const uint32_t ai = __shfl_sync(FULL, a, il);
+                const int rx = __shfl_sync(FULL, row.x, il), ch = __shfl_sync(FULL, chunks, il);
+                const uint32_t same_a = __ballot_sync(FULL, a == ai);
+                uint32_t touch = same_a;
+                for (int c = 0; c < ch; ++c) {
+                    const int4 v = __ldg(A.col4 + rx + c);
+                    touch |= __ballot_sync(FULL, ((int)a == v.x) | ((int)a == v.y) | ((int)a == v.z) | ((int)a == v.w));
                 }
-                if (hmask == 0) {
-                    if (chg) {
+                if (a == ai) dep |= same_a & lane_lt;
+                if (lane == il) dep |= touch & lane_lt;
+            }
+
+            // ---- commit ----
+            bool chg = active && nw != xa;
+            uint32_t hmask = 0;
+            if (flagged) {
+                const uint32_t wmask = __ballot_sync(FULL, chg);
+                hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
+            }
+            if (hmask == 0) {
+                if (chg) {
+                    atomicXor(state + wa, 1u << ba);
+                    my_delta += (int)nw - (int)xa;
+                    ++my_acc;
+                }
+                if (!SMEM) __threadfence_block();
+                __syncwarp();
+            } else {
+                bool pending = active;
+                for (;;) {
+                    const int first = hmask ? (__ffs(hmask) - 1) : 32;
+                    const bool commit = chg && lane < first;
+                    if (commit) {
                         atomicXor(state + wa, 1u << ba);
                         my_delta += (int)nw - (int)xa;
                         ++my_acc;
                     }
+                    pending = pending && lane >= first;
                     if (!SMEM) __threadfence_block();
                     __syncwarp();
-                } else {
-                    bool pending = active;
-                    for (;;) {
-                        const int first = hmask ? (__ffs(hmask) - 1) : 32;
-                        const bool commit = chg && lane < first;
-                        if (commit) {
-                            atomicXor(state + wa, 1u << ba);
-                            my_delta += (int)nw - (int)xa;
-                            ++my_acc;
-                        }
-                        pending = pending && lane >= first;
-                        if (!SMEM) __threadfence_block();
-                        __syncwarp();
-                        if (first == 32) break;
-                        ++n_extra;
-                        scan(false);  // every lane re-scans (cheap relative to how rare this is)
-                        chg = pending && nw != xa;
-                        const uint32_t wmask = __ballot_sync(FULL, chg);
-                        hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
-                    }
+                    if (first == 32) break;
+                    ++n_extra;
+                    scan(false);  // every lane re-scans (cheap relative to how rare this is)
+                    chg = pending && nw != xa;
+                    const uint32_t wmask = __ballot_sync(FULL, chg);
+                    hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
                 }
-                ++n_steps;
-                n_events += (uint32_t)nb;
-                for (int q = 0; q < q_snaps[cur]; ++q) snapshot();
+            }
+            ++n_steps;
+            n_events += (uint32_t)nb;
+        };
+
+        // ---- the chain: output interval by output interval (same structure as the CNVM kernel) ----
+        // Inside an interval of K events all steps are full except the last; the depth-2 pipeline restarts
+        // per interval and always runs two steps ahead (the draws past the end are valid, unused gathers).
+        uint64_t E = 0;  // events of the chain so far
+        int k = 1;
+        snapshot(0);
+        while (k < T && kcounts[k - 1] == 0) snapshot(k++);  // leading empty intervals repeat the initial state
+        int64_t K_left = k < T ? kcounts[k - 1] : 0;
+        while (k < T) {
+            const int64_t Kc = K_left > ((int64_t)1 << 35) ? ((int64_t)1 << 35) : K_left;  // 32-bit step counters
+            K_left -= Kc;
+            const bool ends = K_left == 0;
+            int k_next = k;
+            if (ends) {
+                k_next = k + 1;
+                while (k_next < T && kcounts[k_next - 1] == 0) ++k_next;
+            }
+            const int nsteps = (int)((Kc + 31) >> 5);
+            const int tail = (int)(Kc - 32 * (int64_t)(nsteps - 1));
+            uint64_t e_pre = E;
+            issue1(0, e_pre);
+            e_pre += 32;
+            issue2(0);
+            issue1(1, e_pre);
+            e_pre += 32;
+            int rem = nsteps;
+            while (rem > 0) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    if (rem == 0) break;
+                    issue2((u + 1) % 3);
+                    issue1((u + 2) % 3, e_pre);
+                    e_pre += 32;
+                    process(u, rem == 1 ? tail : 32);
+                    --rem;
+                }
+            }
+            E += (uint64_t)Kc;
+            if (ends) {
+                for (int q = k; q < k_next; ++q) snapshot(q);
+                k = k_next;
+                K_left = k < T ? kcounts[k - 1] : 0;
             }
         }
         c1 += __reduce_add_sync(FULL, my_delta);
