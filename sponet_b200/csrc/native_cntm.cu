@@ -58,8 +58,9 @@ __device__ __forceinline__ uint32_t st_load(const uint32_t* p) {
     return __ldcg(p);
 }
 
+#define SP_CNTM_MAX_WARPS 16
 template <bool SMEM>
-__global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
+__global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(NativeCntmArgs A) {
     constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -67,7 +68,11 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
     const uint32_t noise_thr = A.noise_thr;
     const uint32_t lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
 
-    // shared layout: [bloom W*bloom_words] [states W*words (if SMEM)]
+    // per warp: 32 partial neighbour counts + one word of Bloom hits for the cooperative row tails
+    __shared__ int s_coop[SP_CNTM_MAX_WARPS][33];
+    int* coop = s_coop[warp];
+    for (int i = lane; i < 33; i += 32) coop[i] = 0;
+    // dynamic layout: [bloom W*bloom_words] [states W*words (if SMEM)]
     uint32_t* sp = smem;
     const uint32_t bloom_bits = (uint32_t)A.bloom_words * 32u;
     uint32_t* bloom = sp + (size_t)warp * A.bloom_words;
@@ -164,27 +169,72 @@ __global__ void __launch_bounds__(512, 1) cntm_native_kernel(NativeCntmArgs A) {
             const bool active = lane < nb;
             const uint32_t wa = a >> 5, ba = a & 31;
 
-            // opposite-opinion count over the lane's row; PROBE also tests the Bloom filter
+            // Opposite-opinion count over the lane's row; PROBE also tests the Bloom filter.  The first two
+            // chunks (8 neighbours) were gathered by the pipeline and are scanned by the lane itself.  The
+            // rest of all 32 rows is one shared work list of (lane, chunk) items dealt out to the whole
+            // warp: with heavy-tailed degrees the longest row of a step is ~6x the mean, and a per-lane
+            // loop would run the warp at the pace of that one lane.
             uint32_t xa, nw;
             bool hit = false;
             auto scan = [&](bool probe) {
                 xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
                 const uint32_t other = xa ^ 1u;
                 int cnt = 0;
-                auto one = [&](int v) {
+                auto one = [&](int v, uint32_t oth, int& c_out, bool& h_out) {
                     const bool ok = v >= 0;
                     const uint32_t vv = ok ? (uint32_t)v : 0u;
                     const uint32_t bitv = (st_load<SMEM>(state + (vv >> 5)) >> (vv & 31)) & 1u;
-                    cnt += (int)(ok & (bitv == other));
+                    c_out += (int)(ok & (bitv == oth));
                     if (probe && bloom_bits) {
                         const uint32_t h = __umulhi(vv * 2654435761u, bloom_bits);
-                        hit |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
+                        h_out |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
                     }
                 };
-                auto four = [&](const int4& v) { one(v.x); one(v.y); one(v.z); one(v.w); };
-                if (chunks > 0) four(q_c0[cur]);
-                if (chunks > 1) four(q_c1[cur]);
-                for (int c = 2; c < chunks; ++c) four(__ldg(A.col4 + row.x + c));
+                auto four = [&](const int4& v, uint32_t oth, int& c_out, bool& h_out) {
+                    one(v.x, oth, c_out, h_out);
+                    one(v.y, oth, c_out, h_out);
+                    one(v.z, oth, c_out, h_out);
+                    one(v.w, oth, c_out, h_out);
+                };
+                if (chunks > 0) four(q_c0[cur], other, cnt, hit);
+                if (chunks > 1) four(q_c1[cur], other, cnt, hit);
+                // ---- cooperative tail ----
+                const int t = chunks > 2 ? chunks - 2 : 0;
+                int inc = t;  // inclusive prefix sum over the lanes
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                const int total = __shfl_sync(FULL, inc, 31);
+                if (total > 0) {  // warp-uniform
+                    for (int base = 0; base < total; base += 32) {
+                        const int it = base + lane;
+                        int o = 0;  // owner of item `it`: the number of lanes whose prefix sum is <= it
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) {
+                            const int v = __shfl_sync(FULL, inc, o + sft - 1);
+                            if (v <= it) o += sft;
+                        }
+                        const int first_item = __shfl_sync(FULL, inc - t, o);
+                        const int rx = __shfl_sync(FULL, row.x, o);
+                        const uint32_t oth = __shfl_sync(FULL, other, o);
+                        if (it < total) {
+                            const int4 v = __ldg(A.col4 + rx + 2 + (it - first_item));
+                            int c_it = 0;
+                            bool h_it = false;
+                            four(v, oth, c_it, h_it);
+                            if (c_it) atomicAdd(&coop[o], c_it);
+                            if (h_it) atomicOr((uint32_t*)&coop[32], 1u << o);
+                        }
+                    }
+                    __syncwarp();
+                    cnt += coop[lane];
+                    hit |= (bool)(((uint32_t)coop[32] >> lane) & 1u);
+                    __syncwarp();
+                    coop[lane] = 0;
+                    if (lane == 0) coop[32] = 0;
+                }
                 if (noise) {
                     nw = meta >> 1;
                 } else {
@@ -428,7 +478,7 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.words = (int32_t)((n + 31) / 32);
     cudaDeviceProp prop;
     SP_CUDA(cudaGetDeviceProperties(&prop, dev));
-    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    const size_t smem_max = prop.sharedMemPerBlockOptin - SP_CNTM_MAX_WARPS * 33 * 4;  // minus the static arrays
     const size_t chain_bytes = (size_t)A.words * 4;
     bool smem_state = !o->force_global_state;
     int warps = 0;
