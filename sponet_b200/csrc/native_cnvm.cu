@@ -404,6 +404,11 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 sp_mbar_wait(bar_pred, (wait_base + own_done) & 1u);
                 ++own_done;
             }
+            // The next own step's neighbour comes out of the entry gathered more than a step ago.  Doing
+            // this here, in a block of its own behind the wait, keeps it away from the gather issued at the
+            // top of this step: in one block ptxas put the two on one scoreboard and the consumer then
+            // waited for the fresh load (10 % of all stall samples).
+            issue2((cur + 1) % 3);
 
             // ---- commit ----
             const uint32_t wa = P::word(a), sa = P::shift(a);
@@ -515,8 +520,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
                             if (rem == stop) break;
-                            issue2((u + 1) % 3);              // next own step: column gather
-                            issue1((u + 2) % 3, e_pre);       // the one after: Philox + row gather
+                            issue1((u + 2) % 3, e_pre);       // two own steps ahead: Philox + gather
                             e_pre += e_stride;
                             const bool last_own = rem == 1;   // the chunk's last step, if ours, is our last one
                             process(u, (last_own && own_last) ? tail : 32);
