@@ -140,44 +140,70 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
             }
         };
 
-        uint32_t q_a[3], q_meta[3];
-        int2 q_row[3];
-        int4 q_c0[3], q_c1[3];
+        // ---- software pipeline: three steps in flight, ONE copy of the step body ----
+        // Set 0 is the step being committed (agent, flags, row, first two neighbour chunks), set 1 the next
+        // one (its chunks are gathered while set 0 commits), set 2 the one after (Philox + row gather).
+        // The sets rotate through register moves instead of a 3x unrolled body: the body is large (the row
+        // scan), and three copies of it plus their re-scan paths overflowed the instruction cache
+        // (no_instruction was 33 % of the stall samples).
+        uint32_t a0 = 0, meta0 = 0, a1 = 0, meta1 = 0, a2 = 0, meta2 = 0;
+        int2 row0 = make_int2(0, 0), row1 = row0, row2 = row0;
         const int4 none = make_int4(-1, -1, -1, -1);
+        int4 c00 = none, c01 = none, c10 = none, c11 = none;
 
-        auto issue1 = [&](int s, uint64_t e0) {
+        auto draw = [&](uint64_t e0, uint32_t& a, uint32_t& meta, int2& row) {
             const uint64_t e = e0 + (uint64_t)lane;
             const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
-            const uint32_t a = __umulhi(r.y, n);
-            q_a[s] = a;
-            q_meta[s] = (uint32_t)(r.x < noise_thr) | ((r.z >> 31) << 1);  // bit 0 noise, bit 1 the noise opinion
-            q_row[s] = __ldg(A.row4 + a);
+            a = __umulhi(r.y, n);
+            meta = (uint32_t)(r.x < noise_thr) | ((r.z >> 31) << 1);  // bit 0 noise, bit 1 the noise opinion
+            row = __ldg(A.row4 + a);
         };
-        auto issue2 = [&](int s) {
-            const int chunks = (q_row[s].y + 3) >> 2;
-            q_c0[s] = chunks > 0 ? __ldg(A.col4 + q_row[s].x) : none;
-            q_c1[s] = chunks > 1 ? __ldg(A.col4 + q_row[s].x + 1) : none;
+        auto gather = [&](const int2& row, int4& c0, int4& c1) {
+            const int chunks = (row.y + 3) >> 2;
+            c0 = chunks > 0 ? __ldg(A.col4 + row.x) : none;
+            c1 = chunks > 1 ? __ldg(A.col4 + row.x + 1) : none;
         };
 
-        // stage 3 + commit of the step held in register set `cur` (nb events)
-        auto process = [&](int cur, int nb) {
-            const uint32_t a = q_a[cur], meta = q_meta[cur];
+        // stage 3 + commit of the step in set 0 (nb events)
+        auto process = [&](int nb) {
+            const uint32_t a = a0, meta = meta0;
             const bool noise = meta & 1u;
-            const int2 row = q_row[cur];
+            const int2 row = row0;
             const int deg = noise ? 0 : row.y;  // a noise event reads no neighbour
             const int chunks = (deg + 3) >> 2;
-            const bool active = lane < nb;
             const uint32_t wa = a >> 5, ba = a & 31;
 
-            // Opposite-opinion count over the lane's row; PROBE also tests the Bloom filter.  The first two
-            // chunks (8 neighbours) were gathered by the pipeline and are scanned by the lane itself.  The
-            // rest of all 32 rows is one shared work list of (lane, chunk) items dealt out to the whole
-            // warp: with heavy-tailed degrees the longest row of a step is ~6x the mean, and a per-lane
-            // loop would run the warp at the pace of that one lane.
-            uint32_t xa, nw;
+            // tails of the rows beyond the two gathered chunks: one work list of (lane, chunk) items for
+            // the whole warp.  With heavy-tailed degrees the longest row of a step is ~6x the mean and a
+            // per-lane loop would run the warp at the pace of that one lane.
+            const int t = chunks > 2 ? chunks - 2 : 0;
+            int inc = t;  // inclusive prefix sum of the tail lengths over the lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += v;
+            }
+            const int total = __shfl_sync(FULL, inc, 31);
+
+            // ---- Bloom insert of the agents ----
+            uint32_t ha = 0;
             bool hit = false;
-            auto scan = [&](bool probe) {
-                xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
+            if (bloom_bits) {
+                ha = __umulhi(a * 2654435761u, bloom_bits);
+                const uint32_t bit = 1u << (ha & 31);
+                hit = atomicOr(bloom + (ha >> 5), bit) & bit;  // an equal agent (or a collision)
+                __syncwarp();
+            }
+
+            // Rounds: the first one scans every row (probing the Bloom filter with every neighbour), flags
+            // the lanes that may depend on an earlier lane and builds their exact masks; lanes up to the
+            // first hazard commit, the rest re-scan in the next round.  Almost always there is one round.
+            bool pending = lane < nb;
+            bool first_round = true;
+            uint32_t dep = 0, flagged = 0;
+#pragma unroll 1
+            for (;;) {
+                const uint32_t xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
                 const uint32_t other = xa ^ 1u;
                 int cnt = 0;
                 auto one = [&](int v, uint32_t oth, int& c_out, bool& h_out) {
@@ -185,7 +211,7 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                     const uint32_t vv = ok ? (uint32_t)v : 0u;
                     const uint32_t bitv = (st_load<SMEM>(state + (vv >> 5)) >> (vv & 31)) & 1u;
                     c_out += (int)(ok & (bitv == oth));
-                    if (probe && bloom_bits) {
+                    if (bloom_bits) {  // (a re-scan probes the cleared filter: no hits, and none are used)
                         const uint32_t h = __umulhi(vv * 2654435761u, bloom_bits);
                         h_out |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
                     }
@@ -196,18 +222,10 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                     one(v.z, oth, c_out, h_out);
                     one(v.w, oth, c_out, h_out);
                 };
-                if (chunks > 0) four(q_c0[cur], other, cnt, hit);
-                if (chunks > 1) four(q_c1[cur], other, cnt, hit);
-                // ---- cooperative tail ----
-                const int t = chunks > 2 ? chunks - 2 : 0;
-                int inc = t;  // inclusive prefix sum over the lanes
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(FULL, inc, d);
-                    if (lane >= d) inc += v;
-                }
-                const int total = __shfl_sync(FULL, inc, 31);
+                if (chunks > 0) four(c00, other, cnt, hit);
+                if (chunks > 1) four(c01, other, cnt, hit);
                 if (total > 0) {  // warp-uniform
+#pragma unroll 1
                     for (int base = 0; base < total; base += 32) {
                         const int it = base + lane;
                         int o = 0;  // owner of item `it`: the number of lanes whose prefix sum is <= it
@@ -219,14 +237,12 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                         const int first_item = __shfl_sync(FULL, inc - t, o);
                         const int rx = __shfl_sync(FULL, row.x, o);
                         const uint32_t oth = __shfl_sync(FULL, other, o);
-                        if (it < total) {
-                            const int4 v = __ldg(A.col4 + rx + 2 + (it - first_item));
-                            int c_it = 0;
-                            bool h_it = false;
-                            four(v, oth, c_it, h_it);
-                            if (c_it) atomicAdd(&coop[o], c_it);
-                            if (h_it) atomicOr((uint32_t*)&coop[32], 1u << o);
-                        }
+                        const int4 v = it < total ? __ldg(A.col4 + rx + 2 + (it - first_item)) : none;
+                        int c_it = 0;
+                        bool h_it = false;
+                        four(v, oth, c_it, h_it);
+                        if (c_it) atomicAdd(&coop[o], c_it);
+                        if (h_it) atomicOr((uint32_t*)&coop[32], 1u << o);
                     }
                     __syncwarp();
                     cnt += coop[lane];
@@ -235,88 +251,65 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                     coop[lane] = 0;
                     if (lane == 0) coop[32] = 0;
                 }
+                uint32_t nw;
                 if (noise) {
                     nw = meta >> 1;
                 } else {
                     const int need = deg > 0 ? __ldg((xa ? A.need10 : A.need01) + deg) : 0x7fffffff;
                     nw = cnt >= need ? other : xa;
                 }
-            };
 
-            // ---- Bloom insert of the agents, first scan with probes ----
-            uint32_t flagged;
-            if (bloom_bits) {
-                const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
-                const uint32_t bit = 1u << (ha & 31);
-                hit = atomicOr(bloom + (ha >> 5), bit) & bit;  // an equal agent (or a collision)
-                __syncwarp();
-                scan(true);
-                flagged = __ballot_sync(FULL, hit);
-                bloom[ha >> 5] = 0u;
-            } else {
-                scan(false);
-                flagged = FULL;
-            }
-            // exact masks for flagged lanes: earlier lanes whose agent is this lane's agent or one of
-            // its neighbours (the flagged lane's row is re-walked by the whole warp)
-            uint32_t dep = 0;
-            for (uint32_t f = flagged; f; f &= f - 1) {
-                const int il = __ffs(f) - 1;
-                const uint32_t ai = __shfl_sync(FULL, a, il);
-                const int rx = __shfl_sync(FULL, row.x, il), ch = __shfl_sync(FULL, chunks, il);
-                const uint32_t same_a = __ballot_sync(FULL, a == ai);
-                uint32_t touch = same_a;
-                for (int c = 0; c < ch; ++c) {
-                    const int4 v = __ldg(A.col4 + rx + c);
-                    touch |= __ballot_sync(FULL, ((int)a == v.x) | ((int)a == v.y) | ((int)a == v.z) | ((int)a == v.w));
+                if (first_round) {
+                    first_round = false;
+                    if (bloom_bits) {
+                        flagged = __ballot_sync(FULL, hit);
+                        bloom[ha >> 5] = 0u;
+                    } else {
+                        flagged = FULL;
+                    }
+                    // exact masks for flagged lanes: earlier lanes whose agent is this lane's agent or one
+                    // of its neighbours (the flagged lane's row is re-walked by the whole warp)
+                    for (uint32_t f = flagged; f; f &= f - 1) {
+                        const int il = __ffs(f) - 1;
+                        const uint32_t ai = __shfl_sync(FULL, a, il);
+                        const int rx = __shfl_sync(FULL, row.x, il), ch = __shfl_sync(FULL, chunks, il);
+                        const uint32_t same_a = __ballot_sync(FULL, a == ai);
+                        uint32_t touch = same_a;
+                        for (int c = 0; c < ch; ++c) {
+                            const int4 v = __ldg(A.col4 + rx + c);
+                            touch |= __ballot_sync(FULL, ((int)a == v.x) | ((int)a == v.y) | ((int)a == v.z) | ((int)a == v.w));
+                        }
+                        if (a == ai) dep |= same_a & lane_lt;
+                        if (lane == il) dep |= touch & lane_lt;
+                    }
                 }
-                if (a == ai) dep |= same_a & lane_lt;
-                if (lane == il) dep |= touch & lane_lt;
-            }
 
-            // ---- commit ----
-            bool chg = active && nw != xa;
-            uint32_t hmask = 0;
-            if (flagged) {
-                const uint32_t wmask = __ballot_sync(FULL, chg);
-                hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
-            }
-            if (hmask == 0) {
-                if (chg) {
+                // ---- commit up to the first hazard ----
+                const bool chg = pending && nw != xa;
+                uint32_t hmask = 0;
+                if (flagged) {
+                    const uint32_t wmask = __ballot_sync(FULL, chg);
+                    hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
+                }
+                const int first = hmask ? (__ffs(hmask) - 1) : 32;
+                if (chg && lane < first) {
                     atomicXor(state + wa, 1u << ba);
                     my_delta += (int)nw - (int)xa;
                     ++my_acc;
                 }
+                pending = pending && lane >= first;
                 if (!SMEM) __threadfence_block();
                 __syncwarp();
-            } else {
-                bool pending = active;
-                for (;;) {
-                    const int first = hmask ? (__ffs(hmask) - 1) : 32;
-                    const bool commit = chg && lane < first;
-                    if (commit) {
-                        atomicXor(state + wa, 1u << ba);
-                        my_delta += (int)nw - (int)xa;
-                        ++my_acc;
-                    }
-                    pending = pending && lane >= first;
-                    if (!SMEM) __threadfence_block();
-                    __syncwarp();
-                    if (first == 32) break;
-                    ++n_extra;
-                    scan(false);  // every lane re-scans (cheap relative to how rare this is)
-                    chg = pending && nw != xa;
-                    const uint32_t wmask = __ballot_sync(FULL, chg);
-                    hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
-                }
+                if (first == 32) break;
+                ++n_extra;
             }
             ++n_steps;
             n_events += (uint32_t)nb;
         };
 
         // ---- the chain: output interval by output interval (same structure as the CNVM kernel) ----
-        // Inside an interval of K events all steps are full except the last; the depth-2 pipeline restarts
-        // per interval and always runs two steps ahead (the draws past the end are valid, unused gathers).
+        // Inside an interval of K events all steps are full except the last; the pipeline restarts per
+        // interval and always runs two steps ahead (the draws past the end are valid, unused gathers).
         uint64_t E = 0;  // events of the chain so far
         int k = 1;
         snapshot(0);
@@ -334,22 +327,19 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
             const int nsteps = (int)((Kc + 31) >> 5);
             const int tail = (int)(Kc - 32 * (int64_t)(nsteps - 1));
             uint64_t e_pre = E;
-            issue1(0, e_pre);
+            draw(e_pre, a0, meta0, row0);
             e_pre += 32;
-            issue2(0);
-            issue1(1, e_pre);
+            gather(row0, c00, c01);
+            draw(e_pre, a1, meta1, row1);
             e_pre += 32;
-            int rem = nsteps;
-            while (rem > 0) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    if (rem == 0) break;
-                    issue2((u + 1) % 3);
-                    issue1((u + 2) % 3, e_pre);
-                    e_pre += 32;
-                    process(u, rem == 1 ? tail : 32);
-                    --rem;
-                }
+#pragma unroll 1
+            for (int rem = nsteps; rem > 0; --rem) {
+                gather(row1, c10, c11);
+                draw(e_pre, a2, meta2, row2);
+                e_pre += 32;
+                process(rem == 1 ? tail : 32);
+                a0 = a1, meta0 = meta1, row0 = row1, c00 = c10, c01 = c11;
+                a1 = a2, meta1 = meta2, row1 = row2;
             }
             E += (uint64_t)Kc;
             if (ends) {
