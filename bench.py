@@ -306,7 +306,7 @@ def run_gpu_arm(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bytes_per_event,
-                         "kernel": "cnvm_native_kernel<2,smem,csr,noalias,ring>",
+                         "kernel": "cnvm_native_kernel<2,smem,nbtab,noalias,ring>",
                          "ncu": {k: v for k, v in ncu_capture().items() if k.endswith("_pct") or k.startswith("warp_")},
                          "note": "chain states live in shared memory and the CSR in L2, so DRAM traffic is far below the algorithmic bytes by design; the kernel is issue/latency bound (DESIGN.md section 5)"},
             "wall_s_timed_region": wall,
