@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPONET_ABI_VERSION 1
+#define SPONET_ABI_VERSION 2
 
 enum {
     SPONET_OK = 0,
@@ -175,7 +175,24 @@ typedef struct {
     const int32_t* agent_class;  /* [n] HOST, NULL = class 0                                    */
     const int32_t* agent_weight; /* [n] HOST integer weights (may be negative), NULL = 1        */
     const double* divisors;      /* [D] HOST per-output divisors, NULL = `divisor` for all      */
+    /* Edge collective variables of a two-opinion model, evaluated at every output time by a scan of
+     * `graph` against the chain state held on chip (no snapshot leaves the SM):
+     *   SPONET_CV_INTERFACES    D = 1: #edges {u,v} with x[u] != x[v]       (collective_variables.py:259-305)
+     *   SPONET_CV_PROPENSITIES  D = 2: out[m] = sum over agents j in state m of
+     *                           r[m,n] * #{neighbours of j in state n} / degree_alpha[j] + r_tilde[m,n],
+     *                           n = 1 - m                                    (collective_variables.py:308-384)
+     * The result is divided by `divisor` (normalize: number of edges / number of agents).  idx,
+     * agent_class, agent_weight and divisors are ignored for these kinds; out_sum / out_sumsq are
+     * available for INTERFACES only (integer counts). */
+    int32_t kind;                /* SPONET_CV_SHARES (0) | SPONET_CV_INTERFACES | SPONET_CV_PROPENSITIES */
+    const sponet_graph* graph;   /* kinds 1, 2: the CV's own network (Interfaces(network) need not be the model's) */
+    const double* degree_alpha;  /* kind 2: [n] HOST, d(j)^alpha (collective_variables.py:353-356)      */
+    double rates[4];             /* kind 2: r[0,1], r[1,0], r_tilde[0,1], r_tilde[1,0]                   */
 } sponet_shares_cv;
+
+#define SPONET_CV_SHARES 0
+#define SPONET_CV_INTERFACES 1
+#define SPONET_CV_PROPENSITIES 2
 
 typedef struct {
     uint64_t seed;

@@ -261,6 +261,33 @@ def opinion_shares(x, M, weights=None):
     return out
 
 
+def interfaces(x, row_ptr, col):
+    """sponet/collective_variables.py:293-301: number of edges {u, v} with x[u] != x[v], per snapshot
+    (the reference loops over network.edges; here over the CSR entries with u < v)."""
+    x = np.atleast_2d(np.asarray(x))
+    rp = np.asarray(row_ptr, dtype=np.int64)
+    src = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    dst = np.asarray(col, dtype=np.int64)
+    keep = src < dst
+    return (x[:, src[keep]] != x[:, dst[keep]]).sum(axis=1).astype(np.float64)[:, None]
+
+
+def propensities(x, row_ptr, col, degrees_alpha, r, r_tilde):
+    """sponet/collective_variables.py:370-383 (_propensities_numba): sequential f64 sums over the agents j,
+    out[i, m] += r[m, n] * #{neighbours of j with opinion n} / degrees_alpha[j] + r_tilde[m, n]."""
+    x = np.atleast_2d(np.asarray(x))
+    r, r_tilde = np.asarray(r, dtype=np.float64), np.asarray(r_tilde, dtype=np.float64)
+    da = np.asarray(degrees_alpha, dtype=np.float64)
+    out = np.zeros((x.shape[0], 2))
+    for j in range(x.shape[1]):
+        nbrs = col[row_ptr[j] : row_ptr[j + 1]]
+        for i in range(x.shape[0]):
+            m, n = (0, 1) if x[i, j] == 0 else (1, 0)
+            count = np.float64(np.sum(x[i, nbrs] == n))
+            out[i, m] += r[m, n] * count / da[j] + r_tilde[m, n]
+    return out
+
+
 def argmatch(x_ref, x):
     """sponet/utils.py:7-45."""
     x_ref = np.ascontiguousarray(x_ref, dtype=np.float64)

@@ -63,6 +63,10 @@ class sponet_shares_cv(C.Structure):
         ("agent_class", C.c_void_p),
         ("agent_weight", C.c_void_p),
         ("divisors", C.c_void_p),
+        ("kind", C.c_int32),
+        ("graph", C.c_void_p),
+        ("degree_alpha", C.c_void_p),
+        ("rates", C.c_double * 4),
     ]
 
 
@@ -125,7 +129,7 @@ def lib() -> C.CDLL:
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args
-            if L.sponet_abi_version() != 1:
+            if L.sponet_abi_version() != 2:
                 raise ImportError("libsponet_b200.so: ABI version mismatch, rebuild the library")
             _lib = L
     return _lib

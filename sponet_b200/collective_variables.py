@@ -184,7 +184,7 @@ class CompositeCollectiveVariable:
         from .engine import KernelCV
 
         specs = [cv._kernel_spec(num_agents) if hasattr(cv, "_kernel_spec") else None for cv in self.collective_variables]
-        if not specs or any(sp is None for sp in specs):
+        if not specs or any(sp is None or sp.edge for sp in specs):
             return None
 
         def same(a, b):
@@ -237,6 +237,15 @@ class Interfaces:
         self._neighbor_list = calculate_neighbor_list(network)
         self._graphs = GraphCache()
 
+    def _kernel_spec(self, num_agents: int):
+        """In-kernel: the simulation kernels scan this CV's CSR against the on-chip state per output time."""
+        from .engine import KernelCV
+
+        if len(self._neighbor_list) != num_agents:
+            return None
+        div = float(self.network.number_of_edges()) if self.normalize else 1.0
+        return KernelCV([], div, kind=KernelCV.INTERFACES, graph=self._graphs.get(self._neighbor_list))
+
     def __call__(self, x):
         xs, was_1d = _host_states(x)
         if xs.size and np.max(xs) > 1:
@@ -260,6 +269,18 @@ class Propensities:
         self.params = params
         self.normalize = normalize
         self._graphs = GraphCache()
+
+    def _kernel_spec(self, num_agents: int):
+        """In-kernel on a network (the complete-graph form is evaluated from stored states)."""
+        from .engine import KernelCV
+
+        p = self.params
+        if p.network is None or p.num_agents != num_agents or p.num_opinions != 2:
+            return None
+        das = np.array([len(nb) for nb in p.network]) ** p.alpha
+        r, rt = np.asarray(p.r, dtype=np.float64), np.asarray(p.r_tilde, dtype=np.float64)
+        return KernelCV([], float(p.num_agents) if self.normalize else 1.0, kind=KernelCV.PROPENSITIES,
+                        graph=self._graphs.get(p.network), degree_alpha=das, rates=(r[0, 1], r[1, 0], rt[0, 1], rt[1, 0]))
 
     def __call__(self, x):
         xs, was_1d = _host_states(x)

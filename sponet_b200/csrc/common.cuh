@@ -197,7 +197,53 @@ inline uint32_t sp_prob_to_thr(double p) {
 }
 
 // launchers implemented in the kernel translation units --------------------------------------
+// Edge collective variable of a two-opinion chain (sponet_shares_cv.kind != 0), evaluated from the 1-bit
+// packed state: one warp strides over the agents and walks each agent's CSR row.
+struct SpEdgeCv {
+    int32_t kind;      // 0 none, SPONET_CV_INTERFACES, SPONET_CV_PROPENSITIES
+    const int2* row;   // (begin, degree) of the CV's network
+    const int32_t* col;
+    const double* da;  // PROPENSITIES: d(j)^alpha
+    double r01, r10, rt01, rt10;
+};
+
+// iface = number of ordered pairs (j, v in N(j)) with x[j] != x[v] (twice the interface count);
+// p0 / p1 = the two propensity sums.  Every lane returns the warp totals (fixed reduction tree).
+template <bool SMEM>
+__device__ __noinline__ void sp_edge_cv_scan(const uint32_t* state, uint32_t n, const SpEdgeCv& E, int lane,
+                                             unsigned long long* iface, double* p0, double* p1) {
+    auto bit = [&](uint32_t a) {
+        const uint32_t w = SMEM ? state[a >> 5] : __ldcg(state + (a >> 5));
+        return (w >> (a & 31)) & 1u;
+    };
+    unsigned int diff = 0;
+    double a0 = 0.0, a1 = 0.0;
+    for (uint32_t j = (uint32_t)lane; j < n; j += 32) {
+        const uint32_t xj = bit(j);
+        const int2 r = __ldg(E.row + j);
+        unsigned int c = 0;
+        for (int e = 0; e < r.y; ++e) c += bit((uint32_t)__ldg(E.col + r.x + e)) ^ xj;
+        diff += c;
+        if (E.kind == SPONET_CV_PROPENSITIES) {
+            const double dj = __ldg(E.da + j);
+            if (xj == 0) a0 += __dadd_rn(__ddiv_rn(__dmul_rn(E.r01, (double)c), dj), E.rt01);
+            else a1 += __dadd_rn(__ddiv_rn(__dmul_rn(E.r10, (double)c), dj), E.rt10);
+        }
+    }
+    unsigned long long t = diff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    *iface = t;
+    *p0 = a0;
+    *p1 = a1;
+}
+
 struct SpCvDev {
+    SpEdgeCv ecv;
     int32_t D;
     const int32_t* d_idx;  // device [D]
     double divisor;

@@ -44,6 +44,7 @@ struct NativeCntmArgs {
     int32_t D;
     const int32_t* cv_idx;
     double cv_div;
+    SpEdgeCv ecv;  // Interfaces / Propensities (kind != 0): replaces the share outputs
     unsigned long long* counters;
     uint32_t* gstate;
     int32_t words;
@@ -121,7 +122,27 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
             my_delta = 0;
             my_acc = n_events = n_steps = n_extra = 0;
             const int64_t snap = cl * (int64_t)T + k;
-            if (A.out_cv || A.out_sum) {
+            if (A.ecv.kind != 0) {  // edge CV: scan the CV's graph against the on-chip state
+                if (A.out_cv || A.out_sum) {
+                    unsigned long long twice;
+                    double p0, p1;
+                    sp_edge_cv_scan<SMEM>(state, n, A.ecv, lane, &twice, &p0, &p1);
+                    if (lane == 0) {
+                        if (A.ecv.kind == SPONET_CV_INTERFACES) {
+                            const long long c = (long long)(twice >> 1);  // every edge was seen from both ends
+                            if (A.out_cv) A.out_cv[snap] = (A.cv_div == 1.0) ? (double)c : (double)c / A.cv_div;
+                            if (A.out_sum) {
+                                const int64_t o = j * (int64_t)T + k;
+                                atomicAdd(A.out_sum + o, (unsigned long long)c);
+                                atomicAdd(A.out_sumsq + o, (unsigned long long)(c * c));
+                            }
+                        } else if (A.out_cv) {
+                            A.out_cv[snap * 2 + 0] = (A.cv_div == 1.0) ? p0 : p0 / A.cv_div;
+                            A.out_cv[snap * 2 + 1] = (A.cv_div == 1.0) ? p1 : p1 / A.cv_div;
+                        }
+                    }
+                }
+            } else if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
                     const long long c = A.cv_idx[d] == 1 ? (long long)c1 : (long long)n - c1;
                     if (A.out_cv)
@@ -430,9 +451,12 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
         A.need10 = d_need + g->max_degree + 1;
     }
     SpCvDev cvd;
-    SP_TRY(sp_stage_cv(sc, cv, 2, &cvd, 0));
+    SP_TRY(sp_stage_cv(sc, cv, 2, &cvd, (cv && cv->kind != SPONET_CV_SHARES) ? (int64_t)g->n : 0));
     if (cvd.d_divisors)
         return sponet_fail(SPONET_ERR_UNSUPPORTED, "cntm_run: per-output divisors are not supported");
+    SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq),
+               "cntm_run: integer moment sums are not defined for Propensities");
+    A.ecv = cvd.ecv;
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
     A.cv_div = cvd.divisor;

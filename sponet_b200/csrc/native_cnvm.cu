@@ -44,6 +44,7 @@ struct NativeCnvmArgs {
     double cv_div;
     const double* cv_divs;  // per-output divisors (nullptr = cv_div)
     const int2* cw;         // per-agent (class, weight) of a grouped / weighted CV (nullptr = plain counts)
+    SpEdgeCv ecv;           // Interfaces / Propensities (kind != 0): replaces the table outputs
     int32_t cnt_stride;     // counters per chain: num_classes * M
     unsigned long long* counters;
     uint32_t* gstate;  // global chain states (fallback), [total_warps, words]
@@ -296,7 +297,27 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             extra_total += n_extra;
             my_acc = n_events = n_steps = n_extra = 0;
             const int64_t snap = cl * (int64_t)T + k;
-            if (A.out_cv || A.out_sum) {
+            if (BITS == 1 && A.ecv.kind != 0) {  // edge CV: scan the CV's graph against the on-chip state
+                if (A.out_cv || A.out_sum) {
+                    unsigned long long twice;
+                    double p0, p1;
+                    sp_edge_cv_scan<SMEM>(state, n, A.ecv, lane, &twice, &p0, &p1);
+                    if (lane == 0) {
+                        if (A.ecv.kind == SPONET_CV_INTERFACES) {
+                            const long long c = (long long)(twice >> 1);  // every edge was seen from both ends
+                            if (A.out_cv) A.out_cv[snap] = (A.cv_div == 1.0) ? (double)c : (double)c / A.cv_div;
+                            if (A.out_sum) {
+                                const int64_t o = j * (int64_t)T + k;
+                                atomicAdd(A.out_sum + o, (unsigned long long)c);
+                                atomicAdd(A.out_sumsq + o, (unsigned long long)(c * c));
+                            }
+                        } else if (A.out_cv) {
+                            A.out_cv[snap * 2 + 0] = (A.cv_div == 1.0) ? p0 : p0 / A.cv_div;
+                            A.out_cv[snap * 2 + 1] = (A.cv_div == 1.0) ? p1 : p1 / A.cv_div;
+                        }
+                    }
+                }
+            } else if (A.out_cv || A.out_sum) {
                 for (int d = lane; d < A.D; d += 32) {
                     const long long c = cnt_mem[A.cv_idx[d]];
                     if (A.out_cv) {
@@ -766,7 +787,35 @@ int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, 
     out->d_divisors = nullptr;
     out->num_classes = 1;
     out->d_cw = nullptr;
+    out->ecv = SpEdgeCv{0, nullptr, nullptr, nullptr, 0.0, 0.0, 0.0, 0.0};
     if (!cv) return SPONET_OK;
+    if (cv->kind != SPONET_CV_SHARES) {  // Interfaces / Propensities: scanned from the on-chip state per output time
+        SP_REQUIRE(cv->kind == SPONET_CV_INTERFACES || cv->kind == SPONET_CV_PROPENSITIES, "cv: unknown kind %d", cv->kind);
+        if (n <= 0)
+            return sponet_fail(SPONET_ERR_UNSUPPORTED, "cv: edge collective variables need the agent states (not the count-only kernel)");
+        SP_REQUIRE(M == 2, "cv: Interfaces / Propensities are defined for 2 opinions (model has %d)", M);
+        SP_REQUIRE(cv->graph && cv->graph->n == n, "cv: edge collective variable needs a graph over the model's %lld agents", (long long)n);
+        SP_REQUIRE(cv->dimension == (cv->kind == SPONET_CV_INTERFACES ? 1 : 2), "cv: dimension %d does not match the kind", cv->dimension);
+        SP_REQUIRE(cv->divisor != 0.0, "cv: divisor must be non-zero");
+        out->ecv.kind = cv->kind;
+        out->ecv.row = cv->graph->d_row;
+        out->ecv.col = cv->graph->d_col;
+        if (cv->kind == SPONET_CV_PROPENSITIES) {
+            SP_REQUIRE(cv->degree_alpha, "cv: Propensities need degree_alpha");
+            double* d_da;
+            SP_CUDA(sc.alloc((void**)&d_da, (size_t)n * sizeof(double)));
+            SP_CUDA(cudaMemcpyAsync(d_da, cv->degree_alpha, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
+            SP_CUDA(cudaStreamSynchronize(sc.stream));
+            out->ecv.da = d_da;
+            out->ecv.r01 = cv->rates[0];
+            out->ecv.r10 = cv->rates[1];
+            out->ecv.rt01 = cv->rates[2];
+            out->ecv.rt10 = cv->rates[3];
+        }
+        out->D = cv->dimension;
+        out->divisor = cv->divisor;
+        return SPONET_OK;
+    }
     SP_REQUIRE(cv->dimension >= 1 && cv->idx, "cv: dimension/idx invalid");
     SP_REQUIRE(cv->divisors || cv->divisor != 0.0, "cv: divisor must be non-zero");
     const int C = cv->num_classes > 1 ? cv->num_classes : 1;
@@ -941,6 +990,9 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     A.cv_div = cvd.divisor;
     A.cv_divs = cvd.d_divisors;
     A.cw = cvd.d_cw;
+    A.ecv = cvd.ecv;
+    SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq),
+               "cnvm_run: integer moment sums are not defined for Propensities");
     A.cnt_stride = cvd.num_classes * M;
     A.S = S;
     A.nrun = nrun;

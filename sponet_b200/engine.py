@@ -129,27 +129,48 @@ def cnvm_event_rates(params, degree_alpha, complete: bool) -> tuple[float, float
 
 
 class KernelCV:
-    """What the simulation kernels need to evaluate a CV of the OpinionShares family on the fly
-    (sponet_shares_cv): out[d] = count[idx[d]] / divisor(s), count = integer table [class * M + opinion]."""
+    """What the simulation kernels need to evaluate a collective variable on the fly (sponet_shares_cv).
 
-    def __init__(self, idx, divisor=1.0, divisors=None, num_classes=1, agent_class=None, agent_weight=None):
+    kind 0 (OpinionShares family): out[d] = count[idx[d]] / divisor(s), count = integer table
+    [class * M + opinion] kept up to date on every accepted event.
+    kind 1 / 2 (Interfaces / Propensities, two opinions): a scan of ``graph`` against the on-chip chain
+    state at every output time; ``divisor`` is the normalisation."""
+
+    SHARES, INTERFACES, PROPENSITIES = 0, 1, 2
+
+    def __init__(self, idx, divisor=1.0, divisors=None, num_classes=1, agent_class=None, agent_weight=None,
+                 kind=0, graph=None, degree_alpha=None, rates=None):
         self.idx = np.ascontiguousarray(idx, dtype=np.int32)
         self.divisor = float(divisor)
         self.divisors = None if divisors is None else np.ascontiguousarray(divisors, dtype=np.float64)
         self.num_classes = int(num_classes)
         self.agent_class = None if agent_class is None else np.ascontiguousarray(agent_class, dtype=np.int32)
         self.agent_weight = None if agent_weight is None else np.ascontiguousarray(agent_weight, dtype=np.int32)
+        self.kind = int(kind)
+        self.graph = graph  # GraphHandle of the CV's own network (kinds 1, 2)
+        self.degree_alpha = None if degree_alpha is None else np.ascontiguousarray(degree_alpha, dtype=np.float64)
+        self.rates = (0.0, 0.0, 0.0, 0.0) if rates is None else tuple(float(v) for v in rates)
 
     @property
     def grouped(self) -> bool:
         return self.agent_class is not None or self.agent_weight is not None
 
     @property
+    def edge(self) -> bool:
+        """Interfaces / Propensities: needs the agent states (never the count-only kernel)."""
+        return self.kind != 0
+
+    @property
+    def integer_valued(self) -> bool:
+        """Whether the kernels can accumulate exact integer moment sums of this CV."""
+        return self.kind != self.PROPENSITIES
+
+    @property
     def dimension(self) -> int:
-        return int(self.idx.size)
+        return {0: int(self.idx.size), 1: 1, 2: 2}[self.kind]
 
     def divisor_vector(self) -> np.ndarray:
-        return self.divisors if self.divisors is not None else np.full(self.idx.size, self.divisor)
+        return self.divisors if self.divisors is not None else np.full(self.dimension, self.divisor)
 
 
 def as_kernel_cv(spec) -> "KernelCV | None":
@@ -165,7 +186,9 @@ def cv_struct(spec):
         return None, None
     s = _lib.sponet_shares_cv(
         spec.dimension, _lib.ptr(spec.idx), spec.divisor, spec.num_classes, _lib.ptr(spec.agent_class),
-        _lib.ptr(spec.agent_weight), _lib.ptr(spec.divisors),
+        _lib.ptr(spec.agent_weight), _lib.ptr(spec.divisors), spec.kind,
+        None if spec.graph is None else spec.graph.handle, _lib.ptr(spec.degree_alpha),
+        (_lib.C.c_double * 4)(*spec.rates),
     )
     return s, spec
 

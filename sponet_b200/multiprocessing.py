@@ -176,8 +176,10 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
     spec = _kernel_cv_spec(cv, N)
     if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
         spec = None  # grouped / weighted tables are kept by the CNVM agent-level kernel only
+    if spec is not None and spec.edge and p.num_opinions != 2:
+        raise ValueError("Interfaces / Propensities can only be used for 2 opinions.")
     if spec is not None:
-        if use_count_only(model, kind, spec, S * num_runs):
+        if not spec.edge and use_count_only(model, kind, spec, S * num_runs):
             counts0 = np.stack([np.bincount(s, minlength=p.num_opinions) for s in states]).astype(np.int64)
             struct, keep = model._struct()
             _, local = engine.run_native("cnvm_counts", None, N, struct, None, t_out, seed, num_runs, rb, re,

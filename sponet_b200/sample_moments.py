@@ -50,6 +50,8 @@ def batch_moment_sums(model, kind, state, t_grid, batch_size, cv, rng) -> tuple[
     spec = _kernel_cv_spec(cv, N) if p.num_opinions <= 256 else None
     if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
         spec = None
+    if spec is not None and (not spec.integer_valued or (spec.edge and p.num_opinions != 2)):
+        spec = None  # Propensities are float sums: moments from the returned CV values instead
     if spec is not None and engine.resolve_mode(None) == "native":
         from .multiprocessing import _broadcast_seed
 
@@ -64,7 +66,7 @@ def batch_moment_sums(model, kind, state, t_grid, batch_size, cv, rng) -> tuple[
         x0 = np.ascontiguousarray(np.asarray(state, dtype=np.uint8)[None, :])
         if kind == "cnvm":
             struct, keep = model._struct()
-            if plain and use_count_only(model, kind, spec, batch_size):
+            if plain and not spec.edge and use_count_only(model, kind, spec, batch_size):
                 c0 = np.bincount(x0[0], minlength=p.num_opinions).astype(np.int64)[None, :]
                 engine.run_native("cnvm_counts", None, N, struct, None, t_grid, seed, batch_size, rb, re,
                                   cv_spec=spec, sums=sums, counts_init=c0)

@@ -379,3 +379,86 @@ def test_neighbor_table_construction_and_uniformity(oracle):
         assert np.allclose(list(prob.values()), 1.0 / len(nl[a]), atol=2.0**-22)
     star = calculate_neighbor_list(nx.star_graph(80))  # hub of degree 80
     assert library_neighbor_table(engine.GraphHandle(star))[0] is None
+
+
+@pytest.mark.parametrize("force_global,wpc", [(False, 0), (True, 0), (False, 2)])
+def test_edge_cvs_in_kernel_match_oracle_on_the_returned_states(oracle, force_global, wpc):
+    """Interfaces / Propensities evaluated by the simulation kernels at every output time
+    (a scan of the CV's CSR against the on-chip state) == the reference formulas applied to the states the same
+    chains return.  Interface counts and their integer moment sums are exact; the propensity sums are f64 in a
+    fixed tree order against the reference's sequential order (rtol 1e-12)."""
+    from sponet_b200 import CNVM, CNVMParameters, engine
+    from sponet_b200.engine import GraphCache, KernelCV
+
+    n, S, R, T = 1500, 2, 6, 5
+    net = _net("er", n, 5)
+    r, rt = np.array([[0, 1.3], [0.7, 0]]), np.array([[0, 0.03], [0.05, 0]])
+    params = CNVMParameters(num_opinions=2, network=net, r=r, r_tilde=rt, alpha=0.5)
+    model = CNVM(params)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    # the CV's own network need not be the model's: Interfaces over a different graph on the same agents
+    other = _net("ba", n, 9)
+    from sponet_b200.utils import calculate_neighbor_list
+
+    orp, ocol = oracle.neighbor_list_to_csr(calculate_neighbor_list(other))
+    cache = GraphCache()
+    states = np.random.default_rng(1).integers(0, 2, (S, n)).astype(np.uint8)
+    t_eval = np.linspace(0, 3.0, T)
+    struct, keep = model._struct()
+    kw = dict(force_global_state=force_global, warps_per_chain=wpc)
+    xs, _ = engine.run_native("cnvm", model._graph(), n, struct, states, t_eval, 77, R, 0, R, want_x=True, **kw)
+    flat = xs.reshape(-1, n)
+
+    spec = KernelCV([], 1.0, kind=KernelCV.INTERFACES, graph=cache.get(calculate_neighbor_list(other)))
+    sums = (np.zeros((S, T, 1), dtype=np.int64), np.zeros((S, T, 1), dtype=np.int64))
+    _, cv = engine.run_native("cnvm", model._graph(), n, struct, states, t_eval, 77, R, 0, R, cv_spec=spec, want_cv=True,
+                              sums=sums, **kw)
+    exp = oracle.interfaces(flat, orp, ocol).reshape(S, R, T, 1)
+    np.testing.assert_array_equal(cv, exp)
+    np.testing.assert_array_equal(sums[0], exp.sum(axis=1).astype(np.int64))
+    np.testing.assert_array_equal(sums[1], (exp * exp).sum(axis=1).astype(np.int64))
+    spec = KernelCV([], float(other.number_of_edges()), kind=KernelCV.INTERFACES, graph=cache.get(calculate_neighbor_list(other)))
+    _, cvn = engine.run_native("cnvm", model._graph(), n, struct, states, t_eval, 77, R, 0, R, cv_spec=spec, want_cv=True, **kw)
+    np.testing.assert_array_equal(cvn, exp / other.number_of_edges())
+
+    das = np.diff(rp).astype(float) ** 0.5
+    spec = KernelCV([], 1.0, kind=KernelCV.PROPENSITIES, graph=model._graph(), degree_alpha=das,
+                    rates=(r[0, 1], r[1, 0], rt[0, 1], rt[1, 0]))
+    _, pv = engine.run_native("cnvm", model._graph(), n, struct, states, t_eval, 77, R, 0, R, cv_spec=spec, want_cv=True, **kw)
+    np.testing.assert_allclose(pv, oracle.propensities(flat, rp, col, das, r, rt).reshape(S, R, T, 2), rtol=1e-12)
+    with pytest.raises(Exception, match="Propensities"):
+        engine.run_native("cnvm", model._graph(), n, struct, states, t_eval, 77, R, 0, R, cv_spec=spec,
+                          sums=(np.zeros((S, T, 2), dtype=np.int64), np.zeros((S, T, 2), dtype=np.int64)), **kw)
+    del keep
+
+
+def test_edge_cvs_cntm_and_public_api(oracle):
+    """Interfaces through the CNTM kernel and through sample_many_runs / sample_moments (host API)."""
+    from sponet_b200 import CNTMParameters, CNVMParameters, Interfaces, sample_many_runs, sample_moments
+    from sponet_b200.collective_variables import Propensities
+
+    n = 900
+    net = _net("ba", n, 4)
+    rp, col = oracle.neighbor_list_to_csr([sorted(net.neighbors(i)) for i in range(n)])
+    x0 = np.random.default_rng(2).integers(0, 2, n).astype(np.uint8)
+    p = CNTMParameters(network=net, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5)
+    for normalize in (False, True):
+        cvi = Interfaces(net, normalize=normalize)
+        _, c = sample_many_runs(p, x0, 2.0, 4, 5, collective_variable=cvi, rng=np.random.default_rng(5))
+        _, xs = sample_many_runs(p, x0, 2.0, 4, 5, rng=np.random.default_rng(5))
+        exp = oracle.interfaces(xs.reshape(-1, n), rp, col).reshape(5, 4, 1)
+        np.testing.assert_array_equal(c, exp / net.number_of_edges() if normalize else exp)
+    # CNVM: Propensities(params) in-kernel through the public API, and moments of Interfaces from integer sums
+    pv = CNVMParameters(num_opinions=2, network=net, r=1.0, r_tilde=0.05, alpha=1.0)
+    cvp = Propensities(pv, normalize=True)
+    _, c = sample_many_runs(pv, x0, 1.0, 3, 4, collective_variable=cvp, rng=np.random.default_rng(6))
+    _, xs = sample_many_runs(pv, x0, 1.0, 3, 4, rng=np.random.default_rng(6))
+    exp = oracle.propensities(xs.reshape(-1, n), rp, col, np.diff(rp).astype(float), pv.r, pv.r_tilde).reshape(4, 3, 2) / n
+    np.testing.assert_allclose(c, exp, rtol=1e-12)
+    t, mean, var, num = sample_moments(pv, x0, 1.0, 3, 64, rel_tol=1e9, collective_variable=Interfaces(net),
+                                       rng=np.random.default_rng(7))
+    assert mean.shape == (3, 1) and mean[0, 0] == oracle.interfaces(x0, rp, col)[0, 0] and var[0, 0] == 0.0
+    with pytest.raises(ValueError, match="2 opinions"):
+        p3 = CNVMParameters(num_opinions=3, network=net, r=R3, r_tilde=RT3)
+        sample_many_runs(p3, np.zeros(n, dtype=np.uint8), 1.0, 3, 2, collective_variable=Interfaces(net),
+                         rng=np.random.default_rng(0))

@@ -107,6 +107,20 @@ def test_cv_known_answers(oracle):
     np.testing.assert_array_equal(oracle.opinion_shares(x, 3, deg), g["shares_deg"])
 
 
+def test_edge_cv_known_answers(oracle):
+    """Interfaces / Propensities restatements against values computed by the reference's own classes
+    (tests/golden/make_cv2_golden.py); the GPU tests use them to check the in-kernel evaluation."""
+    g = load_golden("cv2_known_answers")
+    rp, col, x = g["row_ptr"], g["col"], g["x"]
+    np.testing.assert_array_equal(oracle.interfaces(x, rp, col), g["interfaces"])
+    np.testing.assert_array_equal(oracle.interfaces(x, rp, col) / int(g["num_edges"]), g["interfaces_norm"])
+    deg = np.diff(rp)
+    for alpha in (1.0, 0.5, 0.0):
+        out = oracle.propensities(x, rp, col, deg ** alpha, g["r"], g["r_tilde"])
+        np.testing.assert_array_equal(out, g[f"prop_net_a{alpha}"])  # same sequential f64 sum: bit-exact
+        np.testing.assert_array_equal(out / x.shape[1], g[f"prop_net_norm_a{alpha}"])
+
+
 def test_pcg64_stream_matches_numpy(oracle):
     bg = PCG64(11)
     s = oracle.Stream(pcg64_state=bg.state)
