@@ -337,6 +337,12 @@ def _gpu_rate(kind, model, struct, graph, n, x0, t_eval, runs, spec, counts_init
     d_x0 = None if x0 is None else torch.as_tensor(x0[None, :], device="cuda")
     d_c0 = None if counts_init is None else torch.as_tensor(counts_init, device="cuda")
     best = 0.0
+    # warm-up: an idle B200 drops its clocks (the CPU legs run in between); keep the GPU busy for ~0.7 s first
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.7:
+        engine.run_native(kind, graph, n, struct, d_x0, t_eval, 50, runs, 0, runs, cv_spec=spec, want_cv=True,
+                          counts_init=d_c0)
+        torch.cuda.synchronize()
     for rep in range(reps):
         counters = torch.zeros(4, dtype=torch.int64, device="cuda")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
