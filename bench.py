@@ -287,6 +287,7 @@ def run_gpu_arm(args) -> None:
         p_acc = accepted / max(events, 1.0)
         p_noise = params.r_noise * N_AGENTS / rate
         bytes_per_event = (1.0 - p_noise) * 14.0 + p_noise * 1.0 + p_acc * 1.0
+        sector_bytes = (1.0 - p_noise) * 4 * 32.0 + p_noise * 32.0
         peak, peak_src = measured_peaks()
         per_gpu_events_per_s = value / world
         achieved = per_gpu_events_per_s * bytes_per_event / 1e9
@@ -306,6 +307,10 @@ def run_gpu_arm(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bytes_per_event,
+                         # SURVEY.md 8(d) context figure: what an HBM-resident design would move, one 32 B sector per
+                         # independent random access (4 per imitation event, 1 per noise event)
+                         "sector_granular": {"bytes_per_event": sector_bytes, "achieved": per_gpu_events_per_s * sector_bytes / 1e9,
+                                             "frac": per_gpu_events_per_s * sector_bytes / 1e9 / peak},
                          "kernel": "cnvm_native_kernel<2,smem,nbtab,noalias,ring>",
                          "ncu": {k: v for k, v in ncu_capture().items() if k.endswith("_pct") or k.startswith("warp_")},
                          "note": "chain states live in shared memory and the CSR in L2, so DRAM traffic is far below the algorithmic bytes by design; the kernel is issue/latency bound (DESIGN.md section 5)"},
