@@ -462,3 +462,57 @@ def test_edge_cvs_cntm_and_public_api(oracle):
         p3 = CNVMParameters(num_opinions=3, network=net, r=R3, r_tilde=RT3)
         sample_many_runs(p3, np.zeros(n, dtype=np.uint8), 1.0, 3, 2, collective_variable=Interfaces(net),
                          rng=np.random.default_rng(0))
+
+
+def test_crafted_interval_counts_all_schedules(oracle):
+    """Interval bookkeeping of the kernels' per-interval loops: injected event counts with empty intervals (leading,
+    consecutive, trailing), single events, exactly one / two full steps, one event more or less than a step multiple.
+    Every warp schedule (1, 2, 3, 8 warps per chain) and the CNTM kernel against the sequential oracle."""
+    from sponet_b200 import CNTM, CNTMParameters, CNVM, CNVMParameters, engine
+
+    n, M, R = 3000, 3, 4
+    net = _net("er", n, 11)
+    params = CNVMParameters(num_opinions=M, network=net, r=R3, r_tilde=RT3)
+    model = CNVM(params)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    base = np.array([0, 0, 1, 31, 32, 33, 0, 0, 64, 63, 65, 1, 0, 97, 128, 5000, 0, 2, 0, 0], dtype=np.int64)
+    T = base.size + 1
+    counts = np.stack([np.roll(base, 3 * i) for i in range(R)])  # chain i sees the pattern shifted
+    counts[1, :] = 0  # a chain without any event
+    t_eval = np.linspace(0.0, 1.0, T)
+    x0 = np.random.default_rng(8).integers(0, M, (1, n)).astype(np.uint8)
+    struct, keep = model._struct()
+    spec = (np.arange(M, dtype=np.int32), 1.0)
+    rate, noise_p = model.event_rates()
+    nbtab, nblg = _nbtab(oracle, model, rp, col)
+    exp = [oracle.cnvm_native(x0[0], M, rp, col, int(oracle.prob_to_thr(noise_p)), oracle.prob_to_thr(params.prob_imit),
+                              oracle.prob_to_thr(params.prob_noise), None, None, counts[i], 321, i, nbtab=nbtab,
+                              nbtab_log2=nblg) for i in range(R)]
+    for wpc in (1, 2, 3, 8):
+        counters = np.zeros(4, dtype=np.uint64)
+        xs, cv = engine.run_native("cnvm", model._graph(), n, struct, x0, t_eval, 321, R, 0, R, cv_spec=spec, want_x=True,
+                                   want_cv=True, counters=counters, event_counts=counts, warps_per_chain=wpc)
+        for i in range(R):
+            np.testing.assert_array_equal(xs[0, i], exp[i][0], err_msg=f"wpc={wpc} chain {i}")
+            np.testing.assert_array_equal(cv[0, i], exp[i][1].astype(float))
+        assert int(counters[0]) == int(counts.sum()) == sum(e[2] for e in exp)
+        assert int(counters[1]) == sum(e[3] for e in exp)
+    del keep
+
+    pt = CNTMParameters(network=_net("ba", n, 2), r=1.0, r_tilde=0.3, threshold_01=0.4, threshold_10=0.55)
+    mt = CNTM(pt)
+    rp, col = oracle.neighbor_list_to_csr(mt.neighbor_list)
+    x0 = np.random.default_rng(9).integers(0, 2, (1, n)).astype(np.uint8)
+    noise_thr = int(oracle.prob_to_thr(mt.noise_prob))
+    counters = np.zeros(4, dtype=np.uint64)
+    xs, cv = engine.run_native("cntm", mt._graph(), n, mt._struct(), x0, t_eval, 654, R, 0, R,
+                               cv_spec=(np.arange(2, dtype=np.int32), 1.0), want_x=True, want_cv=True, counters=counters,
+                               event_counts=counts)
+    tot_ev = tot_acc = 0
+    for i in range(R):
+        ox, oc, ev, acc = oracle.cntm_native(x0[0], rp, col, noise_thr, 0.4, 0.55, counts[i], 654, i)
+        np.testing.assert_array_equal(xs[0, i], ox)
+        np.testing.assert_array_equal(cv[0, i], oc.astype(float))
+        tot_ev += ev
+        tot_acc += acc
+    assert int(counters[0]) == tot_ev == int(counts.sum()) and int(counters[1]) == tot_acc
