@@ -209,9 +209,11 @@ struct SpEdgeCv {
 
 // iface = number of ordered pairs (j, v in N(j)) with x[j] != x[v] (twice the interface count);
 // p0 / p1 = the two propensity sums.  Every lane returns the warp totals (fixed reduction tree).
+// (Inlined, arguments by value: a call taking the address of a kernel-parameter member makes the compiler
+// copy the whole parameter struct to local memory, which slowed the 1-bit CNVM kernels down 3x.)
 template <bool SMEM>
-__device__ __noinline__ void sp_edge_cv_scan(const uint32_t* state, uint32_t n, const SpEdgeCv& E, int lane,
-                                             unsigned long long* iface, double* p0, double* p1) {
+__device__ __forceinline__ void sp_edge_cv_scan(const uint32_t* state, uint32_t n, const SpEdgeCv E, int lane,
+                                                unsigned long long& iface, double& p0, double& p1) {
     auto bit = [&](uint32_t a) {
         const uint32_t w = SMEM ? state[a >> 5] : __ldcg(state + (a >> 5));
         return (w >> (a & 31)) & 1u;
@@ -237,9 +239,9 @@ __device__ __noinline__ void sp_edge_cv_scan(const uint32_t* state, uint32_t n, 
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
     }
-    *iface = t;
-    *p0 = a0;
-    *p1 = a1;
+    iface = t;
+    p0 = a0;
+    p1 = a1;
 }
 
 struct SpCvDev {

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 if (A.out_cv || A.out_sum) {
                     unsigned long long twice;
                     double p0, p1;
-                    sp_edge_cv_scan<SMEM>(state, n, A.ecv, lane, &twice, &p0, &p1);
+                    sp_edge_cv_scan<SMEM>(state, n, A.ecv, lane, twice, p0, p1);
                     if (lane == 0) {
                         if (A.ecv.kind == SPONET_CV_INTERFACES) {
                             const long long c = (long long)(twice >> 1);  // every edge was seen from both ends

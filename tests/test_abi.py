@@ -48,3 +48,23 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "libsponet_oracle" not in text and "sponet_oracle.c" not in text, f
+
+
+def test_native_kernels_keep_their_state_in_registers():
+    """Build sanity: none of the simulation kernels may use local memory (STACK:0).  A spill or an addressable
+    copy of the kernel parameters in a hot loop costs a multiple (an out-of-line helper that took the address
+    of a parameter member once made the 1-bit CNVM kernels 3x slower without failing any parity test)."""
+    import re
+    import shutil
+    import subprocess
+
+    from sponet_b200 import _lib
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = re.findall(r"Function (\S*(?:cnvm_native_kernel|cntm_native_kernel|cnvm_counts_kernel)\S*):\s*\n\s*(.*)", out)
+    assert len(kernels) >= 70
+    bad = [(name, usage) for name, usage in kernels if "STACK:0 " not in usage + " "]
+    assert not bad, bad[:3]
