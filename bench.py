@@ -427,18 +427,18 @@ def run_all_configs():
     out.append(dict(config="3: CNTM BA N=1e5 m=5, r=1 r~=0.2 thr 0.5/0.5, 1e4 realizations (t_max=2 sample)",
                     gpu_events_per_s=g, cpu_events_per_s=c, cpu_threads=threads, cpu_sample=f"{runs} runs, {sec:.1f} s"))
 
-    # config 4: SIS-as-CNVM WS N=1e6 (per-GPU share of 1e5 realizations: timed on 600)
+    # config 4: SIS-as-CNVM WS N=1e6 (per-GPU share of 1e5 realizations: timed on 2368 = 16 per SM)
     params, x0, rate = workloads.sis_ws(1_000_000)
     model = CNVM(params)
     struct, keep = model._struct()
     t_eval = np.linspace(0, 1.0, 11)
     spec = (np.array([1], dtype=np.int32), 1e6)
-    g, _ = _gpu_rate("cnvm", model, struct, model._graph(), 1_000_000, x0, t_eval, 592, spec)
+    g, _ = _gpu_rate("cnvm", model, struct, model._graph(), 1_000_000, x0, t_eval, 2368, spec)
     rp, col = oracle.neighbor_list_to_csr(params.network)
     c, runs, sec = _cpu_rate("cnvm", x0, t_eval, 2, threads, target_s=6.0, row_ptr=rp, col=col, r_imit=params.r_imit,
                             r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise,
                             degree_alpha=np.ones(1_000_000))
-    out.append(dict(config="4: SIS-as-CNVM WS N=1e6 k=10 p=0.1, lambda=1 (592 realizations, t_max=1 sample)",
+    out.append(dict(config="4: SIS-as-CNVM WS N=1e6 k=10 p=0.1, lambda=1 (2368 realizations, t_max=1 sample)",
                     gpu_events_per_s=g, cpu_events_per_s=c, cpu_threads=threads, cpu_sample=f"{runs} runs, {sec:.1f} s"))
 
     # config 5: one (r, r~) point of the sample_moments sweep on the H graph, fused integer moments (wall clock, host API)
