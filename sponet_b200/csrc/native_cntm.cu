@@ -353,14 +353,17 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
             gather(row0, c00, c01);
             draw(e_pre, a1, meta1, row1);
             e_pre += 32;
+            draw(e_pre, a2, meta2, row2);
+            e_pre += 32;
 #pragma unroll 1
             for (int rem = nsteps; rem > 0; --rem) {
                 gather(row1, c10, c11);
-                draw(e_pre, a2, meta2, row2);
-                e_pre += 32;
                 process(rem == 1 ? tail : 32);
+                // rotate, then draw: every register that moves was loaded at least a full step ago
                 a0 = a1, meta0 = meta1, row0 = row1, c00 = c10, c01 = c11;
                 a1 = a2, meta1 = meta2, row1 = row2;
+                draw(e_pre, a2, meta2, row2);
+                e_pre += 32;
             }
             E += (uint64_t)Kc;
             if (ends) {
