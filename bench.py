@@ -266,7 +266,7 @@ def run_gpu_arm(args) -> None:
         # each rank drives its own 1e4 runs through the public API (no gather: weak scaling)
         smp_dist = smp._dist
         smp._dist = lambda: (0, 1)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     sample_many_runs(params, x0, T_MAX, NUM_T, R, collective_variable=cv, rng=rng)  # warm (graph upload, caches)
     barrier()
     t0 = time.perf_counter()

@@ -83,7 +83,21 @@ struct SpScratch {
         size_t bytes;
     };
     std::vector<Copyback> copybacks;
-    explicit SpScratch(cudaStream_t s) : stream(s) {}
+    explicit SpScratch(cudaStream_t s) : stream(s) {
+        // Keep up to 1 GiB of freed scratch in the device's stream-ordered pool.  With the default release
+        // threshold (0) every synchronising call hands the memory back to the OS and the next call maps
+        // it again, which showed up as 10-100 ms of host time per ensemble call.
+        static bool tuned[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !tuned[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = 1ull << 30;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            tuned[dev] = true;
+        }
+    }
     ~SpScratch() {
         for (void* p : ptrs) cudaFreeAsync(p, stream);
     }
