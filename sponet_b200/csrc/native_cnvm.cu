@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 
         // Per-lane packed deltas of the opinion counts (4 signed 8-bit fields, M <= 4), folded into the
         // shared counters before any field can leave [-127, 127]; 32-bit per-lane statistics with them.
-        uint32_t dpack = 0, my_acc = 0, n_steps = 0, n_events = 0, n_extra = 0;
+        uint32_t dpack = 0, my_acc = 0, n_extra = 0;
+        unsigned long long n_steps = 0, n_events = 0;  // (a chunk has up to 2^30 steps)
         auto fold_counts = [&]() {
             if (PACKCNT) {
                 uint32_t t = dpack;
@@ -488,8 +489,6 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                     hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
                 }
             }
-            ++n_steps;
-            n_events += (uint32_t)nb;
         };
 
         // ---- the chain: output interval by output interval ----
@@ -521,6 +520,9 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             const int first = (int)((uint32_t)(role + W) - s_mod) % W;        // first own step of this chunk
             const int n_own = nsteps > first ? (nsteps - first + W - 1) / W : 0;
             const bool own_last = (int)((s_mod + (uint32_t)(nsteps - 1)) % (uint32_t)W) == role;
+            // statistics per chunk, not per step: own steps are full except the chunk's last one
+            n_steps += (unsigned long long)n_own;
+            n_events += 32ull * (unsigned long long)n_own - ((own_last && n_own > 0) ? (unsigned long long)(32 - tail) : 0ull);
             if (n_own > 0) {
                 // The pipeline always runs two own steps ahead, also past the end of the chunk: the draws of a
                 // step that does not exist are valid gathers that nobody consumes (two per chunk and warp),
