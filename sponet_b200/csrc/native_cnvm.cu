@@ -343,27 +343,49 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3];
         int2 q_row[3];
 
-        auto issue1 = [&](int s, uint64_t e0) {
-            const uint64_t e = e0 + (uint64_t)lane;
-            const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
-            const bool noise = r.x < noise_thr;
-            const uint32_t idx = __umulhi(r.y, n);
-            uint32_t a = idx;
-            if (ALIAS) {  // sampling.py:117-122 with integer thresholds; noise events pick uniformly
-                const uint2 at = __ldg(A.alias_tab + idx);
-                a = (noise | sp_thr_accept(r.y * n, at.x)) ? idx : at.y;
-            }
-            q_a[s] = a;
-            q_r2[s] = r.z;
-            q_r3[s] = r.w;
-            q_meta[s] = (uint32_t)noise | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
+        // Stage 1 of an own step: Philox, agent, gather of the agent's table entry (or CSR row).  With alias
+        // tables (degree-weighted agent selection) the agent itself comes out of a gather, so the stage is
+        // split: draw() runs three own steps ahead into one staging set (z_*) and gathers the alias entry,
+        // resolve() one step later picks the agent and issues the entry gather -- each gather has a full
+        // step to return instead of stalling the warp twice per step.
+        uint32_t z_idx = 0, z_frac = 0, z_r2 = 0, z_r3 = 0, z_meta = 0;
+        uint2 z_at = make_uint2(0u, 0u);
+        auto gather_entry = [&](int s, uint32_t a, uint32_t r2) {
             // every lane gathers (no divergence); noise lanes ignore the result
             if (GRAPH == 1) q_row[s] = __ldg(A.row + a);
             if (GRAPH == 2) {
                 // slot index (a << lg) | (top lg bits of r2) in one funnel shift; the table has < 2^26 entries
-                const uint2 t = __ldg(A.nbtab + __funnelshift_l(r.z, a, (uint32_t)A.nbtab_log2));
+                const uint2 t = __ldg(A.nbtab + __funnelshift_l(r2, a, (uint32_t)A.nbtab_log2));
                 q_row[s] = make_int2((int)t.x, (int)t.y);
             }
+        };
+        auto draw = [&](uint64_t e0) {  // ALIAS only
+            const uint64_t e = e0 + (uint64_t)lane;
+            const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
+            z_idx = __umulhi(r.y, n);
+            z_frac = r.y * n;
+            z_r2 = r.z;
+            z_r3 = r.w;
+            z_meta = (uint32_t)(r.x < noise_thr) | (__umulhi(r.z, (uint32_t)M) << 8);
+            z_at = __ldg(A.alias_tab + z_idx);
+        };
+        auto resolve = [&](int s) {  // ALIAS only: sampling.py:117-122 with integer thresholds; noise events pick uniformly
+            const uint32_t a = ((z_meta & 1u) | (uint32_t)sp_thr_accept(z_frac, z_at.x)) ? z_idx : z_at.y;
+            q_a[s] = a;
+            q_r2[s] = z_r2;
+            q_r3[s] = z_r3;
+            q_meta[s] = z_meta;
+            gather_entry(s, a, z_r2);
+        };
+        auto issue1 = [&](int s, uint64_t e0) {  // uniform agent weights: one stage
+            const uint64_t e = e0 + (uint64_t)lane;
+            const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
+            const uint32_t a = __umulhi(r.y, n);
+            q_a[s] = a;
+            q_r2[s] = r.z;
+            q_r3[s] = r.w;
+            q_meta[s] = (uint32_t)(r.x < noise_thr) | (__umulhi(r.z, (uint32_t)M) << 8);  // bit 0 noise, bits 8.. noise opinion
+            gather_entry(s, a, r.z);
         };
         auto issue2 = [&](int s) {
             uint32_t nbr;
@@ -529,11 +551,23 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 // which keeps the loop body free of prefetch conditions.
                 const uint64_t e_stride = 32ull * (uint64_t)W;
                 uint64_t e_pre = E + 32ull * (uint64_t)first;  // first event of the next step to draw
-                issue1(0, e_pre);
-                e_pre += e_stride;
-                issue2(0);
-                issue1(1, e_pre);
-                e_pre += e_stride;
+                if (ALIAS) {
+                    draw(e_pre);
+                    e_pre += e_stride;
+                    resolve(0);
+                    draw(e_pre);
+                    e_pre += e_stride;
+                    resolve(1);
+                    issue2(0);
+                    draw(e_pre);  // staged for the third own step
+                    e_pre += e_stride;
+                } else {
+                    issue1(0, e_pre);
+                    e_pre += e_stride;
+                    issue2(0);
+                    issue1(1, e_pre);
+                    e_pre += e_stride;
+                }
                 int rem = n_own;  // own steps left in this chunk
                 while (rem > 0) {
                     // blocks of at most 120 own steps (a multiple of the 3 register sets): the packed count
@@ -543,7 +577,12 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
                             if (rem == stop) break;
-                            issue1((u + 2) % 3, e_pre);       // two own steps ahead: Philox + gather
+                            if (ALIAS) {
+                                resolve((u + 2) % 3);  // two own steps ahead: agent + entry gather
+                                draw(e_pre);           // three own steps ahead: Philox + alias gather
+                            } else {
+                                issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
+                            }
                             e_pre += e_stride;
                             const bool last_own = rem == 1;   // the chunk's last step, if ours, is our last one
                             process(u, (last_own && own_last) ? tail : 32);

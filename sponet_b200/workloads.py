@@ -24,18 +24,21 @@ def er_network(num_agents: int, mean_degree: float = 10.0, seed: int = 12345):
     return g
 
 
-def headline_cnvm(num_agents: int = 100_000, seed: int = 12345):
+def headline_cnvm(num_agents: int = 100_000, seed: int = 12345, alpha: float = 1.0):
     """H: CNVM, M = 3, ER <d> = 10, fixture rates (r_imit = 2, r_noise = 0.6), alpha = 1.
 
     Returns (params, x_init, events_per_unit_time).  At N = 1e5: nnz = 998 782, lambda = 2.6e5.
+    (alpha != 1 gives the degree-weighted agent selection: alias tables on the hot path.)
     """
     from .cnvm import CNVMParameters
     from .utils import calculate_neighbor_list
 
     g = er_network(num_agents, 10.0, seed)
-    params = CNVMParameters(num_opinions=3, network=calculate_neighbor_list(g), r=R3, r_tilde=RT3, alpha=1.0)
+    nl = calculate_neighbor_list(g)
+    params = CNVMParameters(num_opinions=3, network=nl, r=R3, r_tilde=RT3, alpha=alpha)
     x_init = np.random.default_rng(0).integers(0, 3, num_agents).astype(np.uint8)
-    rate = params.r_imit * num_agents + params.r_noise * num_agents  # alpha = 1: d^(1-alpha) = 1
+    # cnvm/model.py:257: r_imit * sum_i d_i^(1 - alpha) + r_noise * N
+    rate = params.r_imit * float(np.sum(np.array([len(nb) for nb in nl], dtype=float) ** (1.0 - alpha))) + params.r_noise * num_agents
     return params, x_init, rate
 
 

@@ -16,12 +16,13 @@ ap.add_argument("--t-max", type=float, default=1.0)
 ap.add_argument("--T", type=int, default=11)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--global-state", action="store_true")
+ap.add_argument("--alpha", type=float, default=1.0)
 a = ap.parse_args()
 
 torch.cuda.init()
 t0 = time.time()
 if a.model == "cnvm":
-    params, x0, rate = workloads.headline_cnvm(a.n)
+    params, x0, rate = workloads.headline_cnvm(a.n, alpha=a.alpha)
     model = CNVM(params); kind = "cnvm"; M = 3
     struct, keep = model._struct()
 elif a.model == "sis":
