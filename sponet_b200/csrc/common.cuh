@@ -74,6 +74,23 @@ inline bool sp_is_device_ptr(const void* p) {
 }
 
 // RAII pool of temporary device allocations tied to one call.
+// The two device limits the launch geometry needs (cudaGetDeviceProperties fills the whole struct and costs
+// about a millisecond per call; these attributes are cheap).
+struct SpDeviceLimits {
+    int multiProcessorCount;
+    size_t sharedMemPerBlockOptin;
+};
+inline cudaError_t sp_device_limits(int dev, SpDeviceLimits* out) {
+    int sms = 0, smem = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    out->multiProcessorCount = sms;
+    out->sharedMemPerBlockOptin = (size_t)smem;
+    return cudaSuccess;
+}
+
 struct SpScratch {
     cudaStream_t stream;
     std::vector<void*> ptrs;

@@ -493,8 +493,8 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     SP_CUDA(sc.out((unsigned long long*)counters, SPONET_NUM_COUNTERS, &A.counters, true));
 
     A.words = (int32_t)((n + 31) / 32);
-    cudaDeviceProp prop;
-    SP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    SpDeviceLimits prop;
+    SP_CUDA(sp_device_limits(dev, &prop));
     const size_t smem_max = prop.sharedMemPerBlockOptin - SP_CNTM_MAX_WARPS * 33 * 4;  // minus the static arrays
     const size_t chain_bytes = (size_t)A.words * 4;
     bool smem_state = !o->force_global_state;

@@ -1072,8 +1072,8 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     // thresholds + [mbarriers] + counters + Bloom filters + packed states.
     const int bits = M <= 2 ? 1 : M <= 4 ? 2 : M <= 16 ? 4 : 8;
     A.words = (int32_t)((n * bits + 31) / 32);
-    cudaDeviceProp prop;
-    SP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    SpDeviceLimits prop;
+    SP_CUDA(sp_device_limits(dev, &prop));
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
     const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
