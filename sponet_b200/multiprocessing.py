@@ -131,9 +131,13 @@ def sample_many_runs(
     dtype = np.min_scalar_type(params.num_opinions - 1)
 
     per_run_network = getattr(params, "network_generator", None) is not None
-    if mode == "replay" or params.num_opinions > 256 or per_run_network:
+    if mode == "replay" or params.num_opinions > 256:
         x_out = _sample_replay(model, kind, initial_states.astype(dtype), t_max, t_out, num_runs, n_jobs,
                                collective_variable, rng, progress_bar, per_run_network)
+    elif per_run_network:
+        x_out = _sample_native_per_run_network(model, kind, initial_states.astype(np.uint8), t_out, num_runs,
+                                               collective_variable, rng, progress_bar).astype(
+            dtype if collective_variable is None else np.float64, copy=False)
     else:
         x_out = _sample_native(model, kind, initial_states.astype(np.uint8), t_out, num_runs,
                                collective_variable, rng, progress_bar).astype(
@@ -201,6 +205,50 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
         local = _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, pbar)
     _close(pbar)
     return _gather_runs(local, bounds, world) if world > 1 else local
+
+
+def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
+    """A NetworkGenerator in the parameters: a new network for every (initial state, run) pair, sampled in the
+    reference's order (states outer, runs inner: multiprocessing.py:173-178 with cnvm/model.py:95-96).  Every
+    pair is one native chain on its own graph; chain id = j * num_runs + i keys its Philox stream, so the
+    result does not depend on how the pairs are spread over ranks.  Each rank draws the networks of all pairs
+    from its own copy of the generator (as every worker process of the reference does with its pickled copy)
+    and simulates its share."""
+    p = model.params
+    S, N, T = states.shape[0], p.num_agents, t_out.size
+    seed = engine.draw_seed(rng)
+    rank, world = _dist()
+    if world > 1:
+        seed = _broadcast_seed(seed)
+    pairs = S * num_runs
+    bounds = np.concatenate(([0], np.cumsum(_split_runs(pairs, world))))
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    D = N if cv is None else cv.dimension
+    flat = np.zeros((pairs, T, D), dtype=np.uint8 if cv is None else np.float64)
+    pbar = _progress(progress_bar, hi - lo)
+    for c in range(pairs):
+        model.update_network()  # every rank walks the same generator sequence
+        if not (lo <= c < hi):
+            continue
+        j = c // num_runs
+        x0 = np.ascontiguousarray(states[j : j + 1])
+        spec = _kernel_cv_spec(cv, N) if cv is not None else None
+        if spec is not None and (spec.edge and p.num_opinions != 2):
+            raise ValueError("Interfaces / Propensities can only be used for 2 opinions.")
+        if cv is None:
+            out, _ = _native_call(model, kind, x0, t_out, seed, pairs, c, c + 1, want_x=True)
+            flat[c] = out[0, 0]
+        elif spec is not None:
+            _, out = _native_call(model, kind, x0, t_out, seed, pairs, c, c + 1, cv_spec=spec, want_cv=True)
+            flat[c] = out[0, 0]
+        else:
+            out, _ = _native_call(model, kind, x0, t_out, seed, pairs, c, c + 1, want_x=True)
+            flat[c] = np.asarray(cv(out[0, 0]))
+        _tick(pbar, 1)
+    _close(pbar)
+    if world > 1:
+        flat = _gather_runs(flat[None, lo:hi], bounds, world)[0]
+    return flat.reshape(S, num_runs, T, D)
 
 
 def _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, pbar):

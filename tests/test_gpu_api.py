@@ -318,6 +318,38 @@ def test_network_generator_resamples_per_run():
     assert c.shape == (4, 3, 2) and gen.calls == 6 and (c.sum(-1) == 60).all()
 
 
+def test_network_generator_native_chains_match_oracle(oracle):
+    """Native mode with a NetworkGenerator: pair c = (state j, run i) is one chain on the c-th network of the
+    generator, keyed by chain id c -- checked against the sequential oracle on the same networks."""
+    from sponet_b200 import CNVM, CNVMParameters, OpinionShares, engine, sample_many_runs
+    from sponet_b200.utils import calculate_neighbor_list
+
+    n, S, R, T = 200, 2, 3, 4
+    params = CNVMParameters(num_opinions=2, network_generator=_RingGenerator(n, seed=5), r=1.0, r_tilde=0.05)
+    states = np.random.default_rng(0).integers(0, 2, (S, n)).astype(np.uint8)
+    _, c = sample_many_runs(params, states, 3.0, T, R, collective_variable=OpinionShares(2), rng=np.random.default_rng(9))
+    _, x = sample_many_runs(CNVMParameters(num_opinions=2, network_generator=_RingGenerator(n, seed=5), r=1.0, r_tilde=0.05),
+                            states, 3.0, T, R, rng=np.random.default_rng(9))
+    assert c.shape == (S, R, T, 2) and x.shape == (S, R, T, n)
+    seed = engine.draw_seed(np.random.default_rng(9))
+    gen = _RingGenerator(n, seed=5)
+    t_eval = np.linspace(0, 3.0, T)
+    for pair in range(S * R):
+        j, i = divmod(pair, R)
+        nl = calculate_neighbor_list(gen())
+        p = CNVMParameters(num_opinions=2, network=nl, r=1.0, r_tilde=0.05)
+        model = CNVM(p)
+        rate, noise_p = model.event_rates()
+        rp, col = oracle.neighbor_list_to_csr(nl)
+        nbtab, nblg = oracle.build_neighbor_table(rp, col)
+        counts = oracle.native_event_counts(seed, pair, 1, t_eval, rate)[0]
+        ox, oc, _, _ = oracle.cnvm_native(states[j], 2, rp, col, int(oracle.prob_to_thr(noise_p)), oracle.prob_to_thr(p.prob_imit),
+                                          oracle.prob_to_thr(p.prob_noise), None, None, counts, seed, pair, nbtab=nbtab,
+                                          nbtab_log2=max(nblg, 0))
+        np.testing.assert_array_equal(x[j, i], ox)
+        np.testing.assert_array_equal(c[j, i], oc.astype(float))
+
+
 def test_update_rates_and_cntm_drivers():
     import networkx as nx
 
