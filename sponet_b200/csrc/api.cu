@@ -114,10 +114,14 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
         n4 += (row[i].y + 3) / 4;
     }
     SP_REQUIRE(n4 < ((int64_t)1 << 31), "graph_create: network too large");
-    std::vector<int4> col4((size_t)std::max<int64_t>(n4, 1), make_int4(-1, -1, -1, -1));
+    // The padding entries of row i hold i itself: an agent never counts as a neighbour of the opposite
+    // opinion of itself, so the CNTM row scan needs no validity test per entry.
+    std::vector<int4> col4((size_t)std::max<int64_t>(n4, 1), make_int4(0, 0, 0, 0));
     for (int64_t i = 0; i < n; ++i) {
         int32_t* dst = reinterpret_cast<int32_t*>(col4.data() + row4[i].x);
+        const int32_t padded = (row[i].y + 3) / 4 * 4;
         for (int32_t k = 0; k < row[i].y; ++k) dst[k] = col[row[i].x + k];
+        for (int32_t k = row[i].y; k < padded; ++k) dst[k] = (int32_t)i;
     }
     // neighbour sampler table: agent i, slot j of L = 2^lg.  Neighbour k owns the slot interval
     // [k L / d, (k+1) L / d); slot j belongs to its primary neighbour floor(j d / L) up to the boundary

@@ -29,7 +29,7 @@ namespace {
 struct NativeCntmArgs {
     int32_t n;
     const int2* row4;  // (first int4 index, degree)
-    const int4* col4;  // rows padded to multiples of four, -1 sentinels
+    const int4* col4;  // rows padded to multiples of four with the row's own agent
     uint32_t noise_thr;
     const int32_t* need01;  // [max_degree + 1] minimum count of ones for a 0 -> 1 flip (INT_MAX = never)
     const int32_t* need10;  // [max_degree + 1] minimum count of zeros for a 1 -> 0 flip
@@ -227,24 +227,26 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                 const uint32_t xa = (st_load<SMEM>(state + wa) >> ba) & 1u;
                 const uint32_t other = xa ^ 1u;
                 int cnt = 0;
-                auto one = [&](int v, uint32_t oth, int& c_out, bool& h_out) {
-                    const bool ok = v >= 0;
-                    const uint32_t vv = ok ? (uint32_t)v : 0u;
+                // `self` is the agent whose row the entry belongs to: padding entries hold it.  Its own bit
+                // equals its opinion, never the opposite one, so padding adds nothing to the count; only the
+                // Bloom probe has to skip it (the agent itself is in the filter).
+                auto one = [&](int v, uint32_t self, uint32_t oth, int& c_out, bool& h_out) {
+                    const uint32_t vv = (uint32_t)v;
                     const uint32_t bitv = (st_load<SMEM>(state + (vv >> 5)) >> (vv & 31)) & 1u;
-                    c_out += (int)(ok & (bitv == oth));
+                    c_out += (int)(bitv == oth);
                     if (bloom_bits) {  // (a re-scan probes the cleared filter: no hits, and none are used)
                         const uint32_t h = __umulhi(vv * 2654435761u, bloom_bits);
-                        h_out |= ok & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
+                        h_out |= (vv != self) & (bool)((bloom[h >> 5] >> (h & 31)) & 1u);
                     }
                 };
-                auto four = [&](const int4& v, uint32_t oth, int& c_out, bool& h_out) {
-                    one(v.x, oth, c_out, h_out);
-                    one(v.y, oth, c_out, h_out);
-                    one(v.z, oth, c_out, h_out);
-                    one(v.w, oth, c_out, h_out);
+                auto four = [&](const int4& v, uint32_t self, uint32_t oth, int& c_out, bool& h_out) {
+                    one(v.x, self, oth, c_out, h_out);
+                    one(v.y, self, oth, c_out, h_out);
+                    one(v.z, self, oth, c_out, h_out);
+                    one(v.w, self, oth, c_out, h_out);
                 };
-                if (chunks > 0) four(c00, other, cnt, hit);
-                if (chunks > 1) four(c01, other, cnt, hit);
+                if (chunks > 0) four(c00, a, other, cnt, hit);
+                if (chunks > 1) four(c01, a, other, cnt, hit);
                 if (total > 0) {  // warp-uniform
 #pragma unroll 1
                     for (int base = 0; base < total; base += 32) {
@@ -258,10 +260,13 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                         const int first_item = __shfl_sync(FULL, inc - t, o);
                         const int rx = __shfl_sync(FULL, row.x, o);
                         const uint32_t oth = __shfl_sync(FULL, other, o);
-                        const int4 v = it < total ? __ldg(A.col4 + rx + 2 + (it - first_item)) : none;
+                        const uint32_t a_o = __shfl_sync(FULL, a, o);
+                        // lanes beyond the work list scan four copies of some owner's agent: no count, no probe
+                        const int4 v = it < total ? __ldg(A.col4 + rx + 2 + (it - first_item))
+                                                  : make_int4((int)a_o, (int)a_o, (int)a_o, (int)a_o);
                         int c_it = 0;
                         bool h_it = false;
-                        four(v, oth, c_it, h_it);
+                        four(v, a_o, oth, c_it, h_it);
                         if (c_it) atomicAdd(&coop[o], c_it);
                         if (h_it) atomicOr((uint32_t*)&coop[32], 1u << o);
                     }
