@@ -4,12 +4,17 @@ A hundred and ten seeded configurations drawn at random -- graph family and size
 widths), alpha (uniform / alias agent selection), irregular output grids with empty intervals, warp schedule,
 shared- or global-memory chain state -- each compared bit for bit (states, CV values, event counters).
 """
+import os
+
 import numpy as np
 import pytest
 
 from conftest import library_neighbor_table
 
 pytestmark = pytest.mark.gpu
+
+# SPONET_FUZZ_OFFSET=k shifts every seed: more configurations without editing the file
+OFFSET = 100_000 * int(os.environ.get("SPONET_FUZZ_OFFSET", "0"))
 
 
 def _graph(rng, n):
@@ -44,7 +49,7 @@ def _t_eval(rng, mean_gap):
 def test_cnvm_native_fuzz(oracle, case):
     from sponet_b200 import CNVM, CNVMParameters, engine
 
-    rng = np.random.default_rng(1000 + case)
+    rng = np.random.default_rng(1000 + case + OFFSET)
     n = int(rng.choice([33, 64, 100, 257, 1000, 4096, 5000]))
     M = int(rng.choice([2, 3, 4, 5, 16, 17, 60]))
     alpha = float(rng.choice([1.0, 1.0, 0.5, 0.0]))
@@ -107,7 +112,7 @@ def test_cnvm_native_fuzz(oracle, case):
 def test_cntm_native_fuzz(oracle, case):
     from sponet_b200 import CNTM, CNTMParameters, engine
 
-    rng = np.random.default_rng(5000 + case)
+    rng = np.random.default_rng(5000 + case + OFFSET)
     n = int(rng.choice([33, 100, 1000, 5000]))
     thr01, thr10 = float(rng.choice([0.0, 0.25, 0.5, 0.75, 1.0, 1.5])), float(rng.choice([0.0, 0.3, 0.5, 1.0]))
     params = CNTMParameters(network=_graph(rng, n), r=float(rng.uniform(0.2, 2)), r_tilde=float(rng.choice([0.0, 0.1, 1.0])),
