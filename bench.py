@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json metric, SURVEY.md section 8(d) "H", BASELINE.md section 3 headline row):
 CNVM, M = 3, ER G(1e5, 10/(N-1)) seed 12345 (nnz 998 782), fixture rates (r_imit 2, r_noise 0.6),
-alpha = 1, x_init = default_rng(0).integers(0, 3, N), t_max = 10, 101 output times, OpinionShares(3)
+alpha = 1, x_init = default_rng(0).integers(0, 3, N), t_max = 100, 101 output times, OpinionShares(3)
 reduced in-kernel, 10^4 realizations per GPU.  One "step" = one pass of the hot path over that batch
 (~2.6e10 candidate events per GPU).  An "event" is one iteration of the reference while-loop
 (sponet/cnvm/model.py:274-306): one candidate event of the uniformised chain, accepted or not.
@@ -43,11 +43,11 @@ sys.path.insert(0, ROOT)
 METRIC = "agent-update events/sec (CNVM, ER N=1e5, ensemble)"
 N_AGENTS = 100_000
 RUNS_PER_GPU = 10_000
-T_MAX = 10.0
+T_MAX = 100.0  # H runs to t_max = 100 with 101 output times (2.6e7 events per realization)
 NUM_T = 101
 WORKLOAD = (
     "H: CNVM M=3 on ER N=1e5 <d>=10 (fast_gnp seed 12345, nnz 998782), fixture rates r_imit=2 r_noise=0.6, "
-    "alpha=1, t_max=10, 101 output times, OpinionShares(3) in-kernel, 1e4 realizations per GPU"
+    "alpha=1, t_max=100, 101 output times, OpinionShares(3) in-kernel, 1e4 realizations per GPU"
 )
 
 
@@ -301,11 +301,12 @@ def run_gpu_arm(args) -> None:
                        "accepted_fraction": p_acc},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "sponet_b200.sample_many_runs(params, x_init, 10.0, 101, 10000, collective_variable=OpinionShares(3))",
+                    "api": "sponet_b200.sample_many_runs(params, x_init, 100.0, 101, 10000, collective_variable=OpinionShares(3))",
                     "steps": e2e_steps},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                         "traffic": ncu_traffic_per_launch(), "traffic_source": ncu_capture().get("source"),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bytes_per_event,
                          # SURVEY.md 8(d) context figure: what an HBM-resident design would move, one 32 B sector per
                          # independent random access (4 per imitation event, 1 per noise event)
@@ -323,7 +324,7 @@ def run_gpu_arm(args) -> None:
             runs = max(threads, int(threads * max(1.0, 12.0 / max(sec, 1e-3))))
             ev, sec = cpu_reference_run(runs, threads, 3)
             line["cpu_baseline"] = {"value": ev / sec, "unit": "events/s", "cores": threads, "kind": "port",
-                                    "sample": f"{runs} realizations of H (t_max=10, T=101) on {threads} host threads, {sec:.1f} s"}
+                                    "sample": f"{runs} realizations of H (t_max=100, T=101) on {threads} host threads, {sec:.1f} s"}
         print(json.dumps(line), flush=True)
     del keep
     if world > 1:
