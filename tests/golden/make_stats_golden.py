@@ -1,16 +1,24 @@
 """Reference CV samples for the statistical parity tests of native mode (build container only).
 
-    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_stats_golden.py
+    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_stats_golden.py [name ...]
 
-For each small configuration the UNMODIFIED reference runs >= 1e4 realizations through
+For each configuration the UNMODIFIED reference runs >= 1e4 realizations through
 `sample_many_runs(..., n_jobs=8)` with OpinionShares as collective variable; the per-run counts
-[R, T, M] are stored as uint16 in tests/golden/stats_*.npz together with the inputs.
+[R, T, M] are stored in tests/golden/stats_*.npz together with the inputs (uint16, or uint32 when
+N > 65535).  Seeds are fixed integers (SEEDS), so a fixture is reproducible bit for bit with the same
+numpy / numba / networkx versions and n_jobs.
+
+Small shapes (N = 300-500) carry their CSR; the BASELINE-size shapes (config 2: ER N = 1e4; H: ER N = 1e5;
+config 3: CNTM on BA N = 1e4 / 1e5) rebuild their network from `sponet_b200.workloads` (same generator,
+same seed, on every box) and store a CRC of the CSR so that a drifting generator is noticed.
 """
 import os
 import sys
 
 os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
 sys.path.insert(0, "/root/reference")
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+import zlib  # noqa: E402
 
 import networkx as nx  # noqa: E402
 import numpy as np  # noqa: E402
@@ -22,6 +30,9 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 R3 = np.array([[0, 1, 2], [1, 0, 1], [2, 0, 0]], dtype=float)
 RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
 RUNS = 12_000
+SEEDS = {"cnvm_er500": 101, "cnvm_ba400_alpha0": 102, "cnvm_complete300": 103, "cntm_er400": 104,
+         "cnvm_er1e4": 201, "cnvm_er1e5": 202, "cntm_ba1e4": 203, "cntm_ba1e5": 204}
+ONLY = set(sys.argv[1:])
 
 
 def csr(nl):
@@ -37,12 +48,20 @@ def patch(g):
     return g
 
 
-def run(name, params, M, x0, t_max, T, extra):
+def run(name, params, M, x0, t_max, T, extra, runs=RUNS):
+    if ONLY and name not in ONLY:
+        return
     cv = OpinionShares(M)
-    _, x = sample_many_runs(params, x0, t_max, T, RUNS, n_jobs=8, collective_variable=cv, rng=np.random.default_rng(hash(name) % 2**32))
-    np.savez_compressed(os.path.join(OUT, f"stats_{name}.npz"), counts=x.astype(np.uint16), x_init=x0.astype(np.uint8),
-                        t_max=t_max, num_t=T, num_opinions=M, **extra)
-    print(name, x.shape, "mean at t_max:", x[:, -1].mean(0))
+    _, x = sample_many_runs(params, x0, t_max, T, runs, n_jobs=8, collective_variable=cv, rng=np.random.default_rng(SEEDS[name]))
+    dt = np.uint16 if x0.size < 65536 else np.uint32
+    assert np.array_equal(x, np.round(x)) and x.max() <= np.iinfo(dt).max
+    np.savez_compressed(os.path.join(OUT, f"stats_{name}.npz"), counts=x.astype(dt), x_init=x0.astype(np.uint8),
+                        t_max=t_max, num_t=T, num_opinions=M, seed=SEEDS[name], **extra)
+    print(name, x.shape, "mean at t_max:", x[:, -1].mean(0), flush=True)
+
+
+def crc(rp, col):
+    return zlib.crc32(np.ascontiguousarray(col).tobytes(), zlib.crc32(np.ascontiguousarray(rp).tobytes()))
 
 
 # CNVM on a network, alpha = 1 (uniform agent choice)
@@ -74,3 +93,27 @@ rp, col = csr(nl)
 x0 = np.random.default_rng(3).integers(0, 2, 400)
 run("cntm_er400", CNTMParameters(network=g, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5), 2, x0, 10.0, 6,
     dict(model="cntm", row_ptr=rp, col=col, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5))
+
+# ---- BASELINE-size shapes: networks come from sponet_b200.workloads (rebuilt by the test, CRC-checked) ----
+from sponet_b200 import workloads  # noqa: E402  (host-side generators only; no GPU code is touched)
+
+for name, n, t_max, T in (("cnvm_er1e4", 10_000, 10.0, 6), ("cnvm_er1e5", 100_000, 2.0, 5)):
+    if ONLY and name not in ONLY:
+        continue
+    g = workloads.er_network(n, 10.0, 12345)
+    nl = calculate_neighbor_list(g)
+    rp, col = csr(nl)
+    x0 = np.random.default_rng(0).integers(0, 3, n)
+    run(name, CNVMParameters(num_opinions=3, network=nl, r=R3, r_tilde=RT3), 3, x0, t_max, T,
+        dict(model="cnvm", workload="headline_cnvm", num_agents=n, csr_crc=crc(rp, col), r=R3, r_tilde=RT3, alpha=1.0), runs=10_000)
+
+for name, n, t_max, T in (("cntm_ba1e4", 10_000, 10.0, 6), ("cntm_ba1e5", 100_000, 2.0, 5)):
+    if ONLY and name not in ONLY:
+        continue
+    g = nx.barabasi_albert_graph(n, 5, seed=1)
+    nl = calculate_neighbor_list(g)
+    rp, col = csr(nl)
+    x0 = np.random.default_rng(0).integers(0, 2, n)
+    run(name, CNTMParameters(network=g, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5), 2, x0, t_max, T,
+        dict(model="cntm", workload="ba_cntm", num_agents=n, csr_crc=crc(rp, col), r=1.0, r_tilde=0.2, threshold_01=0.5,
+             threshold_10=0.5), runs=10_000)

@@ -255,7 +255,7 @@ def test_cnvm_pair_mode_matches_single_warp_and_oracle(oracle, n, M, alpha):
     del keep
 
 
-def test_headline_size_pair_vs_single_and_conservation():
+def test_headline_size_pair_vs_single_and_conservation(oracle):
     """Full-size workload H (ER N=1e5, nnz 998 782): the two-warps-per-chain schedule (what bench.py runs)
     against one warp per chain -- identical CV trajectories, moment sums and counters -- plus the
     size-independent properties: counts sum to N at every output time, snapshot 0 is the initial
@@ -288,6 +288,24 @@ def test_headline_size_pair_vs_single_and_conservation():
     _lib.check(_lib.lib().sponet_native_event_counts(99, 0, R, _lib.ptr(t_eval), T, 1.0 / rate, _lib.ptr(sched), None))
     assert int(counters[0]) == int(sched.sum())
     assert abs(sched.sum() / (R * 0.5 * rate) - 1) < 1e-3  # Poisson totals
+
+    # the sequential oracle at the full size of H: agent states AND counts of four chains (the first, two
+    # from the middle of the launch -- later waves of their slots -- and the last), bit for bit, in the
+    # schedule bench.py runs (automatic: two warps per chain)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    _, noise_p = model.event_rates()
+    nbtab, nblg = _nbtab(oracle, model, rp, col)
+    assert nblg == 5  # H takes the one-gather neighbour sampler with 32 slots per agent
+    for i in (0, 611, 1234, R - 1):
+        xs, cvi = engine.run_native("cnvm", model._graph(), n, struct, x0[None, :], t_eval, 99, R, i, i + 1, cv_spec=spec,
+                                    want_x=True, want_cv=True)
+        np.testing.assert_array_equal(cvi[0, 0], cv[i])  # the same chain alone == inside the full launch
+        ox, oc, ev, _ = oracle.cnvm_native(x0, 3, rp, col, int(oracle.prob_to_thr(noise_p)),
+                                           oracle.prob_to_thr(params.prob_imit), oracle.prob_to_thr(params.prob_noise),
+                                           None, None, sched[i], 99, i, nbtab=nbtab, nbtab_log2=nblg)
+        np.testing.assert_array_equal(xs[0, 0], ox, err_msg=f"agent states of chain {i} differ from the sequential oracle")
+        np.testing.assert_array_equal(cv[i], oc.astype(float))
+        assert ev == int(sched[i].sum())
     del keep
 
 

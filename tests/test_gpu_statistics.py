@@ -25,13 +25,43 @@ ALPHA = 1e-3
 NATIVE_RUNS = 24_000
 
 
+def _crc(rp, col):
+    import zlib
+
+    return zlib.crc32(np.ascontiguousarray(col).tobytes(), zlib.crc32(np.ascontiguousarray(rp).tobytes()))
+
+
+def _workload_params(g, scale_noise):
+    """BASELINE-size fixtures do not carry their CSR: the network is rebuilt from sponet_b200.workloads (same
+    generator and seed as tests/golden/make_stats_golden.py) and its CRC compared with the stored one."""
+    from sponet_b200 import CNTMParameters, CNVMParameters, workloads
+    from sponet_b200.utils import calculate_neighbor_list, neighbor_list_to_csr
+
+    n = int(g["num_agents"])
+    if str(g["workload"]) == "headline_cnvm":
+        nl = calculate_neighbor_list(workloads.er_network(n, 10.0, 12345))
+        params = CNVMParameters(num_opinions=3, network=nl, r=g["r"], r_tilde=g["r_tilde"] * scale_noise)
+    else:
+        import networkx as nx
+
+        net = nx.barabasi_albert_graph(n, 5, seed=1)
+        nl = calculate_neighbor_list(net)
+        params = CNTMParameters(net, float(g["r"]), float(g["r_tilde"]) * scale_noise, float(g["threshold_01"]),
+                                float(g["threshold_10"]))
+    rp, col = neighbor_list_to_csr(nl)
+    assert _crc(rp.astype(np.int32), col.astype(np.int32)) == int(g["csr_crc"]), "network generator drifted from the fixture's"
+    return params
+
+
 def _native_counts(g, runs, seed, scale_noise=1.0):
     import networkx as nx
 
     from sponet_b200 import CNTMParameters, CNVMParameters, OpinionShares, sample_many_runs
 
     model, M = str(g["model"]), int(g["num_opinions"])
-    if model == "cntm":
+    if "workload" in g:
+        params = _workload_params(g, scale_noise)
+    elif model == "cntm":
         nl = csr_to_neighbor_list(g["row_ptr"], g["col"])
         net = nx.Graph()
         net.add_nodes_from(range(len(nl)))
@@ -82,6 +112,36 @@ def test_native_mode_matches_reference_distribution(name):
     assert zm <= Z, f"means differ: z = {zm:.2f}"
     assert zv <= Z, f"variances differ: z = {zv:.2f}"
     assert pmin >= ALPHA / n_cmp, f"KS rejects: p = {pmin:.3g}"
+
+
+@pytest.mark.parametrize("name", ["cnvm_er1e4", "cnvm_er1e5", "cntm_ba1e4", "cntm_ba1e5"])
+def test_native_mode_matches_reference_at_baseline_sizes(name):
+    """The same comparison on the BASELINE.json shapes: config 2 (CNVM M=3, ER N=1e4), H (ER N=1e5), config 3
+    (CNTM on BA m=5, N=1e4 and N=1e5), 1e4 reference runs each (unmodified numba path, n_jobs=8) against 2e4
+    native runs.  These sizes exercise what the small fixtures cannot: the neighbour sampler table at lg=5,
+    agent selection quantised to N / 2^32, the Bloom-filter sizing, the two-warps-per-chain schedule, hub rows
+    of ~10^3 neighbours (BA), and the native snapshot rule (state AT t_eval[k]) against the reference's
+    nearest-event rule."""
+    g = load_golden("stats_" + name)
+    ref = g["counts"].astype(np.int64)
+    runs = 20_000
+    nat = _native_counts(g, runs, seed=4242)
+    assert nat.shape == (runs,) + ref.shape[1:]
+    np.testing.assert_array_equal(nat[:, 0], np.broadcast_to(ref[0, 0], nat[:, 0].shape))
+    assert (nat.sum(-1) == g["x_init"].size).all()
+    zm, zv, pmin, n_cmp = _compare(ref, nat)
+    print(f"{name}: worst z(mean)={zm:.2f} z(var)={zv:.2f} min KS p={pmin:.3g} over {n_cmp} comparisons")
+    assert zm <= Z, f"means differ: z = {zm:.2f}"
+    assert zv <= Z, f"variances differ: z = {zv:.2f}"
+    assert pmin >= ALPHA / n_cmp, f"KS rejects: p = {pmin:.3g}"
+
+
+def test_statistical_test_has_power_at_baseline_size():
+    """At N = 1e4 the comparison must still reject a 2 % perturbation of the noise rates."""
+    g = load_golden("stats_cnvm_er1e4")
+    nat = _native_counts(g, 20_000, seed=8, scale_noise=1.02)
+    zm, _, _, _ = _compare(g["counts"].astype(np.int64), nat)
+    assert zm > 2 * Z, f"test is too weak: z = {zm:.2f}"
 
 
 def test_statistical_test_has_power():
