@@ -14,6 +14,7 @@ from .collective_variables import (
     Interfaces,
     OpinionShares,
     OpinionSharesByDegree,
+    Propensities,
 )
 from .engine import set_default_mode
 from .multiprocessing import sample_many_runs
@@ -24,7 +25,7 @@ from .steady_state import estimate_steady_state
 __all__ = [
     "CNTM", "CNTMParameters", "CNVM", "CNVMParameters", "CollectiveVariable",
     "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "Interfaces", "OpinionShares",
-    "OpinionSharesByDegree", "Parameters", "load_params", "save_params", "sample_many_runs",
+    "OpinionSharesByDegree", "Parameters", "Propensities", "load_params", "save_params", "sample_many_runs",
     "sample_moments", "estimate_steady_state", "set_default_mode",
 ]
 __version__ = "0.1.0"

@@ -46,7 +46,10 @@ class CNTM:
         if x_init is None:
             x = rng.choice(np.arange(p.num_opinions, dtype=dtype), size=p.num_agents)
         else:
-            x = np.array(x_init, dtype=dtype)
+            xi = np.asarray(x_init)
+            if xi.size and (xi.min() < 0 or xi.max() >= 2):
+                raise ValueError("x_init must hold opinions in [0, num_opinions)")
+            x = np.array(xi, dtype=dtype)
         if x.shape != (p.num_agents,):
             raise ValueError(f"x_init must have shape ({p.num_agents},)")
         if t_eval is not None:

@@ -23,6 +23,7 @@ int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, 
                            int T, double next_event_rate, int64_t* d_counts);
 int sp_validate_native_common(const double* t_eval, int64_t T, const sponet_native_opts* o, int64_t S);
 int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, int64_t n);
+int sp_validate_states(const uint8_t* x, int64_t count, int M);
 
 namespace {
 
@@ -438,6 +439,7 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     SP_REQUIRE(g->device == dev, "graph lives on device %d, current device is %d", g->device, dev);
     const int64_t n = g->n, nrun = o->run_end - o->run_begin, num_chains = S * nrun;
     if (num_chains == 0) return SPONET_OK;
+    SP_TRY(sp_validate_states(x_init, S * n, 2));
 
     SpScratch sc((cudaStream_t)cuda_stream);
     NativeCntmArgs A{};

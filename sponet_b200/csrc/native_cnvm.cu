@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 for (int q = 0; q < P::APW; ++q) {
                     const uint32_t a = base + q;
                     if (a < n) {
-                        const uint32_t v = x0[a];
+                        // (host inputs are range-checked by sponet_cnvm_run; a device-resident x_init is clamped so
+                        // that a bad value can never spill into a neighbour's bits or another chain's counters)
+                        const uint32_t v = min((uint32_t)x0[a], (uint32_t)(M - 1));
                         packed |= v << (q * BITS);
                         if (PACKCNT) {
                             c0 += (v == 0);
@@ -819,6 +821,19 @@ int sp_validate_native_common(const double* t_eval, int64_t T, const sponet_nati
     return SPONET_OK;
 }
 
+// Initial opinions must lie in [0, M): a larger value would be packed into a neighbouring agent's bits and
+// counted in another chain's counters.  Host buffers are checked here (the reference never checks and would
+// index prob_*[x, .] out of bounds, cnvm/model.py:278,288); device-resident buffers cannot be checked without
+// a synchronisation, the kernels clamp them instead.
+int sp_validate_states(const uint8_t* x, int64_t count, int M) {
+    if (!x || M >= 256 || sp_is_device_ptr(x)) return SPONET_OK;
+    for (int64_t i = 0; i < count; ++i)
+        if (x[i] >= M)
+            return sponet_fail(SPONET_ERR_INVALID, "x_init[%lld] = %d is not an opinion in [0, %d)", (long long)i,
+                               (int)x[i], M);
+    return SPONET_OK;
+}
+
 // Stages the in-kernel CV descriptor.  `n` > 0 allows the per-agent class / weight arrays (CNVM agent-level
 // kernel); kernels that only keep plain opinion counts pass n = 0.
 int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, int64_t n) {
@@ -991,6 +1006,8 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     if (g) SP_REQUIRE(g->device == dev, "graph lives on device %d, current device is %d", g->device, dev);
     const int64_t num_chains = S * nrun;
     if (num_chains == 0) return SPONET_OK;
+
+    SP_TRY(sp_validate_states(x_init, S * n, M));
 
     SpScratch sc((cudaStream_t)cuda_stream);
     NativeCnvmArgs A{};

@@ -64,11 +64,27 @@ def _split_runs(num_runs: int, num_chunks: int) -> np.ndarray:
 _MODEL_CACHE: dict[int, tuple] = {}
 
 
+def _network_digest(net) -> int:
+    """Cheap content hash of the adjacency (a network rewired IN PLACE keeps its id): CRC of the degree
+    sequence and of the concatenated neighbour ids.  ~1 ms per 1e6 edges for adjacency lists."""
+    import zlib
+
+    if net is None:
+        return 0
+    if hasattr(net, "adj"):  # networkx graph (CNTM parameters)
+        deg = np.fromiter((d for _, d in net.degree()), dtype=np.int64)
+        nbr = np.fromiter((v for _, nb in net.adjacency() for v in nb), dtype=np.int64, count=int(deg.sum()))
+    else:
+        deg = np.fromiter((len(nb) for nb in net), dtype=np.int64, count=len(net))
+        nbr = np.concatenate([np.asarray(nb, dtype=np.int64) for nb in net]) if len(net) else np.zeros(0, np.int64)
+    return zlib.crc32(nbr.tobytes(), zlib.crc32(deg.tobytes()))
+
+
 def _fingerprint(params):
     net = getattr(params, "network", None)
     if isinstance(params, CNVMParameters):
-        return (id(net), params.alpha, params.num_agents)
-    return (id(net), net.number_of_nodes(), net.number_of_edges(), params.r, params.r_tilde)
+        return (id(net), _network_digest(net), params.alpha, params.num_agents)
+    return (id(net), _network_digest(net), params.r, params.r_tilde)
 
 
 def _make_model(params: Parameters):
@@ -129,6 +145,7 @@ def sample_many_runs(
     model, kind = _make_model(params)
     mode = engine.resolve_mode(mode)
     dtype = np.min_scalar_type(params.num_opinions - 1)
+    _check_states(initial_states, params.num_opinions)
 
     per_run_network = getattr(params, "network_generator", None) is not None
     if mode == "replay" or params.num_opinions > 256:
@@ -143,6 +160,13 @@ def sample_many_runs(
                                collective_variable, rng, progress_bar).astype(
             dtype if collective_variable is None else np.float64, copy=False)
     return t_out, (x_out[0] if is_1d else x_out)
+
+
+def _check_states(states: np.ndarray, num_opinions: int) -> None:
+    """Opinions outside [0, M) would be bit-packed into a neighbouring agent's field; the reference indexes
+    prob_imit[x, .] with them unchecked (cnvm/model.py:288).  Rejected here, before the uint8 cast."""
+    if states.size and (states.min() < 0 or states.max() >= num_opinions):
+        raise ValueError(f"initial states must hold opinions in [0, {num_opinions})")
 
 
 # ---------------------------------------------------------------------------------------------

@@ -52,7 +52,10 @@ def batch_moment_sums(model, kind, state, t_grid, batch_size, cv, rng) -> tuple[
         spec = None
     if spec is not None and (not spec.integer_valued or (spec.edge and p.num_opinions != 2)):
         spec = None  # Propensities are float sums: moments from the returned CV values instead
-    if spec is not None and engine.resolve_mode(None) == "native":
+    # A NetworkGenerator means a fresh network for every run (cnvm/model.py:95-96 via sample_many_runs): that is
+    # what the generic path below does; the fused path would simulate one (stale or complete) network.
+    per_run_network = getattr(p, "network_generator", None) is not None
+    if spec is not None and not per_run_network and engine.resolve_mode(None) == "native":
         from .multiprocessing import _broadcast_seed
 
         seed = engine.draw_seed(rng)

@@ -318,6 +318,69 @@ def test_network_generator_resamples_per_run():
     assert c.shape == (4, 3, 2) and gen.calls == 6 and (c.sum(-1) == 60).all()
 
 
+def test_sample_moments_resamples_the_network_per_run():
+    """sample_moments with a NetworkGenerator must draw a fresh network for every run like the reference
+    (sample_moments.py:96 -> sample_many_runs -> simulate -> update_network), not run the fused path on one
+    (complete / stale) network: its sums equal those of sample_many_runs on an identical generator."""
+    from sponet_b200 import CNVMParameters, OpinionShares, sample_many_runs, sample_moments
+
+    n, R, T = 60, 12, 4
+    x0 = np.random.default_rng(0).integers(0, 2, n)
+    gen = _RingGenerator(n, seed=3)
+    params = CNVMParameters(num_opinions=2, network_generator=gen, r=1.0, r_tilde=0.05)
+    t, mean, var, ns = sample_moments(params, x0, 2.0, T, R, rel_tol=1e9, collective_variable=OpinionShares(2),
+                                      rng=np.random.default_rng(4))
+    assert gen.calls == R and ns == R
+    ref = CNVMParameters(num_opinions=2, network_generator=_RingGenerator(n, seed=3), r=1.0, r_tilde=0.05)
+    _, c = sample_many_runs(ref, x0, 2.0, T, R, collective_variable=OpinionShares(2), rng=np.random.default_rng(4))
+    np.testing.assert_allclose(mean, c.mean(0), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(var, (c**2).mean(0) - c.mean(0) ** 2, rtol=0, atol=1e-9)
+
+
+def test_out_of_range_initial_opinions_are_rejected():
+    """An opinion >= num_opinions would be packed into the neighbouring agent's bits: ValueError from
+    the Python layer, SPONET_ERR_INVALID from the C ABI for host buffers."""
+    from sponet_b200 import CNVM, CNVMParameters, OpinionShares, engine, sample_many_runs, workloads
+
+    params, x0, _ = workloads.headline_cnvm(300)
+    bad = x0.copy()
+    bad[7] = 3
+    with pytest.raises(ValueError, match="opinions in"):
+        CNVM(params).simulate(1.0, bad, 3, rng=np.random.default_rng(0))
+    with pytest.raises(ValueError, match="opinions in"):
+        sample_many_runs(params, bad, 1.0, 3, 2, collective_variable=OpinionShares(3), rng=np.random.default_rng(0))
+    model = CNVM(params)
+    struct, keep = model._struct()
+    with pytest.raises(ValueError, match="not an opinion"):
+        engine.run_native("cnvm", model._graph(), 300, struct, bad[None, :], np.linspace(0, 1, 3), 1, 2, 0, 2,
+                          cv_spec=(np.arange(3, dtype=np.int32), 1.0), want_cv=True)
+    del keep
+
+
+def test_model_cache_notices_in_place_rewiring():
+    """sample_many_runs keeps the model (CSR on the GPU) per parameter object; an adjacency mutated in place
+    keeps its id and its edge count, so the cache keys on a content hash as well."""
+    import networkx as nx
+
+    from sponet_b200 import CNTMParameters, OpinionShares, sample_many_runs
+
+    g = nx.cycle_graph(40)
+    params = CNTMParameters(network=g, r=1.0, r_tilde=0.1, threshold_01=0.5, threshold_10=0.5)
+    x0 = np.random.default_rng(0).integers(0, 2, 40)
+    kw = dict(collective_variable=OpinionShares(2), rng=None)
+    run = lambda: sample_many_runs(params, x0, 3.0, 4, 50, collective_variable=OpinionShares(2),  # noqa: E731
+                                   rng=np.random.default_rng(5))[1]
+    a = run()
+    np.testing.assert_array_equal(a, run())
+    nx.double_edge_swap(g, nswap=15, max_tries=1000, seed=1)  # same node / edge counts, same object
+    b = run()
+    fresh = CNTMParameters(network=g.copy(), r=1.0, r_tilde=0.1, threshold_01=0.5, threshold_10=0.5)
+    c = sample_many_runs(fresh, x0, 3.0, 4, 50, collective_variable=OpinionShares(2), rng=np.random.default_rng(5))[1]
+    np.testing.assert_array_equal(b, c)
+    assert not np.array_equal(a, b)
+    del kw
+
+
 def test_network_generator_native_chains_match_oracle(oracle):
     """Native mode with a NetworkGenerator: pair c = (state j, run i) is one chain on the c-th network of the
     generator, keyed by chain id c -- checked against the sequential oracle on the same networks."""
