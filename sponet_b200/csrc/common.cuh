@@ -186,10 +186,13 @@ __device__ __forceinline__ uint4 sp_philox4x32_10(uint32_t c0, uint32_t c1, uint
 
 // Same function with the ten round keys precomputed on the host (kernel-parameter constants: the key
 // schedule costs no instructions in the event loop).
+#ifndef SP_PHILOX_ROUNDS
+#define SP_PHILOX_ROUNDS 10  // (development switch: profiles/ has the cost of the generator measured with fewer rounds)
+#endif
 __device__ __forceinline__ uint4 sp_philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                      const uint32_t (&rk)[20]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < SP_PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ rk[2 * r];

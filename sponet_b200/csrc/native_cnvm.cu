@@ -9,8 +9,9 @@
 //     25 KB for N = 1e5, M = 3, i.e. 9 chains per SM in the 227 KB a B200 CTA can address -- so the
 //     state-dependent part (read x[a], x[nbr]; accept; write x[a]) costs shared-memory latency;
 //   * sequential semantics are restored exactly: a lane has a hazard when an EARLIER lane of the
-//     same step writes an agent it reads; lanes before the first hazard commit, the rest re-evaluate
-//     against the updated state (expected < 1.02 rounds per step at N = 1e5);
+//     same step writes an agent it reads.  The commit is optimistic: all lanes evaluate and write, then
+//     re-read what they read; a changed input rolls the step back, the exact prefix commits and the rest
+//     re-evaluates against the updated state (expected < 1.01 rounds per step at N = 1e5);
 //   * opinion counts (the OpinionShares CV) are maintained incrementally with warp ballots and
 //     emitted at the output times; full trajectories never leave the SM unless asked for;
 //   * sum / sum-of-squares over runs are accumulated with integer atomics (exact, order-free).
@@ -51,7 +52,6 @@ struct NativeCnvmArgs {
     int32_t words;     // 32-bit words per chain
     int32_t warps_per_cta;
     int32_t warps_per_chain;  // RING kernels: warps serving one chain
-    int32_t bloom_words;  // per-warp Bloom filter size in 32-bit words (0 = disabled)
     uint32_t rk[20];      // Philox4x32-10 round keys of the seed: (k0 + r*W0, k1 + r*W1), r = 0..9
 };
 
@@ -75,13 +75,9 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // Per warp step (32 consecutive candidate events of one chain) the work is split into
 //   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued
 //   stage 2  neighbour slot from the row; column gather issued
-//   stage 3  dependency mask: which EARLIER lanes touch an agent this lane reads.  Agents and
-//            neighbours never depend on the chain state, so this is known before the commit: a
-//            per-warp Bloom filter in shared memory flags lanes whose agent or neighbour may equal
-//            another lane's agent; only flagged lanes (none in most steps) get an exact mask,
-//            built with two shuffles and two ballots per flagged lane
-//   commit   read x[a], x[nbr]; accept; hazard = dep & ballot(accepting lanes); lanes before the
-//            first hazard write (atomicXor on the packed word), the rest re-evaluate
+//   commit   read x[a], x[nbr]; accept; accepting lanes write (atomicXor on the packed word); every lane
+//            re-reads its two locations: an input changed by another lane (or two real writers of one
+//            agent) rolls the step back, the exact prefix is committed and the rest re-evaluates
 // Stages 1 and 2 of the NEXT two steps are issued before the commit of the current one (software
 // pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies).
 //
@@ -101,32 +97,28 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 #define SP_RING_MAX_THREADS 512
 #endif
 
-__device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void sp_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void sp_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SP_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SP_DONE;\n"
-        "bra SP_WAIT;\n"
-        "SP_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t sp_lds(uint32_t saddr) {  // load through a 32-bit shared-window address
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+__device__ __forceinline__ uint2 sp_lds2(uint32_t saddr) {  // 8-byte variant
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
     return v;
 }
 __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named barrier of one chain's warps
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// the same barrier with a vote: true iff `pred` holds for any of the participating threads
+__device__ __forceinline__ bool sp_ring_any(int id, int threads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 q, %3, 0;\n"
+        "bar.red.or.pred p, %1, %2, q;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"(id), "r"(threads), "r"((uint32_t)pred)
+        : "memory");
+    return r != 0u;
 }
 
 // GRAPH: 0 = complete graph (no gather), 1 = CSR (row gather, then column gather), 2 = neighbour sampler
@@ -152,40 +144,40 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
     const int M = A.M, MM = M * M;
     const uint32_t n = (uint32_t)A.n;
     const uint32_t noise_thr = A.noise_thr;
-    const uint32_t lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
 
-    // shared layout: [thr] [mbarriers, one per warp (RING)] [counts slots*M] [bloom warps*bloom_words]
-    //                [states slots*words (if SMEM)]
-    // thr: M <= 4 -> 32 entries indexed (noise << 4 | m << 2 | nw); M <= 16 -> 2*MM entries
+    // shared layout: [thr] [reduction words, 4 per slot (COOP)] [counts slots*M] [states slots*words (if SMEM)]
+    // thr: M <= 4 -> 32 (threshold, packed count delta of the move m -> nw) pairs indexed (noise << 4 | m << 2 | nw),
+    //      one 8-byte load per event; M <= 16 -> 2*MM thresholds
     uint32_t* sp = smem;
     const uint32_t* thr = A.thr;
-    const uint32_t thr4_saddr = (uint32_t)__cvta_generic_to_shared(smem);  // THR4: the padded table sits first
+    uint32_t thr4_saddr = (uint32_t)__cvta_generic_to_shared(smem);  // THR4: the padded table sits first
+    asm volatile("" : "+r"(thr4_saddr));  // keep it in a register (ptxas re-derives it from SR_CgaCtaId per step otherwise)
     if (THR4) {
         for (int i = threadIdx.x; i < 32; i += blockDim.x) {
             const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
-            sp[i] = (m < M && w < M) ? A.thr[nz * MM + m * M + w] : 0u;
+            sp[2 * i] = (m < M && w < M) ? A.thr[nz * MM + m * M + w] : 0u;
+            sp[2 * i + 1] = (1u << (8 * w)) - (1u << (8 * m));  // +1 in byte w, -1 in byte m (see fold_counts)
         }
         thr = sp;
-        sp += 32;
+        sp += 64;
     } else if (THR_SMEM) {
         for (int i = threadIdx.x; i < 2 * MM; i += blockDim.x) sp[i] = A.thr[i];
         thr = sp;
         sp += (2 * MM + 1) & ~1;
     }
-    uint32_t bar_mine = 0, bar_pred = 0;
+    // COOP: three words per chain slot for the (rare) cross-warp reductions of the hazard path:
+    // [0] lowest real writer, [1] lowest flagged lane (positions within the super-step), [2] "two writers met"
+    uint32_t* red = sp + (size_t)slot * 4;
     if (RING) {
-        const uint32_t base = (uint32_t)__cvta_generic_to_shared(sp) + (uint32_t)(slot * W) * 8u;
-        bar_mine = base + (uint32_t)role * 8u;
-        bar_pred = base + (uint32_t)((role + W - 1) % W) * 8u;
-        if (lane == 0) sp_mbar_init(bar_mine, 32u);
-        sp += (size_t)A.warps_per_cta * 2;
+        if (role == 0 && lane == 0) {
+            red[0] = 0xffffffffu;
+            red[1] = 0xffffffffu;
+            red[2] = 0u;
+        }
+        sp += (size_t)slots * 4;
     }
     int32_t* cnt_mem = (int32_t*)sp + slot * A.cnt_stride;
     sp += (size_t)slots * A.cnt_stride;
-    const uint32_t bloom_bits = (uint32_t)A.bloom_words * 32u;  // per warp; 0 = no filter (all lanes flagged)
-    uint32_t* bloom = sp + (size_t)warp * A.bloom_words;
-    for (int i = threadIdx.x; i < A.warps_per_cta * A.bloom_words; i += blockDim.x) sp[i] = 0u;
-    sp += (size_t)A.warps_per_cta * A.bloom_words;
     uint32_t* state;
     if (SMEM) state = sp + (size_t)slot * A.words;
     else state = A.gstate + ((size_t)blockIdx.x * slots + slot) * A.words;
@@ -193,7 +185,6 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 
     const int64_t num_chains = A.S * A.nrun;
     unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_total = 0;
-    uint32_t pred_base = 0;  // RING: steps the predecessor warp completed in earlier chains (mbarrier phase)
     const int T = A.T;
 
     for (int64_t cl = (int64_t)blockIdx.x * slots + slot; cl < num_chains; cl += (int64_t)gridDim.x * slots) {
@@ -402,132 +393,173 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 nbr = __umulhi(q_r2[s], n - 1);
                 nbr += (nbr >= q_a[s]);
             }
-            q_nbr[s] = nbr;
+            q_nbr[s] = (q_meta[s] & 1u) ? q_a[s] : nbr;  // a noise event reads no neighbour: alias of its own agent
         };
 
-        uint32_t own_done = 0;  // own steps committed in this chain (RING: position in the hand-over ring)
-        const uint32_t wait_base = pred_base + (role == 0 ? 1u : 0u);
-        // stage 3 + commit of the step held in register set `cur` (nb events)
-        auto process = [&](int cur, int nb) {
-            const uint32_t a = q_a[cur], r3 = q_r3[cur], meta = q_meta[cur];
-            const bool noise = meta & 1u;
-            const uint32_t nbr = noise ? a : q_nbr[cur];
-            
-            // ---- stage 3: flag lanes that may depend on another lane, exact masks for those ----
-            // Every lane inserts its agent into the warp's Bloom filter.  A lane is flagged when the bit
-            // of its agent was already set (an equal agent in this step, or a hash collision; the
-            // MATCH.ANY alternative costs ~20 % on B200) or when the bit of its neighbour is set (the
-            // neighbour may be another lane's agent).  Flagged lanes get exact masks from two ballots;
-            // lanes sharing the flagged lane's agent get theirs too, because the order of the atomic
-            // inserts says nothing about the lane order.
-            uint32_t dep = 0;
-            uint32_t flagged;
-            if (bloom_bits) {
-                const uint32_t ha = __umulhi(a * 2654435761u, bloom_bits);
-                const uint32_t bit = 1u << (ha & 31);
-                bool hit = atomicOr(bloom + (ha >> 5), bit) & bit;
-                __syncwarp();
-                const uint32_t hn = __umulhi(nbr * 2654435761u, bloom_bits);
-                hit |= (!noise) & (bool)((bloom[hn >> 5] >> (hn & 31)) & 1u);
-                flagged = __ballot_sync(FULL, hit);
-                bloom[ha >> 5] = 0u;  // clear (every lane sharing the word stores the same value)
-            } else {
-                flagged = FULL;
-            }
-            for (uint32_t f = flagged; f; f &= f - 1) {  // usually zero iterations
-                const int il = __ffs(f) - 1;
-                const uint32_t ai = __shfl_sync(FULL, a, il), ni = __shfl_sync(FULL, nbr, il);
-                const uint32_t same_a = __ballot_sync(FULL, a == ai);
-                const uint32_t is_nbr = __ballot_sync(FULL, a == ni);
-                if (a == ai) dep |= same_a & lane_lt;
-                if (lane == il) dep |= is_nbr & lane_lt;
-            }
-
-            // ---- RING: the step right before this one (the predecessor warp's) must be committed ----
-            if (RING) {
-                // our k-th own step follows the predecessor's k-th (role > 0) or (k-1)-th (role 0) step; for
-                // role 0's first step that is the phase before the barrier's current one, complete by definition
-                sp_mbar_wait(bar_pred, (wait_base + own_done) & 1u);
-                ++own_done;
-            }
-            // The next own step's neighbour comes out of the entry gathered more than a step ago.  Doing
-            // this here, in a block of its own behind the wait, keeps it away from the gather issued at the
-            // top of this step: in one block ptxas put the two on one scoreboard and the consumer then
-            // waited for the fresh load (10 % of all stall samples).
-            issue2((cur + 1) % 3);
-
-            // ---- commit ----
-            const uint32_t wa = P::word(a), sa = P::shift(a);
-            const uint32_t wn = P::word(nbr), sn = P::shift(nbr);
-            const bool active = lane < nb;
-            uint32_t m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
-            uint32_t nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
+        // ---------------------------------------------------------------------------------------------------
+        // COMMIT: optimistic, verified, pipelined.
+        //
+        // A SUPER-STEP is the 32 * W consecutive events the W warps of a chain hold (warp `role` the events
+        // 32 * role ... 32 * role + 31 of it: positions v = 32 * role + lane).  It runs in two phases separated by
+        // barriers of the chain's warps (a warp barrier when W = 1):
+        //   write phase   every accepting lane XORs its change into the packed state (the atomic returns the word
+        //                 it replaced)
+        //   read phase    every lane re-reads the two locations its decision was based on -- and, in the same
+        //                 pass, reads the locations of its NEXT step and that step's acceptance threshold.  Nobody
+        //                 writes during a read phase, so the next step's decision is ready when the vote on the
+        //                 current one comes back, and a super-step costs one shared-memory round trip per phase.
+        // The super-step is exact unless some lane read a location that an EARLIER position really changed.  Let
+        // w0 be the lowest position that really changes its agent: positions <= w0 have exact inputs in any case.
+        //   * no location has two real writers (no writer got back a field other than the one it had read): the
+        //     re-reads are reliable -- a changed neighbour, or an own agent that is not what this lane left
+        //     there, flags the lane; the first position i* with stale inputs always flags itself, so with f = the
+        //     lowest flagged position, positions < max(f, w0 + 1) are exact;
+        //   * some location has several real writers: XORs may cancel and hide a change from a reader, so only
+        //     positions <= w0 are trusted.
+        // On a flag everything is rolled back (XOR is its own inverse), the exact prefix is committed for real and
+        // the remaining positions start over (tools/commit_model.py checks this protocol against the sequential
+        // semantics on random instances).  At N = 1e5 about 1 % of the 32-event steps are flagged.
+        // ---------------------------------------------------------------------------------------------------
+        const uint32_t vbase = 32u * (uint32_t)role;
+        auto coop_sync = [&]() {
+            if (RING) sp_ring_sync(slot + 1, 32 * W);
+            else __syncwarp();
+        };
+        auto coop_any = [&](bool p) -> bool {
+            if (RING) return sp_ring_any(slot + 1, 32 * W, p);
+            return __any_sync(FULL, p);
+        };
+        // decision of one lane for one step: locations, what it read, what it wants to write
+        struct Dec {
+            uint32_t wa, wn;    // word index of the agent / of the location imitated (own agent for a noise event)
+            uint32_t sa, sn;    // bit offsets within those words
+            uint32_t m, nw;     // opinion read, new opinion
+            uint32_t delta;     // THR4: packed count delta of m -> nw
+            bool acc;
+        };
+        auto evaluate = [&](int s, bool active, Dec& d) {
+            const uint32_t a = q_a[s], nbr = q_nbr[s], meta = q_meta[s];
+            d.wa = P::word(a);
+            d.wn = P::word(nbr);
+            d.sa = P::shift(a);
+            d.sn = P::shift(nbr);
+            d.m = (state_load<SMEM>(state + d.wa) >> d.sa) & P::VM;
+            d.nw = (meta & 1u) ? (meta >> 8) : ((state_load<SMEM>(state + d.wn) >> d.sn) & P::VM);
             uint32_t th;
-            if (THR4) th = sp_lds(thr4_saddr + ((((meta & 1u) << 4) | (m << 2) | nw) << 2));
-            else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
-            else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
-            bool acc = active && sp_thr_accept(r3, th);
-            uint32_t hmask = 0;
-            if (flagged) {
-                const uint32_t wmask = __ballot_sync(FULL, acc);
-                hmask = __ballot_sync(FULL, active && (dep & wmask) != 0u);
+            d.delta = 0;
+            if (THR4) {
+                const uint2 e = sp_lds2(thr4_saddr + ((((meta & 1u) << 4) | (d.m << 2) | d.nw) << 3));
+                th = e.x;
+                d.delta = e.y;
+            } else if (THR_SMEM) th = thr[((meta & 1u) ? MM : 0) + d.m * M + d.nw];
+            else th = __ldg(thr + ((meta & 1u) ? MM : 0) + d.m * M + d.nw);
+            d.acc = active && sp_thr_accept(q_r3[s], th);
+        };
+        // the same for the lanes still pending in a hazard round (positions >= g)
+        auto reevaluate = [&](int s, bool pending, Dec& d) {
+            evaluate(s, pending, d);
+        };
+        auto book = [&](int s, const Dec& d) {  // an accepted event m -> nw of this lane
+            ++my_acc;
+            if (PACKCNT) dpack += d.delta;
+            else count_move(q_a[s], d.m, d.nw);
+        };
+        auto xmask_of = [&](const Dec& d) -> uint32_t { return (d.m ^ d.nw) << d.sa; };
+        // write phase of one step; returns the word replaced
+        auto write = [&](const Dec& d) -> uint32_t {
+            uint32_t old = 0;
+            if (d.acc) old = atomicXor(state + d.wa, xmask_of(d));
+            return old;
+        };
+        // Between the write phase and the read phase.  Shared memory executes accesses in order: a barrier of the
+        // chain's warps is enough.  In global memory (W = 1) the atomics are performed at the L2 and a load issued
+        // right behind them could overtake them: there every writer first consumes the value its atomic returned
+        // (the vote on `multi`), which it only has once the atomic has been performed.
+        auto settle_writes = [&](const Dec& d, uint32_t old, bool& multi) {
+            multi = d.acc && (((old >> d.sa) & P::VM) != d.m);  // another real writer got there first
+            if (SMEM) {
+                coop_sync();
+            } else {
+                multi = __any_sync(FULL, multi);
+                __threadfence_block();
             }
-            if (hmask == 0) {  // no lane reads what an earlier accepting lane writes: all commit
-                if (acc) {
-                    atomicXor(state + wa, (m ^ nw) << sa);
-                    ++my_acc;
-                    if (PACKCNT) {
-                        dpack += (1u << (8 * nw)) - (1u << (8 * m));
-                    } else {
-                        count_move(a, m, nw);
+        };
+        // re-reads the lane's two locations: has an input changed?
+        auto changed = [&](int s, bool pending, const Dec& d) -> bool {
+            uint32_t chk = (state_load<SMEM>(state + d.wa) >> d.sa) ^ (d.acc ? d.nw : d.m);
+            if (!(q_meta[s] & 1u)) chk |= (state_load<SMEM>(state + d.wn) >> d.sn) ^ d.nw;
+            return pending && (chk & P::VM) != 0u;
+        };
+        // rare path, plain atomics followed by loads of other lanes
+        auto settle_plain = [&]() {
+            if (!SMEM) __threadfence();
+            coop_sync();
+        };
+        // The step in set `s` was flagged: roll back, commit the exact prefix, re-run the rest until clean.
+        auto hazard_rounds = [&](int s, bool active, Dec& d, bool bad, bool multi) {
+            bool pending = active;
+#pragma unroll 1
+            for (;;) {
+                if (d.acc) atomicXor(state + d.wa, xmask_of(d));  // roll back
+                const uint32_t writers = __ballot_sync(FULL, d.acc && d.m != d.nw);
+                const uint32_t badm = __ballot_sync(FULL, bad);
+                bool any_multi = __any_sync(FULL, multi);
+                uint32_t w0 = writers ? vbase + (uint32_t)__ffs(writers) - 1u : 0xffffffffu;
+                uint32_t f = badm ? vbase + (uint32_t)__ffs(badm) - 1u : 0xffffffffu;
+                if (RING) {
+                    if (lane == 0) {
+                        if (writers) atomicMin(red + 0, w0);
+                        if (badm) atomicMin(red + 1, f);
+                        if (any_multi) atomicOr(red + 2, 1u);
+                    }
+                    coop_sync();
+                    w0 = red[0];
+                    f = red[1];
+                    any_multi = red[2] != 0u;
+                    coop_sync();
+                    if (role == 0 && lane == 0) {  // (the next reduction is at least two barriers away)
+                        red[0] = 0xffffffffu;
+                        red[1] = 0xffffffffu;
+                        red[2] = 0u;
                     }
                 }
-                if (!SMEM) __threadfence_block();
-                if (!RING) __syncwarp();  // RING: the mbarrier hand-over orders the writes
-            } else {  // rare: commit up to the first hazard, re-evaluate the rest
-                bool pending = active;
-                for (;;) {
-                    const int first = hmask ? (__ffs(hmask) - 1) : 32;
-                    const bool commit = acc && lane < first;
-                    if (commit) {
-                        atomicXor(state + wa, (m ^ nw) << sa);
-                        ++my_acc;
-                        if (PACKCNT) {
-                            dpack += (1u << (8 * nw)) - (1u << (8 * m));
-                        } else {
-                            count_move(a, m, nw);
-                        }
-                    }
-                    pending = pending && lane >= first;
-                    if (!SMEM) __threadfence_block();
-                    __syncwarp();
-                    if (first == 32) break;
-                    ++n_extra;
-                    m = (state_load<SMEM>(state + wa) >> sa) & P::VM;
-                    nw = noise ? (meta >> 8) : ((state_load<SMEM>(state + wn) >> sn) & P::VM);
-                    if (THR4) th = sp_lds(thr4_saddr + ((((meta & 1u) << 4) | (m << 2) | nw) << 2));
-                    else if (THR_SMEM) th = thr[(noise ? MM : 0) + m * M + nw];
-                    else th = __ldg(thr + (noise ? MM : 0) + m * M + nw);
-                    acc = pending && sp_thr_accept(r3, th);
-                    const uint32_t wmask = __ballot_sync(FULL, acc);
-                    hmask = __ballot_sync(FULL, pending && (dep & wmask) != 0u);
+                // without a real writer nothing can be flagged; should it ever happen, everything is exact
+                uint32_t g = w0 == 0xffffffffu ? 0xffffffffu : w0 + 1u;
+                if (!any_multi && f != 0xffffffffu && f > g) g = f;
+                settle_plain();
+                const uint32_t v = vbase + (uint32_t)lane;
+                if (d.acc && v < g) {
+                    atomicXor(state + d.wa, xmask_of(d));
+                    book(s, d);
+                }
+                pending = pending && v >= g;
+                settle_plain();
+                ++n_extra;
+                reevaluate(s, pending, d);  // the remaining positions against the updated state
+                if (RING) coop_sync();      // all reads before anybody writes
+                const uint32_t old = write(d);
+                settle_writes(d, old, multi);
+                bad = changed(s, pending, d);
+                if (!coop_any(bad || multi)) {
+                    if (d.acc) book(s, d);
+                    return;
                 }
             }
         };
 
         // ---- the chain: output interval by output interval ----
-        // Steps are numbered through the whole chain (RING: step s belongs to warp s mod W).  Inside an
-        // interval of K events the steps are full except the last one, so a warp only needs a counter for
-        // its own steps; the software pipeline (depth 2 over the warp's own steps) restarts per interval.
-        uint32_t s_mod = 0;   // steps of the chain so far, mod W
-        uint32_t gsteps = 0;  // steps of the chain so far
-        uint64_t E = 0;       // events of the chain so far
+        // Inside an interval of K events the 32-event steps are full except the last one; step t of the interval
+        // belongs to warp t mod W, super-step u holds the steps u W ... u W + W - 1.  Every warp runs all the
+        // super-steps of the interval (its step may be partial or not exist at the interval's end: nb < 32), the
+        // software pipeline over the warp's own steps (depth 2) restarts per interval.
+        uint64_t E = 0;  // events of the chain so far
         int k = 1;
         if (role == 0) snapshot(0);  // k = 0: the initial state
         while (k < T && kcounts[k - 1] == 0) {  // leading empty intervals repeat the initial state
             if (role == 0) snapshot(k);
             ++k;
         }
+        coop_sync();
         int64_t K_left = k < T ? kcounts[k - 1] : 0;
         while (k < T) {
             // at most 2^30 steps at a time (32-bit step counters); the interval ends with the last chunk
@@ -540,19 +572,22 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 while (k_next < T && kcounts[k_next - 1] == 0) ++k_next;
             }
             const int nsteps = (int)((Kc + 31) >> 5);
-            const int tail = (int)(Kc - 32 * (int64_t)(nsteps - 1));        // events of the last step
-            const int first = (int)((uint32_t)(role + W) - s_mod) % W;        // first own step of this chunk
-            const int n_own = nsteps > first ? (nsteps - first + W - 1) / W : 0;
-            const bool own_last = (int)((s_mod + (uint32_t)(nsteps - 1)) % (uint32_t)W) == role;
+            const int tail = (int)(Kc - 32 * (int64_t)(nsteps - 1));  // events of the last step
+            const int n_super = (nsteps + W - 1) / W;
+            const int n_own = nsteps > role ? (nsteps - role + W - 1) / W : 0;  // n_super or n_super - 1
+            const bool own_last = (nsteps - 1) % W == role;
+            // Only the LAST super-step of a chunk can hold a partial step (the chunk's last one, `tail` events) or
+            // none at all for this warp; everywhere else the warp's step is full.
+            const bool in_last = lane < (n_own == n_super ? (own_last ? tail : 32) : 0);
             // statistics per chunk, not per step: own steps are full except the chunk's last one
             n_steps += (unsigned long long)n_own;
             n_events += 32ull * (unsigned long long)n_own - ((own_last && n_own > 0) ? (unsigned long long)(32 - tail) : 0ull);
-            if (n_own > 0) {
+            {
                 // The pipeline always runs two own steps ahead, also past the end of the chunk: the draws of a
                 // step that does not exist are valid gathers that nobody consumes (two per chunk and warp),
                 // which keeps the loop body free of prefetch conditions.
                 const uint64_t e_stride = 32ull * (uint64_t)W;
-                uint64_t e_pre = E + 32ull * (uint64_t)first;  // first event of the next step to draw
+                uint64_t e_pre = E + 32ull * (uint64_t)role;  // first event of the next step to draw
                 if (ALIAS) {
                     draw(e_pre);
                     e_pre += e_stride;
@@ -570,7 +605,10 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                     issue1(1, e_pre);
                     e_pre += e_stride;
                 }
-                int rem = n_own;  // own steps left in this chunk
+                int rem = n_super;  // super-steps left in this chunk
+                Dec dec[3];  // decisions of the step being committed and of the next one (rotating with the stage sets)
+                evaluate(0, rem != 1 || in_last, dec[0]);
+                if (RING) coop_sync();  // all reads before anybody writes
                 while (rem > 0) {
                     // blocks of at most 120 own steps (a multiple of the 3 register sets): the packed count
                     // deltas of a lane move by at most 1 per step and are folded after each block
@@ -586,28 +624,38 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                                 issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
                             }
                             e_pre += e_stride;
-                            const bool last_own = rem == 1;   // the chunk's last step, if ours, is our last one
-                            process(u, (last_own && own_last) ? tail : 32);
-                            if (last_own) {
-                                // the interval ends within the next W-1 steps: whoever owns its last step writes
-                                // the output times and needs every warp's count deltas
-                                if (ends && own_last) {
-                                    for (int q = k; q < k_next; ++q) snapshot(q);
-                                } else {
-                                    fold_counts();
-                                }
+                            issue2((u + 1) % 3);  // the next own step's neighbour, out of the entry gathered a step ago
+                            const bool active = rem != 1 || in_last;
+                            const bool active_next = rem > 2 || (rem == 2 && in_last);
+                            // write phase of this step, read phase: verify it, evaluate the next one
+                            Dec& cur = dec[u];
+                            Dec& nxt = dec[(u + 1) % 3];
+                            const uint32_t old = write(cur);
+                            bool multi;
+                            settle_writes(cur, old, multi);
+                            const bool bad = changed(u, active, cur);
+                            evaluate((u + 1) % 3, active_next, nxt);
+                            if (!coop_any(bad || multi)) {
+                                if (cur.acc) book(u, cur);
+                            } else {
+                                hazard_rounds(u, active, cur, bad, multi);
+                                evaluate((u + 1) % 3, active_next, nxt);  // the state has moved on
+                                if (RING) coop_sync();
                             }
-                            if (RING) sp_mbar_arrive(bar_mine);  // release: state + counters of this step are visible
                             --rem;
                         }
                     }
                     if (rem > 0) fold_counts();
                 }
             }
-            s_mod = (s_mod + (uint32_t)nsteps) % (uint32_t)W;
-            gsteps += (uint32_t)nsteps;
             E += (uint64_t)Kc;
             if (ends) {
+                // every warp's count deltas, then the output times k .. k_next - 1 by the chain's first warp
+                fold_counts();
+                coop_sync();
+                if (role == 0)
+                    for (int q = k; q < k_next; ++q) snapshot(q);
+                coop_sync();
                 k = k_next;
                 K_left = k < T ? kcounts[k - 1] : 0;
             }
@@ -616,15 +664,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         step_total += n_steps;
         extra_total += n_extra;
         acc_total += __reduce_add_sync(FULL, my_acc);
-        if (RING) {
-            // every warp of the ring is done with the chain; the predecessor's barrier has advanced by the
-            // number of steps it owned
-            sp_ring_sync(slot + 1, 32 * W);
-            const uint32_t pr = (uint32_t)((role + W - 1) % W);
-            pred_base += gsteps > pr ? (gsteps - pr + (uint32_t)W - 1u) / (uint32_t)W : 0u;
-        } else {
-            __syncwarp();
-        }
+        coop_sync();
+        if (!SMEM) __threadfence_block();
     }
     if (lane == 0 && A.counters) {
         atomicAdd(A.counters + 0, ev_total);
@@ -917,6 +958,11 @@ namespace {
 // kernel selection over (BITS, SMEM, GRAPH, ALIAS, RING); RING exists for shared-memory states only
 typedef void (*cnvm_kernel_t)(NativeCnvmArgs);
 
+#ifdef SP_FAST_BUILD  // development builds: only the kernels of workload H (2-bit states in shared memory, sampler table)
+cnvm_kernel_t pick_cnvm_kernel(int, bool, int, bool, bool ring) {
+    return ring ? cnvm_native_kernel<2, true, 2, false, true> : cnvm_native_kernel<2, true, 2, false, false>;
+}
+#else
 template <int BITS, bool SMEM, int GRAPH>
 cnvm_kernel_t pick_cnvm(bool alias, bool ring) {
     if (SMEM && ring) return alias ? cnvm_native_kernel<BITS, SMEM, GRAPH, true, SMEM> : cnvm_native_kernel<BITS, SMEM, GRAPH, false, SMEM>;
@@ -943,6 +989,7 @@ cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, int graph, bool alias, bool 
         default: return pick_cnvm_b<8>(smem, graph, alias, ring);
     }
 }
+#endif
 
 // Threshold tables: thr[0:MM] imitation, thr[MM:2MM] noise.
 int stage_thresholds(SpScratch& sc, const sponet_cnvm_params* p, const uint32_t** d_thr) {
@@ -1093,7 +1140,7 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     SP_CUDA(sp_device_limits(dev, &prop));
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
-    const size_t fixed = bits <= 2 ? 128 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
+    const size_t fixed = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
     const size_t per_slot_min = cnt_bytes + 16 * 8;              // counters + (possible) mbarrier ring
     bool smem_state = !o->force_global_state;
@@ -1101,10 +1148,8 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     if (smem_state) {
         if (smem_max > fixed + 64) slots = (int)std::min<size_t>(16, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
         if (slots < 1) smem_state = false;
-        // A chain that fills an SM's shared memory alone runs as one ring of 8 warps whose commits are
-        // serialized; with enough chains to give every SM 16 independent ones, chain states in global
-        // memory (L2 / HBM gathers) win: 3.4e10 vs 2.8e10 events/s on the N = 1e6 workload.
-        if (slots == 1 && num_chains >= (int64_t)16 * prop.multiProcessorCount) smem_state = false;
+        // (A chain that fills an SM's shared memory alone is served by all 16 warps of the CTA, 512 events per
+        // super-step; states in global memory are the fallback for chains beyond 227 KB only.)
     }
     int wpc = 1;  // warps per chain
     if (smem_state) {
@@ -1112,13 +1157,13 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         const int64_t need = (num_chains + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
         slots = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
         // Large chains leave only a few warps per SM: give each chain several warps that take its steps
-        // round-robin (RING).  At most 512 threads per CTA (keeps 118 registers), at most 8 warps a chain.
+        // (COOP: super-steps of 32 * wpc events).  At most 512 threads per CTA (128 registers each).
         const int max_warps = SP_RING_MAX_THREADS / 32;
         if (o->warps_per_chain > 0) {
             wpc = std::min(o->warps_per_chain, 16);
         } else {
             if (slots == 9 && chain_bytes >= 8192) slots = 8;  // 8 x 2 warps beat 9 x 1 (A/B on H)
-            if (slots <= 8) wpc = std::min(8, max_warps / slots);
+            if (slots <= 8) wpc = std::min(16, max_warps / slots);
         }
         while (wpc > 1 && slots * wpc > max_warps) --slots;  // explicit request: trade slots for warps
         if (slots < 1) slots = 1;
@@ -1132,16 +1177,6 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     A.warps_per_chain = wpc;
     size_t smem_bytes = fixed + (pair ? (size_t)warps * 8 : 0) + (size_t)slots * cnt_bytes +
                         (smem_state ? (size_t)slots * chain_bytes : 0);
-    // Per-warp Bloom filter for the dependency pre-check, carved from the shared memory the chain states
-    // leave over (a chain is never given up for it).  ~N/4 bits are plenty: a step flags a lane with
-    // probability ~ 32*25/bits, against a true overlap rate of ~1000/N.  Below 1 Kbit it is not worth it.
-    {
-        const size_t spare = smem_max > smem_bytes + 64 ? (smem_max - smem_bytes - 64) / warps : 0;
-        size_t words = std::min<size_t>(spare / 4, 2048);
-        words = std::min<size_t>(words, std::max<size_t>(32, (size_t)n / 128));
-        A.bloom_words = words >= 32 ? (int32_t)words : 0;
-        smem_bytes += (size_t)A.bloom_words * 4 * warps;
-    }
     A.warps_per_cta = warps;
     const int threads = warps * 32;
     const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
