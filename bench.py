@@ -276,12 +276,50 @@ def run_reference_arm(args) -> None:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def numba_baseline_subprocess():
+    """cpu_baseline of the GPU line: the unmodified numba reference in a SUBPROCESS (its process pool forks; this
+    process holds a CUDA context), one bounded step.  Returns the dict of that run's `cpu_baseline`, or a reason."""
+    ok, why = numba_reference_available()
+    if not ok:
+        return {"unavailable": why}
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=900, env=env)
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def sharded_equals_single(params, x0, graph, struct, world: int, rank: int) -> bool:
+    """Self-check before the timed region: a small ensemble through the REAL (distributed) public API -- seed
+    broadcast, runs split over the ranks, all-gather -- equals the same ensemble computed by ONE launch on this
+    GPU, bit for bit.  At N = 1 the sharding is emulated by two launches over complementary run ranges."""
+    from sponet_b200 import OpinionShares, engine, sample_many_runs
+
+    R, T, t_max = 96, 6, 0.5
+    t_eval = np.linspace(0, t_max, T)
+    spec = (np.arange(3, dtype=np.int32), 1.0)
+    _, c_api = sample_many_runs(params, x0, t_max, T, R, collective_variable=OpinionShares(3), rng=np.random.default_rng(5))
+    seed = engine.draw_seed(np.random.default_rng(5))  # the key sample_many_runs drew (rank 0's under torch.distributed)
+    _, one = engine.run_native("cnvm", graph, N_AGENTS, struct, x0[None, :], t_eval, seed, R, 0, R, cv_spec=spec, want_cv=True)
+    ok = c_api.shape == (R, T, 3) and np.array_equal(c_api, one[0])
+    if world == 1:
+        _, lo = engine.run_native("cnvm", graph, N_AGENTS, struct, x0[None, :], t_eval, seed, R, 0, 40, cv_spec=spec, want_cv=True)
+        _, hi = engine.run_native("cnvm", graph, N_AGENTS, struct, x0[None, :], t_eval, seed, R, 40, R, cv_spec=spec, want_cv=True)
+        ok = ok and np.array_equal(np.concatenate([lo[0], hi[0]]), one[0])
+    return bool(ok)
+
+
 def run_gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
 
     from sponet_b200 import CNVM, OpinionShares, engine, sample_many_runs, workloads
-    from sponet_b200 import multiprocessing as smp
+    from sponet_b200.multiprocessing import _split_runs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -303,14 +341,17 @@ def run_gpu_arm(args) -> None:
     t_eval = np.linspace(0, T_MAX, NUM_T)
     spec = (np.arange(3, dtype=np.int32), 1.0)
     d_x0 = torch.as_tensor(x0[None, :], device="cuda")
-    R, R_total = RUNS_PER_GPU, RUNS_PER_GPU * world
-    rb, re = rank * R, (rank + 1) * R
+    strong = args.scaling == "strong"
+    R_total = RUNS_PER_GPU if strong else RUNS_PER_GPU * world  # strong: SURVEY.md 8(d) H has 1e4 realizations in total
+    bounds = np.concatenate(([0], np.cumsum(_split_runs(R_total, world))))
+    rb, re = int(bounds[rank]), int(bounds[rank + 1])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step(seed, counters=None):
         return engine.run_native("cnvm", graph, N_AGENTS, struct, d_x0, t_eval, seed, R_total, rb, re,
                                  cv_spec=spec, want_cv=True, counters=counters)
 
+    check = sharded_equals_single(params, x0, graph, struct, world, rank)
     # the sampler starts before the warm-up so that the timed steps follow the warm-up without an idle gap
     # (an idle B200 drops its clocks within ~100 ms and the next launch pays the ramp); only the samples
     # taken inside the timed region are reported
@@ -336,34 +377,33 @@ def run_gpu_arm(args) -> None:
     clocks = sampler.stop(wall0, wall1)
 
     c = counters.cpu().numpy().astype(np.float64)
-    stats = torch.tensor([sum(step_ms), c[0], c[1]], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([sum(step_ms), c[0], c[1], float(check)], dtype=torch.float64, device="cuda")
     tmax = stats[:1].clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     total_ms = float(tmax.item())
     events, accepted = float(stats[1].item()), float(stats[2].item())
+    check_all = float(stats[3].item()) == float(world)
     value = events / (total_ms * 1e-3)
 
-    # ---- e2e: public API, host buffers in, host array out ----
+    # ---- e2e: the public API with host buffers in and a host array out, exactly as a user calls it.  Under
+    # torch.distributed that is the real sharded path: seed broadcast, this rank's share of the runs, NCCL
+    # all-gather of the per-rank slabs, device-to-host copy of the full [R_total, T, 3] array on every rank.
     cv = OpinionShares(3)
     rng = np.random.default_rng(7)
-    if world > 1:
-        # each rank drives its own 1e4 runs through the public API (no gather: weak scaling)
-        smp_dist = smp._dist
-        smp._dist = lambda: (0, 1)
     e2e_steps = max(1, min(args.steps, 5))
-    sample_many_runs(params, x0, T_MAX, NUM_T, R, collective_variable=cv, rng=rng)  # warm (graph upload, caches)
+    sample_many_runs(params, x0, T_MAX, NUM_T, R_total, collective_variable=cv, rng=rng)  # warm (graph upload, caches)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _, x = sample_many_runs(params, x0, T_MAX, NUM_T, R, collective_variable=cv, rng=rng)
+        _, x = sample_many_runs(params, x0, T_MAX, NUM_T, R_total, collective_variable=cv, rng=rng)
     torch.cuda.synchronize()
     e2e_sec = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
     if world > 1:
-        smp._dist = smp_dist
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    assert x.shape == (R_total, NUM_T, 3)
     e2e_events = events / max(args.steps, 1) * e2e_steps  # same expected work per step (Poisson counts)
     e2e_value = e2e_events / float(e2e_t.item())
     h2d = int(x0.nbytes + t_eval.nbytes + 2 * 9 * 4 + 3 * 4)
@@ -377,17 +417,22 @@ def run_gpu_arm(args) -> None:
         peak, peak_src = measured_peaks()
         per_gpu_events_per_s = value / world
         achieved = per_gpu_events_per_s * bytes_per_event / 1e9
+        workload = WORKLOAD if not strong else WORKLOAD.replace("1e4 realizations per GPU", "1e4 realizations in total (strong scaling)")
         line = {
             "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8 (2-bit packed states, u32 Philox draws)",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8 (2-bit packed states, u32 Philox draws)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"runs sharded over {world} GPU(s), no collective",
+            "config": {"workload": workload,
+                       "parallelism": f"runs sharded over {world} GPU(s); value: no collective in the timed region; e2e: "
+                                      + ("seed broadcast + NCCL all-gather of the per-rank CV slabs" if world > 1 else "single GPU"),
                        "l2": "flushed between timed steps (256 MiB write)", "events_per_step_per_gpu": events / max(args.steps, 1) / world,
                        "accepted_fraction": p_acc},
             "clocks": clocks,
+            "sharded_equals_single": check_all,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "sponet_b200.sample_many_runs(params, x_init, 100.0, 101, 10000, collective_variable=OpinionShares(3))",
+                    "api": f"sponet_b200.sample_many_runs(params, x_init, 100.0, 101, {R_total}, collective_variable=OpinionShares(3))"
+                           + (" under torch.distributed (unpatched: broadcast, shard, all-gather)" if world > 1 else ""),
                     "steps": e2e_steps},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -398,21 +443,182 @@ def run_gpu_arm(args) -> None:
                          # independent random access (4 per imitation event, 1 per noise event)
                          "sector_granular": {"bytes_per_event": sector_bytes, "achieved": per_gpu_events_per_s * sector_bytes / 1e9,
                                              "frac": per_gpu_events_per_s * sector_bytes / 1e9 / peak},
-                         "kernel": "cnvm_native_kernel<2,smem,nbtab,noalias,ring>",
+                         "kernel": "cnvm_native_kernel<2,smem,nbtab,noalias,coop>",
                          "ncu": {k: v for k, v in ncu_capture().items() if k.endswith("_pct") or k.startswith("warp_")},
                          "note": "chain states live in shared memory and the CSR in L2, so DRAM traffic is far below the algorithmic bytes by design; the kernel is issue/latency bound (DESIGN.md section 5)"},
             "wall_s_timed_region": wall,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
+            nb = numba_baseline_subprocess()
             cpu_reference_run(threads, threads, 1)  # warm + calibrate
             ev, sec = cpu_reference_run(threads, threads, 2)
-            runs = max(threads, int(threads * max(1.0, 12.0 / max(sec, 1e-3))))
+            runs = max(threads, int(threads * max(1.0, 8.0 / max(sec, 1e-3))))
             ev, sec = cpu_reference_run(runs, threads, 3)
-            line["cpu_baseline"] = {"value": ev / sec, "unit": "events/s", "cores": threads, "kind": "port",
-                                    "sample": f"{runs} realizations of H (t_max=100, T=101) on {threads} host threads, {sec:.1f} s"}
+            port = {"value": ev / sec, "unit": "events/s", "cores": threads, "kind": "port",
+                    "sample": f"{runs} realizations of H (t_max=100, T=101) on {threads} host threads, {sec:.1f} s"}
+            if "value" in nb:
+                line["cpu_baseline"] = nb
+                line["cpu_baseline_port"] = port
+            else:  # the numba reference could not run on this box: the C port of its loops stands in
+                port["numba_unavailable"] = nb.get("unavailable")
+                line["cpu_baseline"] = port
+        if world == 1 and not args.no_configs:
+            try:
+                line["configs"] = other_configs(peak)
+            except Exception as e:  # the headline line must not depend on the side measurements
+                line["configs"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     del keep
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_configs(peak_gbs: float) -> list:
+    """The other single-GPU BASELINE.json configurations, measured in the same run (device-timed, best of 3 after a
+    warm-up, inputs resident), each with its algorithmic bytes per event, the fraction of the HBM
+    roofline and the C port of the reference loop on this box's host threads beside it.
+      2: CNVM M=3, ER N=1e4, 1e4 realizations, 100 output times (t_max = 10)
+      3: CNTM on Barabasi-Albert N=1e5 m=5, 1e4 realizations, t_max = 20, 101 output times
+      4: SIS-as-CNVM on Watts-Strogatz N=1e6 (this GPU's share: 2368 realizations, t_max = 1)"""
+    import oracle  # CPU baseline legs only
+    from sponet_b200 import CNTM, CNVM, workloads
+
+    threads = host_threads()
+    out = []
+
+    def entry(name, kernel, g_rate, events, accepted, bytes_fn, cpu):
+        p_acc = accepted / max(events, 1.0)
+        bpe = bytes_fn(p_acc)
+        out.append({"config": name, "kernel": kernel, "events_per_s": g_rate, "algorithmic_bytes_per_event": bpe,
+                    "roofline_frac": g_rate * bpe / 1e9 / peak_gbs, "cpu_port_events_per_s": cpu[0], "cpu_threads": threads,
+                    "cpu_sample": f"{cpu[1]} runs, {cpu[2]:.1f} s"})
+
+    # config 2
+    params, x0, rate = workloads.headline_cnvm(10_000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    t_eval = np.linspace(0, 10.0, 100)
+    spec = (np.arange(3, dtype=np.int32), 1.0)
+    g, ev, acc = _gpu_rate("cnvm", model, struct, model._graph(), 10_000, x0, t_eval, 10_000, spec)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    cpu = _cpu_rate("cnvm", x0, t_eval, 3, threads, target_s=3.0, row_ptr=rp, col=col, r_imit=params.r_imit,
+                    r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise, degree_alpha=np.ones(10_000))
+    pn = params.r_noise * 10_000 / rate
+    entry("2: CNVM M=3 ER N=1e4 <d>=10, 1e4 realizations, 100 outputs (t_max=10)", "cnvm_native_kernel<2,smem,nbtab,noalias>",
+          g, ev, acc, lambda pa: (1 - pn) * 14.0 + pn + pa, cpu)
+
+    # config 3
+    params, x0, rate = workloads.ba_cntm(100_000)
+    model = CNTM(params)
+    t_eval = np.linspace(0, 20.0, 101)
+    spec2 = (np.arange(2, dtype=np.int32), 1.0)
+    g, ev, acc = _gpu_rate("cntm", model, model._struct(), model._graph(), 100_000, x0, t_eval, 10_000, spec2, reps=2, warm_s=0.0)
+    rp, col = oracle.neighbor_list_to_csr(model.neighbor_list)
+    cpu = _cpu_rate("cntm", x0, np.linspace(0, 2.0, 11), 2, threads, target_s=3.0, row_ptr=rp, col=col,
+                    next_event_rate=model.next_event_rate, noise_prob=model.noise_prob, threshold_01=0.5, threshold_10=0.5)
+    mean_deg = float(len(col)) / 100_000
+    entry("3: CNTM BA N=1e5 m=5, r=1 r~=0.2 thr 0.5/0.5, 1e4 realizations, t_max=20, 101 outputs", "cntm_native_kernel<smem>",
+          g, ev, acc, lambda pa: 1.0 + (1 - model.noise_prob) * (8.0 + 5.0 * mean_deg) + pa, cpu)
+
+    # config 4 (this GPU's share)
+    params, x0, rate = workloads.sis_ws(1_000_000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    t_eval = np.linspace(0, 1.0, 11)
+    spec1 = (np.array([1], dtype=np.int32), 1e6)
+    g, ev, acc = _gpu_rate("cnvm", model, struct, model._graph(), 1_000_000, x0, t_eval, 2368, spec1, reps=2)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    cpu = _cpu_rate("cnvm", x0, t_eval, 2, threads, target_s=3.0, row_ptr=rp, col=col, r_imit=params.r_imit,
+                    r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise, degree_alpha=np.ones(1_000_000))
+    pn = params.r_noise / (params.r_noise + params.r_imit)
+    entry("4: SIS-as-CNVM WS N=1e6 k=10 p=0.1, lambda=1 (2368 realizations, t_max=1: one GPU's sample of the 1e5)",
+          "cnvm_native_kernel<1,smem,nbtab,noalias,coop16>", g, ev, acc, lambda pa: (1 - pn) * 14.0 + pn + pa, cpu)
+    del keep
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# --workload sweep: BASELINE config 5, the parameter sweep with the moments all-reduced over the GPUs
+# ---------------------------------------------------------------------------------------------
+def run_sweep(args) -> None:
+    """256 (r, r~) points on the H graph (M = 2), `--sweep-runs` realizations per point and GPU-eighth (1e5 on the
+    8-GPU box: weak scaling in the number of runs per point), t_max = 1, 11 output times, OpinionShares moments.
+    One launch per GPU covers its share of the points; sum c / sum c^2 stay on the device and meet in ONE NCCL
+    all-reduce, which is INSIDE the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from sponet_b200 import CNVMParameters, OpinionShares, engine, sample_moments_sweep, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hp, hx0, _ = workloads.headline_cnvm(N_AGENTS)
+    grid_r = np.linspace(0.5, 2.0, 16)
+    grid_rt = np.linspace(0.005, 0.05, 16)
+    plist = [CNVMParameters(num_opinions=2, network=hp.network, r=float(r), r_tilde=float(rt)) for r in grid_r for rt in grid_rt]
+    P = len(plist)
+    x0 = (hx0 % 2).astype(np.uint8)
+    runs = max(1, int(args.sweep_runs * world / 8))
+    t_max, T = 1.0, 11
+    cv = OpinionShares(2, normalize=True)
+    ev_per_step = sum(runs * t_max * (q.r_imit + q.r_noise) * N_AGENTS for q in plist)
+    rng = np.random.default_rng(11)
+    sample_moments_sweep(plist[:8], x0, 0.1, 3, 8 * world, cv, rng=rng)  # warm (graph upload, caches)
+
+    # bit-equality of one sweep point with a stand-alone run of its parameters (small, before the timed region)
+    t_s, m_s, v_s = sample_moments_sweep(plist[:16], x0, 0.2, 3, 64, cv, rng=np.random.default_rng(3))
+    from sponet_b200 import CNVM
+    pm = CNVM(plist[5])
+    struct, keep = pm._struct()
+    seed = engine.draw_seed(np.random.default_rng(3))
+    sums = (np.zeros((1, 3, 2), dtype=np.int64), np.zeros((1, 3, 2), dtype=np.int64))
+    engine.run_native("cnvm", pm._graph(), N_AGENTS, struct, x0[None, :], t_s, seed, 64, 0, 64, cv_spec=cv._kernel_spec(N_AGENTS),
+                      sums=sums, chain_offset=5 * 64)
+    point_ok = bool(np.array_equal(sums[0][0] / 64 / N_AGENTS, m_s[5]))
+    del keep
+
+    stats_acc = {"kernel_s": 0.0, "allreduce_s": 0.0}
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        st = {}
+        t, mean, var = sample_moments_sweep(plist, x0, t_max, T, runs, cv, rng=rng, stats=st)
+        for key in stats_acc:
+            stats_acc[key] += st.get(key, 0.0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sec = time.perf_counter() - t0
+    tt = torch.tensor([sec, stats_acc["kernel_s"], stats_acc["allreduce_s"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec, ks, ars = (float(v) for v in tt.cpu())
+        value = ev_per_step * args.steps / sec
+        line = {"metric": "agent-update events/sec (CNVM parameter sweep, ER N=1e5, moments all-reduced)", "value": value,
+                "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 * sec / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (1-bit packed states), int64 moment sums",
+                "data": "synthetic",
+                "config": {"workload": f"config 5: 16 x 16 grid of (r, r~) in [0.5,2] x [0.005,0.05], M=2 on the H graph (ER N=1e5), "
+                                       f"{runs} realizations per point ({args.sweep_runs} on 8 GPUs), t_max=1, 11 output times, "
+                                       "OpinionShares moments", "points": P,
+                           "parallelism": f"points dealt to {world} GPU(s), one launch per GPU, one all-reduce of [2, {P}, {T}, 2] int64"},
+                "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": int(x0.nbytes), "d2h_bytes_per_step": int(2 * P * T * 2 * 8),
+                        "api": "sponet_b200.sample_moments_sweep(params_list, x_init, 1.0, 11, runs, OpinionShares(2, normalize=True))"},
+                "allreduce": {"seconds_per_step": ars / args.steps, "share_of_step": ars / sec if sec > 0 else 0.0,
+                              "bytes": int(2 * P * T * 2 * 8), "inside_timed_region": True},
+                "kernel_seconds_per_step": ks / args.steps,
+                "sweep_point_equals_standalone": point_ok, "gpu_launches": 2 * args.steps,
+                "sample_mean_first_last_point": [float(mean[0, -1, 1]), float(mean[-1, -1, 1])]}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -421,7 +627,7 @@ def run_gpu_arm(args) -> None:
 # --all-configs: every BASELINE.json configuration shape on one GPU next to the CPU arm
 # (writes gpurun_out/configs.json; summarised in profiles/r1_configs.md).  Not part of the default run.
 # ---------------------------------------------------------------------------------------------
-def _gpu_rate(kind, model, struct, graph, n, x0, t_eval, runs, spec, counts_init=None, reps=3):
+def _gpu_rate(kind, model, struct, graph, n, x0, t_eval, runs, spec, counts_init=None, reps=3, warm_s=0.7):
     import torch
 
     from sponet_b200 import engine
@@ -431,7 +637,7 @@ def _gpu_rate(kind, model, struct, graph, n, x0, t_eval, runs, spec, counts_init
     best = 0.0
     # warm-up: an idle B200 drops its clocks (the CPU legs run in between); keep the GPU busy for ~0.7 s first
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.7:
+    while time.perf_counter() - t0 < warm_s:
         engine.run_native(kind, graph, n, struct, d_x0, t_eval, 50, runs, 0, runs, cv_spec=spec, want_cv=True,
                           counts_init=d_c0)
         torch.cuda.synchronize()
@@ -444,9 +650,9 @@ def _gpu_rate(kind, model, struct, graph, n, x0, t_eval, runs, spec, counts_init
                           counters=counters, counts_init=d_c0)
         e1.record()
         torch.cuda.synchronize()
-        ev = float(counters[0].item())
+        ev, acc = float(counters[0].item()), float(counters[1].item())
         best = max(best, ev / (e0.elapsed_time(e1) * 1e-3))
-    return best, ev
+    return best, ev, acc
 
 
 def _cpu_rate(model_name, x0, t_eval, M, threads, target_s=8.0, **kw):
@@ -479,9 +685,9 @@ def run_all_configs():
     t_eval = np.linspace(0, 100.0, 101)
     spec = (np.arange(2, dtype=np.int32), 1.0)
     c0 = np.bincount(x0, minlength=2).astype(np.int64)[None, :]
-    g, _ = _gpu_rate("cnvm_counts", model, struct, None, 1000, None, t_eval, 100_000, spec, counts_init=c0)
-    g1k, _ = _gpu_rate("cnvm_counts", model, struct, None, 1000, None, t_eval, 1000, spec, counts_init=c0)
-    ga, _ = _gpu_rate("cnvm", model, struct, None, 1000, x0, t_eval, 100_000, spec)
+    g, _, _ = _gpu_rate("cnvm_counts", model, struct, None, 1000, None, t_eval, 100_000, spec, counts_init=c0)
+    g1k, _, _ = _gpu_rate("cnvm_counts", model, struct, None, 1000, None, t_eval, 1000, spec, counts_init=c0)
+    ga, _, _ = _gpu_rate("cnvm", model, struct, None, 1000, x0, t_eval, 100_000, spec)
     c, runs, sec = _cpu_rate("cnvm_complete", x0, t_eval, 2, threads, r_imit=params.r_imit, r_noise=params.r_noise,
                             prob_imit=params.prob_imit, prob_noise=params.prob_noise, degree_alpha=model.degree_alpha)
     out.append(dict(config="1: CNVM M=2 complete N=1000, t_max=100, T=101", gpu_events_per_s=g,
@@ -494,7 +700,7 @@ def run_all_configs():
     struct, keep = model._struct()
     t_eval = np.linspace(0, 10.0, 100)
     spec = (np.arange(3, dtype=np.int32), 1.0)
-    g, _ = _gpu_rate("cnvm", model, struct, model._graph(), 10_000, x0, t_eval, 10_000, spec)
+    g, _, _ = _gpu_rate("cnvm", model, struct, model._graph(), 10_000, x0, t_eval, 10_000, spec)
     rp, col = oracle.neighbor_list_to_csr(params.network)
     c, runs, sec = _cpu_rate("cnvm", x0, t_eval, 3, threads, row_ptr=rp, col=col, r_imit=params.r_imit,
                             r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise,
@@ -507,7 +713,7 @@ def run_all_configs():
     model = CNTM(params)
     t_eval = np.linspace(0, 2.0, 11)
     spec = (np.arange(2, dtype=np.int32), 1.0)
-    g, _ = _gpu_rate("cntm", model, model._struct(), model._graph(), 100_000, x0, t_eval, 10_000, spec)
+    g, _, _ = _gpu_rate("cntm", model, model._struct(), model._graph(), 100_000, x0, t_eval, 10_000, spec)
     rp, col = oracle.neighbor_list_to_csr(model.neighbor_list)
     c, runs, sec = _cpu_rate("cntm", x0, t_eval, 2, threads, row_ptr=rp, col=col, next_event_rate=model.next_event_rate,
                             noise_prob=model.noise_prob, threshold_01=0.5, threshold_10=0.5)
@@ -520,7 +726,7 @@ def run_all_configs():
     struct, keep = model._struct()
     t_eval = np.linspace(0, 1.0, 11)
     spec = (np.array([1], dtype=np.int32), 1e6)
-    g, _ = _gpu_rate("cnvm", model, struct, model._graph(), 1_000_000, x0, t_eval, 2368, spec)
+    g, _, _ = _gpu_rate("cnvm", model, struct, model._graph(), 1_000_000, x0, t_eval, 2368, spec)
     rp, col = oracle.neighbor_list_to_csr(params.network)
     c, runs, sec = _cpu_rate("cnvm", x0, t_eval, 2, threads, target_s=6.0, row_ptr=rp, col=col, r_imit=params.r_imit,
                             r_noise=params.r_noise, prob_imit=params.prob_imit, prob_noise=params.prob_noise,
@@ -559,6 +765,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side measurements of configs 2-4")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 1e4 realizations per GPU; strong: 1e4 realizations in total (SURVEY.md 8(d))")
+    ap.add_argument("--workload", default="H", choices=["H", "sweep"], help="sweep: BASELINE config 5 (moments all-reduced)")
+    ap.add_argument("--sweep-runs", type=int, default=100_000, help="realizations per sweep point on 8 GPUs (scaled by N/8)")
     ap.add_argument("--all-configs", action="store_true", help="measure every BASELINE config shape (one GPU)")
     args = ap.parse_args()
     if args.all_configs:
@@ -572,6 +783,9 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", port,
                                    os.path.abspath(__file__), *sys.argv[1:]])
+    if args.workload == "sweep":
+        run_sweep(args)
+        return
     run_gpu_arm(args)
 
 

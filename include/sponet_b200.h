@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPONET_ABI_VERSION 2
+#define SPONET_ABI_VERSION 3
 
 enum {
     SPONET_OK = 0,
@@ -202,8 +202,22 @@ typedef struct {
      * overriding the in-kernel Poisson(dt / next_event_rate) sampler (tests, host-side schedules) */
     const int64_t* event_counts;
     int32_t force_global_state; /* debug/tests: keep chain state in global memory                   */
-    int32_t warps_per_chain;    /* 0 = auto, W >= 1: W warps take a chain's steps round-robin (W <= 16) */
+    int32_t warps_per_chain;    /* 0 = auto, W >= 1: the W warps of a chain execute super-steps of 32 W events */
                                 /* (CNVM agent-level kernel, shared-memory states only)             */
+    /* ---- ABI 3 ---- */
+    int32_t final_state_only;   /* out_x holds the state at the LAST output time only: [S, nrun, n] -- what a     */
+                                /* caller needs to continue the chains (estimate_steady_state, steady_state.py:64) */
+    /* In-kernel histogram of the collective variable over the runs, per initial state, output time and
+     * component: out_hist[s, k, d, b] += 1 with b = clamp((c - hist_lo) / hist_width, 0, hist_bins - 1), c the RAW
+     * integer value of component d (the count before division by the divisor).  Integer atomics like out_sum:
+     * exact, order-free, the per-GPU partial of one all-reduce.  hist_bins = 0: none.  Not available for
+     * SPONET_CV_PROPENSITIES (float valued). */
+    int32_t hist_bins;
+    int64_t hist_lo, hist_width;
+    uint64_t* out_hist;         /* [S, T, D, hist_bins], ACCUMULATED into (caller zeroes), or NULL               */
+    int64_t chain_offset;       /* added to every chain id: id = chain_offset + s * R_total + run.  A sweep sharded  */
+                                /* over GPUs by points passes first_point * R_total, so that results do not depend  */
+                                /* on the sharding                                                                  */
 } sponet_native_opts;
 
 /* counters: [0] candidate events executed, [1] accepted changes, [2] warp steps, [3] extra commit
@@ -212,7 +226,7 @@ typedef struct {
 
 /* CNVM on a network (g != NULL; replaces cnvm/model.py:239-308 + utils.py:96-135 +
  * collective_variables.py:400-405 for a batch) or on the complete graph (g == NULL, :365-433).
- *   out_x   [S, nrun, T, n] uint8 snapshots, or NULL
+ *   out_x   [S, nrun, T, n] uint8 snapshots ([S, nrun, n] with opts->final_state_only), or NULL
  *   out_cv  [S, nrun, T, D] float64, or NULL          (needs cv)
  *   out_sum, out_sumsq [S, T, D] int64 sums over runs of count and count^2 (raw counts of the
  *           selected opinions; ACCUMULATED into, caller zeroes) -- the per-GPU partials of
@@ -222,6 +236,19 @@ int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const sponet_cnvm
                     const sponet_native_opts* opts, const sponet_shares_cv* cv, uint8_t* out_x,
                     double* out_cv, int64_t* out_sum, int64_t* out_sumsq, uint64_t* counters,
                     void* cuda_stream);
+
+/* PARAMETER SWEEP (BASELINE config 5; the per-point loop a user writes around sponet/sample_moments.py:96-108):
+ * P rate sets on ONE network in ONE launch.  Point p takes the place of the initial-state index everywhere:
+ * chain id = p * R_total + run, out_cv [P, nrun, T, D], out_sum / out_sumsq / out_hist [P, T, D(, bins)],
+ * out_x [P, nrun, T, n].  params[p] may differ in r_imit, r_noise, prob_imit, prob_noise (num_opinions and
+ * degree_alpha must agree: one network, one alpha); every chain looks its acceptance table and noise
+ * probability up by its point.  x_init is [P, n], or [1, n] shared by all points (x_init_shared != 0).
+ * Point p of a sweep is bit-identical to sponet_cnvm_run with params[p] and chain_offset = p * R_total. */
+int sponet_cnvm_run_sweep(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* params,
+                          int64_t P, const uint8_t* x_init, int32_t x_init_shared, const double* t_eval,
+                          int64_t T, const sponet_native_opts* opts, const sponet_shares_cv* cv,
+                          uint8_t* out_x, double* out_cv, int64_t* out_sum, int64_t* out_sumsq,
+                          uint64_t* counters, void* cuda_stream);
 
 /* Complete graph, count-only fast path: the chain state is the M opinion counts, kept in registers
  * (valid because agents are exchangeable on the complete graph and OpinionShares only reads counts).
@@ -251,7 +278,7 @@ int sponet_native_event_counts(uint64_t seed, int64_t chain_begin, int64_t num_c
 
 /* sponet/collective_variables.py:400-405 _opinion_shares_numba: out[s, m] = sum_j w[j] [x[s,j]==m]
  * (weights NULL = 1).  x is uint8 [S, n]; out float64 [S, M].  Integer-valued weights give exact
- * results; general weights are summed in a fixed tree order (tolerance in tests/test_cv.py). */
+ * results; general weights are summed in a fixed tree order (tolerance in tests/test_gpu_api.py::test_collective_variables_known_answers). */
 int sponet_opinion_shares(const uint8_t* x, int64_t S, int64_t num_agents, int32_t num_opinions,
                           const double* weights, double* out, void* cuda_stream);
 

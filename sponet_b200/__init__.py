@@ -19,13 +19,13 @@ from .collective_variables import (
 from .engine import set_default_mode
 from .multiprocessing import sample_many_runs
 from .parameters import Parameters, load_params, save_params
-from .sample_moments import sample_moments
+from .sample_moments import sample_histogram, sample_moments, sample_moments_sweep
 from .steady_state import estimate_steady_state
 
 __all__ = [
     "CNTM", "CNTMParameters", "CNVM", "CNVMParameters", "CollectiveVariable",
     "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "Interfaces", "OpinionShares",
     "OpinionSharesByDegree", "Parameters", "Propensities", "load_params", "save_params", "sample_many_runs",
-    "sample_moments", "estimate_steady_state", "set_default_mode",
+    "sample_moments", "sample_moments_sweep", "sample_histogram", "estimate_steady_state", "set_default_mode",
 ]
 __version__ = "0.1.0"

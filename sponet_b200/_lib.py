@@ -79,6 +79,12 @@ class sponet_native_opts(C.Structure):
         ("event_counts", C.c_void_p),
         ("force_global_state", C.c_int32),
         ("warps_per_chain", C.c_int32),
+        ("final_state_only", C.c_int32),
+        ("hist_bins", C.c_int32),
+        ("hist_lo", C.c_int64),
+        ("hist_width", C.c_int64),
+        ("out_hist", C.c_void_p),
+        ("chain_offset", C.c_int64),
     ]
 
 
@@ -102,6 +108,7 @@ _SIGNATURES = {
     "sponet_cnvm_replay_all": (C.c_int, [_vp, _i64, C.POINTER(sponet_cnvm_params), _vp, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sponet_cntm_replay_all": (C.c_int, [_vp, C.POINTER(sponet_cntm_params), _vp, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sponet_cnvm_run": (C.c_int, [_vp, _i64, C.POINTER(sponet_cnvm_params), _vp, _i64, _vp, _i64, C.POINTER(sponet_native_opts), C.POINTER(sponet_shares_cv), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sponet_cnvm_run_sweep": (C.c_int, [_vp, _i64, C.POINTER(sponet_cnvm_params), _i64, _vp, _i32, _vp, _i64, C.POINTER(sponet_native_opts), C.POINTER(sponet_shares_cv), _vp, _vp, _vp, _vp, _vp, _vp]),
     "sponet_cnvm_run_complete_counts": (C.c_int, [_i64, C.POINTER(sponet_cnvm_params), _vp, _i64, _vp, _i64, C.POINTER(sponet_native_opts), C.POINTER(sponet_shares_cv), _vp, _vp, _vp, _vp, _vp]),
     "sponet_cntm_run": (C.c_int, [_vp, C.POINTER(sponet_cntm_params), _vp, _i64, _vp, _i64, C.POINTER(sponet_native_opts), C.POINTER(sponet_shares_cv), _vp, _vp, _vp, _vp, _vp, _vp]),
     "sponet_native_event_counts": (C.c_int, [_u64, _i64, _i64, _vp, _i64, _f64, _vp, _vp]),
@@ -129,7 +136,7 @@ def lib() -> C.CDLL:
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args
-            if L.sponet_abi_version() != 2:
+            if L.sponet_abi_version() != 3:
                 raise ImportError("libsponet_b200.so: ABI version mismatch, rebuild the library")
             _lib = L
     return _lib

@@ -215,6 +215,12 @@ __device__ __forceinline__ bool sp_thr_accept(uint32_t r, uint32_t thr) {
     return (r < thr) | (thr == 0xFFFFFFFFu);
 }
 
+// histogram bin of a raw integer CV value (sponet_native_opts.hist_*): clamp((c - lo) / width, 0, bins - 1)
+__device__ __forceinline__ int64_t sp_hist_bin(long long c, int64_t lo, int64_t width, int32_t bins) {
+    long long b = c >= lo ? (c - lo) / width : 0;
+    return b < (long long)bins ? b : (long long)bins - 1;
+}
+
 __device__ __forceinline__ double sp_u53(uint32_t a, uint32_t b) {
     return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * (1.0 / 9007199254740992.0);
 }

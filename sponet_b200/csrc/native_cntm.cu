@@ -20,7 +20,7 @@
 
 int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, int64_t num_chains,
                            int64_t nrun, int64_t R_total, int64_t run_begin, const double* d_t_eval,
-                           int T, double next_event_rate, int64_t* d_counts);
+                           int T, double next_event_rate, int64_t* d_counts, const double* d_state_rates);
 int sp_validate_native_common(const double* t_eval, int64_t T, const sponet_native_opts* o, int64_t S);
 int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, int64_t n);
 int sp_validate_states(const uint8_t* x, int64_t count, int M);
@@ -42,6 +42,10 @@ struct NativeCntmArgs {
     double* out_cv;
     unsigned long long* out_sum;
     unsigned long long* out_sumsq;
+    unsigned long long* out_hist;  // [S, T, D, hist_bins] or nullptr
+    int32_t hist_bins;
+    int64_t hist_lo, hist_width;
+    int32_t final_only;  // out_x holds the last output time only
     int32_t D;
     const int32_t* cv_idx;
     double cv_div;
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
             my_acc = n_events = n_steps = n_extra = 0;
             const int64_t snap = cl * (int64_t)T + k;
             if (A.ecv.kind != 0) {  // edge CV: scan the CV's graph against the on-chip state
-                if (A.out_cv || A.out_sum) {
+                if (A.out_cv || A.out_sum || A.out_hist) {
                     unsigned long long twice;
                     double p0, p1;
                     sp_edge_cv_scan<SMEM>(state, n, A.ecv, lane, twice, p0, p1);
@@ -137,15 +141,18 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                                 atomicAdd(A.out_sum + o, (unsigned long long)c);
                                 atomicAdd(A.out_sumsq + o, (unsigned long long)(c * c));
                             }
+                            if (A.out_hist) atomicAdd(A.out_hist + (j * (int64_t)T + k) * A.hist_bins + sp_hist_bin(c, A.hist_lo, A.hist_width, A.hist_bins), 1ull);
                         } else if (A.out_cv) {
                             A.out_cv[snap * 2 + 0] = (A.cv_div == 1.0) ? p0 : p0 / A.cv_div;
                             A.out_cv[snap * 2 + 1] = (A.cv_div == 1.0) ? p1 : p1 / A.cv_div;
                         }
                     }
                 }
-            } else if (A.out_cv || A.out_sum) {
+            } else if (A.out_cv || A.out_sum || A.out_hist) {
                 for (int d = lane; d < A.D; d += 32) {
                     const long long c = A.cv_idx[d] == 1 ? (long long)c1 : (long long)n - c1;
+                    if (A.out_hist)
+                        atomicAdd(A.out_hist + ((j * (int64_t)T + k) * A.D + d) * A.hist_bins + sp_hist_bin(c, A.hist_lo, A.hist_width, A.hist_bins), 1ull);
                     if (A.out_cv)
                         A.out_cv[snap * A.D + d] = (A.cv_div == 1.0) ? (double)c : (double)c / A.cv_div;
                     if (A.out_sum) {
@@ -155,8 +162,8 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
                     }
                 }
             }
-            if (A.out_x) {
-                uint8_t* dst = A.out_x + snap * (int64_t)n;
+            if (A.out_x && (!A.final_only || k == T - 1)) {
+                uint8_t* dst = A.out_x + (A.final_only ? cl : snap) * (int64_t)n;
                 for (uint32_t a = lane; a < n; a += 32)
                     dst[a] = (uint8_t)((st_load<SMEM>(state + (a >> 5)) >> (a & 31)) & 1u);
             }
@@ -464,8 +471,13 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     SP_TRY(sp_stage_cv(sc, cv, 2, &cvd, (cv && cv->kind != SPONET_CV_SHARES) ? (int64_t)g->n : 0));
     if (cvd.d_divisors)
         return sponet_fail(SPONET_ERR_UNSUPPORTED, "cntm_run: per-output divisors are not supported");
-    SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq),
-               "cntm_run: integer moment sums are not defined for Propensities");
+    SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq && !o->out_hist),
+               "cntm_run: integer moment sums / histograms are not defined for Propensities");
+    SP_REQUIRE(!o->out_hist || (o->hist_bins >= 1 && o->hist_width >= 1 && cv), "out_hist needs hist_bins >= 1, hist_width >= 1 and a cv descriptor");
+    A.final_only = o->final_state_only ? 1 : 0;
+    A.hist_bins = o->out_hist ? o->hist_bins : 0;
+    A.hist_lo = o->hist_lo;
+    A.hist_width = o->hist_width;
     A.ecv = cvd.ecv;
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
@@ -473,7 +485,7 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.S = S;
     A.nrun = nrun;
     A.R_total = o->num_runs_total;
-    A.run_begin = o->run_begin;
+    A.run_begin = o->run_begin + o->chain_offset;
     A.T = (int32_t)T;
     for (int r = 0; r < 10; ++r) {
         A.rk[2 * r] = (uint32_t)o->seed + (uint32_t)r * 0x9E3779B9u;
@@ -489,11 +501,12 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
             int64_t* d_c;
             SP_CUDA(sc.alloc((void**)&d_c, (size_t)num_chains * (T - 1) * sizeof(int64_t)));
             SP_TRY(sp_launch_event_counts(sc.stream, o->seed, 0, num_chains, nrun, o->num_runs_total,
-                                          o->run_begin, d_t, (int)T, p->next_event_rate, d_c));
+                                          o->run_begin + o->chain_offset, d_t, (int)T, p->next_event_rate, d_c, nullptr));
             A.counts = d_c;
         }
     }
-    SP_CUDA(sc.out(out_x, (size_t)num_chains * T * n, &A.out_x));
+    SP_CUDA(sc.out(out_x, (size_t)num_chains * (A.final_only ? 1 : T) * n, &A.out_x));
+    SP_CUDA(sc.out((unsigned long long*)o->out_hist, (size_t)S * T * cvd.D * (size_t)A.hist_bins, &A.out_hist, true));
     SP_CUDA(sc.out(out_cv, (size_t)num_chains * T * cvd.D, &A.out_cv));
     SP_CUDA(sc.out((unsigned long long*)out_sum, (size_t)S * T * cvd.D, &A.out_sum, true));
     SP_CUDA(sc.out((unsigned long long*)out_sumsq, (size_t)S * T * cvd.D, &A.out_sumsq, true));

@@ -28,10 +28,12 @@ struct NativeCnvmArgs {
     const int32_t* col;
     const uint2* nbtab;  // neighbour sampler table (GRAPH == 2): [n << nbtab_log2]
     int32_t nbtab_log2;
-    uint32_t noise_thr;
+    const uint32_t* noise_thr;  // [P] noise-branch threshold of the chain's parameter set
     const uint2* alias_tab;  // (threshold, alias) per agent; nullptr = uniform agent weights
-    const uint32_t* thr;  // [2*M*M]: imitation thresholds, then noise thresholds
+    const uint32_t* thr;  // [P][2*M*M]: imitation thresholds, then noise thresholds
+    int32_t param_stride;  // 0: one parameter set for all initial states; 1: parameter set j for state slot j (sweep)
     const uint8_t* x_init;
+    int64_t x_stride;      // n, or 0 when all state slots share one initial state (sweep)
     const int64_t* counts;  // [S*nrun, T-1]
     int64_t S, nrun, R_total, run_begin;
     int32_t T;
@@ -40,6 +42,10 @@ struct NativeCnvmArgs {
     double* out_cv;
     unsigned long long* out_sum;
     unsigned long long* out_sumsq;
+    unsigned long long* out_hist;  // [S, T, D, hist_bins] or nullptr
+    int32_t hist_bins;
+    int64_t hist_lo, hist_width;
+    int32_t final_only;  // out_x holds the last output time only
     int32_t D;
     const int32_t* cv_idx;
     double cv_div;
@@ -143,36 +149,30 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
     const int slots = A.warps_per_cta / W;
     const int M = A.M, MM = M * M;
     const uint32_t n = (uint32_t)A.n;
-    const uint32_t noise_thr = A.noise_thr;
 
     // shared layout: [thr] [reduction words, 4 per slot (COOP)] [counts slots*M] [states slots*words (if SMEM)]
     // thr: M <= 4 -> 32 (threshold, packed count delta of the move m -> nw) pairs indexed (noise << 4 | m << 2 | nw),
     //      one 8-byte load per event; M <= 16 -> 2*MM thresholds
     uint32_t* sp = smem;
-    const uint32_t* thr = A.thr;
-    uint32_t thr4_saddr = (uint32_t)__cvta_generic_to_shared(smem);  // THR4: the padded table sits first
-    asm volatile("" : "+r"(thr4_saddr));  // keep it in a register (ptxas re-derives it from SR_CgaCtaId per step otherwise)
+    const uint32_t* thr = A.thr;  // (re-pointed per chain: the chain's parameter set, staged in shared memory)
+    uint32_t* thr_stage = sp;     // this chain slot's copy of the table
+    uint32_t thr4_saddr = 0;      // THR4: its shared-window address
     if (THR4) {
-        for (int i = threadIdx.x; i < 32; i += blockDim.x) {
-            const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
-            sp[2 * i] = (m < M && w < M) ? A.thr[nz * MM + m * M + w] : 0u;
-            sp[2 * i + 1] = (1u << (8 * w)) - (1u << (8 * m));  // +1 in byte w, -1 in byte m (see fold_counts)
-        }
-        thr = sp;
-        sp += 64;
+        thr_stage = sp + (size_t)slot * 64;
+        thr4_saddr = (uint32_t)__cvta_generic_to_shared(thr_stage);
+        asm volatile("" : "+r"(thr4_saddr));  // keep it in a register (ptxas re-derives it from SR_CgaCtaId per step otherwise)
+        sp += (size_t)slots * 64;
     } else if (THR_SMEM) {
-        for (int i = threadIdx.x; i < 2 * MM; i += blockDim.x) sp[i] = A.thr[i];
-        thr = sp;
-        sp += (2 * MM + 1) & ~1;
+        thr_stage = sp + (size_t)slot * ((2 * MM + 1) & ~1);
+        sp += (size_t)slots * ((2 * MM + 1) & ~1);
     }
     // COOP: three words per chain slot for the (rare) cross-warp reductions of the hazard path:
-    // [0] lowest real writer, [1] lowest flagged lane (positions within the super-step), [2] "two writers met"
+    // [0] lowest real writer, [1] lowest flagged lane (positions within the super-step)
     uint32_t* red = sp + (size_t)slot * 4;
     if (RING) {
         if (role == 0 && lane == 0) {
             red[0] = 0xffffffffu;
             red[1] = 0xffffffffu;
-            red[2] = 0u;
         }
         sp += (size_t)slots * 4;
     }
@@ -191,8 +191,28 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
-        const uint8_t* x0 = A.x_init + j * (int64_t)n;
+        const uint8_t* x0 = A.x_init + j * A.x_stride;
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
+        // the chain's parameter set: noise-branch threshold, acceptance tables (staged per chain slot)
+        const int64_t pset = j * A.param_stride;
+        const uint32_t noise_thr = __ldg(A.noise_thr + pset);
+        {
+            const uint32_t* tab = A.thr + pset * (2 * MM);
+            if (THR4) {
+                // 32 (threshold, packed count delta of the move m -> nw) pairs indexed (noise << 4 | m << 2 | nw)
+                for (int i = role * 32 + lane; i < 32; i += 32 * W) {
+                    const int nz = i >> 4, m = (i >> 2) & 3, w = i & 3;
+                    thr_stage[2 * i] = (m < M && w < M) ? __ldg(tab + nz * MM + m * M + w) : 0u;
+                    thr_stage[2 * i + 1] = (1u << (8 * w)) - (1u << (8 * m));  // +1 in byte w, -1 in byte m (see fold_counts)
+                }
+                thr = thr_stage;
+            } else if (THR_SMEM) {
+                for (int i = role * 32 + lane; i < 2 * MM; i += 32 * W) thr_stage[i] = __ldg(tab + i);
+                thr = thr_stage;
+            } else {
+                thr = tab;
+            }
+        }
 
         // ---- load + pack the initial state, count opinions ----
         if (role == 0)
@@ -292,7 +312,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             my_acc = n_events = n_steps = n_extra = 0;
             const int64_t snap = cl * (int64_t)T + k;
             if (BITS == 1 && A.ecv.kind != 0) {  // edge CV: scan the CV's graph against the on-chip state
-                if (A.out_cv || A.out_sum) {
+                if (A.out_cv || A.out_sum || A.out_hist) {
                     unsigned long long twice;
                     double p0, p1;
                     sp_edge_cv_scan<SMEM>(state, n, A.ecv, lane, twice, p0, p1);
@@ -305,15 +325,18 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                                 atomicAdd(A.out_sum + o, (unsigned long long)c);
                                 atomicAdd(A.out_sumsq + o, (unsigned long long)(c * c));
                             }
+                            if (A.out_hist) atomicAdd(A.out_hist + (j * (int64_t)T + k) * A.hist_bins + sp_hist_bin(c, A.hist_lo, A.hist_width, A.hist_bins), 1ull);
                         } else if (A.out_cv) {
                             A.out_cv[snap * 2 + 0] = (A.cv_div == 1.0) ? p0 : p0 / A.cv_div;
                             A.out_cv[snap * 2 + 1] = (A.cv_div == 1.0) ? p1 : p1 / A.cv_div;
                         }
                     }
                 }
-            } else if (A.out_cv || A.out_sum) {
+            } else if (A.out_cv || A.out_sum || A.out_hist) {
                 for (int d = lane; d < A.D; d += 32) {
                     const long long c = cnt_mem[A.cv_idx[d]];
+                    if (A.out_hist)
+                        atomicAdd(A.out_hist + ((j * (int64_t)T + k) * A.D + d) * A.hist_bins + sp_hist_bin(c, A.hist_lo, A.hist_width, A.hist_bins), 1ull);
                     if (A.out_cv) {
                         const double dv = A.cv_divs ? A.cv_divs[d] : A.cv_div;
                         A.out_cv[snap * A.D + d] = (dv == 1.0) ? (double)c : (double)c / dv;
@@ -325,8 +348,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                     }
                 }
             }
-            if (A.out_x) {
-                uint8_t* dst = A.out_x + snap * (int64_t)n;
+            if (A.out_x && (!A.final_only || k == T - 1)) {
+                uint8_t* dst = A.out_x + (A.final_only ? cl : snap) * (int64_t)n;
                 for (uint32_t a = lane; a < n; a += 32)
                     dst[a] = (uint8_t)((state_load<SMEM>(state + P::word(a)) >> P::shift(a)) & P::VM);
             }
@@ -402,20 +425,19 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         // A SUPER-STEP is the 32 * W consecutive events the W warps of a chain hold (warp `role` the events
         // 32 * role ... 32 * role + 31 of it: positions v = 32 * role + lane).  It runs in two phases separated by
         // barriers of the chain's warps (a warp barrier when W = 1):
-        //   write phase   every accepting lane XORs its change into the packed state (the atomic returns the word
-        //                 it replaced)
+        //   write phase   every accepting lane swaps its change into the packed state (compare-and-swap on the
+        //                 agent's field: of several writers of one agent only the first writes, the others are
+        //                 flagged, so an agent changes at most once per phase and changes cannot cancel)
         //   read phase    every lane re-reads the two locations its decision was based on -- and, in the same
         //                 pass, reads the locations of its NEXT step and that step's acceptance threshold.  Nobody
         //                 writes during a read phase, so the next step's decision is ready when the vote on the
         //                 current one comes back, and a super-step costs one shared-memory round trip per phase.
         // The super-step is exact unless some lane read a location that an EARLIER position really changed.  Let
         // w0 be the lowest position that really changes its agent: positions <= w0 have exact inputs in any case.
-        //   * no location has two real writers (no writer got back a field other than the one it had read): the
-        //     re-reads are reliable -- a changed neighbour, or an own agent that is not what this lane left
-        //     there, flags the lane; the first position i* with stale inputs always flags itself, so with f = the
-        //     lowest flagged position, positions < max(f, w0 + 1) are exact;
-        //   * some location has several real writers: XORs may cancel and hide a change from a reader, so only
-        //     positions <= w0 are trusted.
+        // A location written in the phase holds a value different from the one everybody read, so the re-reads are
+        // reliable: a changed neighbour, an own agent that is not what this lane left there, or a lost write flags
+        // the lane.  The first position i* with stale inputs always flags itself, so with f = the lowest flagged
+        // position, positions < max(f, w0 + 1) are exact.
         // On a flag everything is rolled back (XOR is its own inverse), the exact prefix is committed for real and
         // the remaining positions start over (tools/commit_model.py checks this protocol against the sequential
         // semantics on random instances).  At N = 1e5 about 1 % of the 32-event steps are flagged.
@@ -433,9 +455,11 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         struct Dec {
             uint32_t wa, wn;    // word index of the agent / of the location imitated (own agent for a noise event)
             uint32_t sa, sn;    // bit offsets within those words
+            uint32_t word;      // the agent's packed word as read (the compare value of the write)
             uint32_t m, nw;     // opinion read, new opinion
             uint32_t delta;     // THR4: packed count delta of m -> nw
-            bool acc;
+            bool acc;           // accepted
+            bool lost;          // write phase: another lane changed this agent first, nothing was written
         };
         auto evaluate = [&](int s, bool active, Dec& d) {
             const uint32_t a = q_a[s], nbr = q_nbr[s], meta = q_meta[s];
@@ -443,7 +467,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             d.wn = P::word(nbr);
             d.sa = P::shift(a);
             d.sn = P::shift(nbr);
-            d.m = (state_load<SMEM>(state + d.wa) >> d.sa) & P::VM;
+            d.word = state_load<SMEM>(state + d.wa);
+            d.m = (d.word >> d.sa) & P::VM;
             d.nw = (meta & 1u) ? (meta >> 8) : ((state_load<SMEM>(state + d.wn) >> d.sn) & P::VM);
             uint32_t th;
             d.delta = 0;
@@ -454,10 +479,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             } else if (THR_SMEM) th = thr[((meta & 1u) ? MM : 0) + d.m * M + d.nw];
             else th = __ldg(thr + ((meta & 1u) ? MM : 0) + d.m * M + d.nw);
             d.acc = active && sp_thr_accept(q_r3[s], th);
-        };
-        // the same for the lanes still pending in a hazard round (positions >= g)
-        auto reevaluate = [&](int s, bool pending, Dec& d) {
-            evaluate(s, pending, d);
+            d.lost = false;
         };
         auto book = [&](int s, const Dec& d) {  // an accepted event m -> nw of this lane
             ++my_acc;
@@ -465,30 +487,41 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             else count_move(q_a[s], d.m, d.nw);
         };
         auto xmask_of = [&](const Dec& d) -> uint32_t { return (d.m ^ d.nw) << d.sa; };
-        // write phase of one step; returns the word replaced
-        auto write = [&](const Dec& d) -> uint32_t {
-            uint32_t old = 0;
-            if (d.acc) old = atomicXor(state + d.wa, xmask_of(d));
-            return old;
+        // Write phase of one step.  A compare-and-swap on the agent's word, retried while only OTHER agents of the
+        // word have changed: the first writer of an agent wins, a later one finds the field changed, writes nothing
+        // and is flagged (`lost`).  So an agent is written at most once per write phase and writes cannot cancel.
+        auto write = [&](Dec& d) {
+            if (d.acc && d.m != d.nw) {
+                const uint32_t x = xmask_of(d);
+                uint32_t expect = d.word;
+                for (;;) {
+                    const uint32_t old = atomicCAS(state + d.wa, expect, expect ^ x);
+                    if (old == expect) break;
+                    if (((old >> d.sa) & P::VM) != d.m) {
+                        d.lost = true;
+                        break;
+                    }
+                    expect = old;
+                }
+            }
         };
         // Between the write phase and the read phase.  Shared memory executes accesses in order: a barrier of the
         // chain's warps is enough.  In global memory (W = 1) the atomics are performed at the L2 and a load issued
-        // right behind them could overtake them: there every writer first consumes the value its atomic returned
-        // (the vote on `multi`), which it only has once the atomic has been performed.
-        auto settle_writes = [&](const Dec& d, uint32_t old, bool& multi) {
-            multi = d.acc && (((old >> d.sa) & P::VM) != d.m);  // another real writer got there first
+        // right behind them could overtake them; every writer has consumed the value its atomic returned, so all
+        // of them have been performed once the warp has voted.
+        auto settle_writes = [&](const Dec& d) {
             if (SMEM) {
                 coop_sync();
             } else {
-                multi = __any_sync(FULL, multi);
+                (void)__any_sync(FULL, d.lost);
                 __threadfence_block();
             }
         };
-        // re-reads the lane's two locations: has an input changed?
+        // re-reads the lane's two locations: has an input changed (or has the lane lost its write)?
         auto changed = [&](int s, bool pending, const Dec& d) -> bool {
-            uint32_t chk = (state_load<SMEM>(state + d.wa) >> d.sa) ^ (d.acc ? d.nw : d.m);
+            uint32_t chk = (state_load<SMEM>(state + d.wa) >> d.sa) ^ ((d.acc && !d.lost) ? d.nw : d.m);
             if (!(q_meta[s] & 1u)) chk |= (state_load<SMEM>(state + d.wn) >> d.sn) ^ d.nw;
-            return pending && (chk & P::VM) != 0u;
+            return (pending && (chk & P::VM) != 0u) || d.lost;
         };
         // rare path, plain atomics followed by loads of other lanes
         auto settle_plain = [&]() {
@@ -496,51 +529,49 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             coop_sync();
         };
         // The step in set `s` was flagged: roll back, commit the exact prefix, re-run the rest until clean.
-        auto hazard_rounds = [&](int s, bool active, Dec& d, bool bad, bool multi) {
+        auto hazard_rounds = [&](int s, bool active, Dec& d, bool bad) {
             bool pending = active;
 #pragma unroll 1
             for (;;) {
-                if (d.acc) atomicXor(state + d.wa, xmask_of(d));  // roll back
-                const uint32_t writers = __ballot_sync(FULL, d.acc && d.m != d.nw);
+                const bool writer = d.acc && d.m != d.nw;
+                if (writer && !d.lost) atomicXor(state + d.wa, xmask_of(d));  // roll back
+                const uint32_t writers = __ballot_sync(FULL, writer);
                 const uint32_t badm = __ballot_sync(FULL, bad);
-                bool any_multi = __any_sync(FULL, multi);
                 uint32_t w0 = writers ? vbase + (uint32_t)__ffs(writers) - 1u : 0xffffffffu;
                 uint32_t f = badm ? vbase + (uint32_t)__ffs(badm) - 1u : 0xffffffffu;
                 if (RING) {
                     if (lane == 0) {
                         if (writers) atomicMin(red + 0, w0);
                         if (badm) atomicMin(red + 1, f);
-                        if (any_multi) atomicOr(red + 2, 1u);
                     }
                     coop_sync();
                     w0 = red[0];
                     f = red[1];
-                    any_multi = red[2] != 0u;
                     coop_sync();
                     if (role == 0 && lane == 0) {  // (the next reduction is at least two barriers away)
                         red[0] = 0xffffffffu;
                         red[1] = 0xffffffffu;
-                        red[2] = 0u;
                     }
                 }
-                // without a real writer nothing can be flagged; should it ever happen, everything is exact
+                // positions <= w0 are exact in any case, positions below the first flagged one as well; without a
+                // real writer nothing can be flagged (should it ever happen, everything is exact)
                 uint32_t g = w0 == 0xffffffffu ? 0xffffffffu : w0 + 1u;
-                if (!any_multi && f != 0xffffffffu && f > g) g = f;
+                if (f != 0xffffffffu && f > g) g = f;
                 settle_plain();
                 const uint32_t v = vbase + (uint32_t)lane;
                 if (d.acc && v < g) {
-                    atomicXor(state + d.wa, xmask_of(d));
+                    if (writer) atomicXor(state + d.wa, xmask_of(d));
                     book(s, d);
                 }
                 pending = pending && v >= g;
                 settle_plain();
                 ++n_extra;
-                reevaluate(s, pending, d);  // the remaining positions against the updated state
-                if (RING) coop_sync();      // all reads before anybody writes
-                const uint32_t old = write(d);
-                settle_writes(d, old, multi);
+                evaluate(s, pending, d);  // the remaining positions against the updated state
+                if (RING) coop_sync();    // all reads before anybody writes
+                write(d);
+                settle_writes(d);
                 bad = changed(s, pending, d);
-                if (!coop_any(bad || multi)) {
+                if (!coop_any(bad)) {
                     if (d.acc) book(s, d);
                     return;
                 }
@@ -617,6 +648,17 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
                             if (rem == stop) break;
+                            issue2((u + 1) % 3);  // the next own step's neighbour, out of the entry gathered a step ago
+                            const bool active = rem != 1 || in_last;
+                            const bool active_next = rem > 2 || (rem == 2 && in_last);
+                            // write phase of this step, read phase: verify it, evaluate the next one
+                            Dec& cur = dec[u];
+                            Dec& nxt = dec[(u + 1) % 3];
+                            write(cur);
+                            settle_writes(cur);
+                            // The draws of the step after the next one sit in the read phase on purpose: its block
+                            // holds the shared-memory round trips (re-reads, next decision, threshold), and the
+                            // Philox rounds are independent work to issue while those are in flight.
                             if (ALIAS) {
                                 resolve((u + 2) % 3);  // two own steps ahead: agent + entry gather
                                 draw(e_pre);           // three own steps ahead: Philox + alias gather
@@ -624,21 +666,12 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                                 issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
                             }
                             e_pre += e_stride;
-                            issue2((u + 1) % 3);  // the next own step's neighbour, out of the entry gathered a step ago
-                            const bool active = rem != 1 || in_last;
-                            const bool active_next = rem > 2 || (rem == 2 && in_last);
-                            // write phase of this step, read phase: verify it, evaluate the next one
-                            Dec& cur = dec[u];
-                            Dec& nxt = dec[(u + 1) % 3];
-                            const uint32_t old = write(cur);
-                            bool multi;
-                            settle_writes(cur, old, multi);
                             const bool bad = changed(u, active, cur);
                             evaluate((u + 1) % 3, active_next, nxt);
-                            if (!coop_any(bad || multi)) {
+                            if (!coop_any(bad)) {
                                 if (cur.acc) book(u, cur);
                             } else {
-                                hazard_rounds(u, active, cur, bad, multi);
+                                hazard_rounds(u, active, cur, bad);
                                 evaluate((u + 1) % 3, active_next, nxt);  // the state has moved on
                                 if (RING) coop_sync();
                             }
@@ -690,6 +723,9 @@ struct CountsArgs {
     double* out_cv;
     unsigned long long* out_sum;
     unsigned long long* out_sumsq;
+    unsigned long long* out_hist;
+    int32_t hist_bins;
+    int64_t hist_lo, hist_width;
     int32_t D;
     const int32_t* cv_idx;
     double cv_div;
@@ -766,6 +802,8 @@ __global__ void __launch_bounds__(128) cnvm_counts_kernel(CountsArgs A) {
                     atomicAdd(A.out_sum + o, (unsigned long long)cv);
                     atomicAdd(A.out_sumsq + o, (unsigned long long)(cv * cv));
                 }
+                if (A.out_hist)
+                    atomicAdd(A.out_hist + ((j * (int64_t)A.T + k) * A.D + d) * A.hist_bins + sp_hist_bin(cv, A.hist_lo, A.hist_width, A.hist_bins), 1ull);
             }
         }
     }
@@ -816,7 +854,7 @@ __device__ int64_t native_poisson(uint64_t seed, uint64_t chain, uint64_t interv
 // chain id of local chain cl: (cl / nrun) * R_total + run_begin + cl % nrun; nrun == 0 -> chain_begin + cl
 __global__ void event_counts_kernel(uint64_t seed, int64_t chain_begin, int64_t num_chains, int64_t nrun,
                                     int64_t R_total, int64_t run_begin, const double* t_eval, int T,
-                                    double next_event_rate, int64_t* counts) {
+                                    double next_event_rate, int64_t* counts, const double* state_rates) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = T - 1;
     if (tid >= num_chains * per) return;
@@ -826,6 +864,7 @@ __global__ void event_counts_kernel(uint64_t seed, int64_t chain_begin, int64_t 
     if (nrun > 0) {
         const int64_t j = cl / nrun, i = cl - j * nrun;
         chain = (uint64_t)(j * R_total + run_begin + i);
+        if (state_rates) next_event_rate = state_rates[j];  // sweep: one rate per state slot
     } else {
         chain = (uint64_t)(chain_begin + cl);
     }
@@ -838,7 +877,7 @@ __global__ void event_counts_kernel(uint64_t seed, int64_t chain_begin, int64_t 
 // Shared with native_cntm.cu.
 int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, int64_t num_chains,
                            int64_t nrun, int64_t R_total, int64_t run_begin, const double* d_t_eval,
-                           int T, double next_event_rate, int64_t* d_counts) {
+                           int T, double next_event_rate, int64_t* d_counts, const double* d_state_rates) {
     const int64_t total = num_chains * (int64_t)(T - 1);
     if (total <= 0) return SPONET_OK;
     const int block = 128;
@@ -846,7 +885,7 @@ int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, 
     SP_REQUIRE(grid < ((int64_t)1 << 31), "too many (chain, interval) pairs for one launch");
     event_counts_kernel<<<(unsigned)grid, block, 0, st>>>(seed, chain_begin, num_chains, nrun, R_total,
                                                           run_begin, d_t_eval, T, next_event_rate,
-                                                          d_counts);
+                                                          d_counts, d_state_rates);
     SP_CUDA(cudaGetLastError());
     return SPONET_OK;
 }
@@ -991,22 +1030,27 @@ cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, int graph, bool alias, bool 
 }
 #endif
 
-// Threshold tables: thr[0:MM] imitation, thr[MM:2MM] noise.
-int stage_thresholds(SpScratch& sc, const sponet_cnvm_params* p, const uint32_t** d_thr) {
+// Threshold tables of P parameter sets: thr[p][0:MM] imitation, thr[p][MM:2MM] noise; noise-branch thresholds [P].
+int stage_thresholds(SpScratch& sc, const sponet_cnvm_params* p, int64_t P, const std::vector<double>& noise_prob,
+                     const uint32_t** d_thr, const uint32_t** d_noise) {
     const int64_t MM = (int64_t)p->num_opinions * p->num_opinions;
-    std::vector<uint32_t> h(2 * MM);
-    for (int64_t i = 0; i < MM; ++i) {
-        SP_REQUIRE(p->prob_imit[i] >= 0.0 && p->prob_imit[i] <= 1.0 && p->prob_noise[i] >= 0.0 &&
-                       p->prob_noise[i] <= 1.0,
-                   "Probabilities have to be between 0 and 1.");
-        h[i] = sp_prob_to_thr(p->prob_imit[i]);
-        h[MM + i] = sp_prob_to_thr(p->prob_noise[i]);
+    std::vector<uint32_t> h((size_t)P * 2 * MM + P);
+    for (int64_t q = 0; q < P; ++q) {
+        for (int64_t i = 0; i < MM; ++i) {
+            SP_REQUIRE(p[q].prob_imit[i] >= 0.0 && p[q].prob_imit[i] <= 1.0 && p[q].prob_noise[i] >= 0.0 &&
+                           p[q].prob_noise[i] <= 1.0,
+                       "Probabilities have to be between 0 and 1.");
+            h[q * 2 * MM + i] = sp_prob_to_thr(p[q].prob_imit[i]);
+            h[q * 2 * MM + MM + i] = sp_prob_to_thr(p[q].prob_noise[i]);
+        }
+        h[(size_t)P * 2 * MM + q] = sp_prob_to_thr(noise_prob[q]);
     }
     uint32_t* d;
-    SP_CUDA(sc.alloc((void**)&d, 2 * MM * sizeof(uint32_t)));
-    SP_CUDA(cudaMemcpyAsync(d, h.data(), 2 * MM * sizeof(uint32_t), cudaMemcpyHostToDevice, sc.stream));
+    SP_CUDA(sc.alloc((void**)&d, h.size() * sizeof(uint32_t)));
+    SP_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, sc.stream));
     SP_CUDA(cudaStreamSynchronize(sc.stream));
     *d_thr = d;
+    *d_noise = d + (size_t)P * 2 * MM;
     return SPONET_OK;
 }
 
@@ -1023,17 +1067,24 @@ extern "C" int sponet_native_event_counts(uint64_t seed, int64_t chain_begin, in
     SP_CUDA(sc.in(t_eval, (size_t)T, &d_t));
     SP_CUDA(sc.out(counts, (size_t)(num_chains * (T - 1)), &d_c));
     SP_TRY(sp_launch_event_counts(sc.stream, seed, chain_begin, num_chains, 0, 0, 0, d_t, (int)T,
-                                  next_event_rate, d_c));
+                                  next_event_rate, d_c, nullptr));
     SP_CUDA(sc.finish());
     return SPONET_OK;
 }
 
-extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* p,
-                               const uint8_t* x_init, int64_t S, const double* t_eval, int64_t T,
-                               const sponet_native_opts* o, const sponet_shares_cv* cv, uint8_t* out_x,
-                               double* out_cv, int64_t* out_sum, int64_t* out_sumsq, uint64_t* counters,
-                               void* cuda_stream) {
-    SP_REQUIRE(p && p->prob_imit && p->prob_noise && p->degree_alpha && x_init, "cnvm_run: null pointer");
+// Shared implementation of sponet_cnvm_run (P = 1: one parameter set for all S initial states) and
+// sponet_cnvm_run_sweep (sweep: S = P state slots, slot j runs parameter set j; x_shared: one initial state).
+static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* p, int64_t P,
+                         bool sweep, const uint8_t* x_init, bool x_shared, int64_t S, const double* t_eval,
+                         int64_t T, const sponet_native_opts* o, const sponet_shares_cv* cv, uint8_t* out_x,
+                         double* out_cv, int64_t* out_sum, int64_t* out_sumsq, uint64_t* counters,
+                         void* cuda_stream) {
+    SP_REQUIRE(p && x_init && P >= 1, "cnvm_run: null pointer");
+    for (int64_t q = 0; q < P; ++q) {
+        SP_REQUIRE(p[q].prob_imit && p[q].prob_noise && p[q].degree_alpha, "cnvm_run: null pointer in parameter set %lld", (long long)q);
+        SP_REQUIRE(p[q].num_opinions == p[0].num_opinions && p[q].degree_alpha == p[0].degree_alpha,
+                   "cnvm_run_sweep: all parameter sets must share num_opinions and degree_alpha (one network, one alpha)");
+    }
     SP_REQUIRE(num_agents >= 2 && num_agents < ((int64_t)1 << 31), "num_agents out of range");
     SP_TRY(sp_validate_native_common(t_eval, T, o, S));
     const int M = p->num_opinions;
@@ -1054,17 +1105,19 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     const int64_t num_chains = S * nrun;
     if (num_chains == 0) return SPONET_OK;
 
-    SP_TRY(sp_validate_states(x_init, S * n, M));
+    SP_TRY(sp_validate_states(x_init, (x_shared ? 1 : S) * n, M));
+    SP_REQUIRE(!o->out_hist || (o->hist_bins >= 1 && o->hist_width >= 1 && cv), "out_hist needs hist_bins >= 1, hist_width >= 1 and a cv descriptor");
 
     SpScratch sc((cudaStream_t)cuda_stream);
     NativeCnvmArgs A{};
     A.n = (int32_t)n;
     A.M = M;
-    double next_event_rate, noise_probability;
+    std::vector<double> rates((size_t)P), noise_prob((size_t)P);
+    for (int64_t q = 0; q < P; ++q)
+        SP_TRY(sponet_cnvm_event_rates(g ? p->degree_alpha : nullptr, n, g ? 0.0 : p->degree_alpha[0], p[q].r_imit,
+                                       p[q].r_noise, &rates[q], &noise_prob[q]));
     bool uniform = true;
     if (g) {
-        SP_TRY(sponet_cnvm_event_rates(p->degree_alpha, n, 0.0, p->r_imit, p->r_noise, &next_event_rate,
-                                       &noise_probability));
         for (int64_t i = 1; i < n && uniform; ++i) uniform = (p->degree_alpha[i] == p->degree_alpha[0]);
         if (!uniform) {
             std::vector<double> prob(n);
@@ -1082,12 +1135,10 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         A.col = g->d_col;
         A.nbtab = g->d_nbtab;
         A.nbtab_log2 = g->nbtab_log2;
-    } else {
-        SP_TRY(sponet_cnvm_event_rates(nullptr, n, p->degree_alpha[0], p->r_imit, p->r_noise,
-                                       &next_event_rate, &noise_probability));
     }
-    A.noise_thr = sp_prob_to_thr(noise_probability);
-    SP_TRY(stage_thresholds(sc, p, &A.thr));
+    SP_TRY(stage_thresholds(sc, p, P, noise_prob, &A.thr, &A.noise_thr));
+    A.param_stride = sweep ? 1 : 0;
+    A.x_stride = x_shared ? 0 : n;
     SpCvDev cvd;
     SP_TRY(sp_stage_cv(sc, cv, M, &cvd, n));
     A.D = cvd.D;
@@ -1096,13 +1147,17 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     A.cv_divs = cvd.d_divisors;
     A.cw = cvd.d_cw;
     A.ecv = cvd.ecv;
-    SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq),
-               "cnvm_run: integer moment sums are not defined for Propensities");
+    SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq && !o->out_hist),
+               "cnvm_run: integer moment sums / histograms are not defined for Propensities");
     A.cnt_stride = cvd.num_classes * M;
+    A.final_only = o->final_state_only ? 1 : 0;
+    A.hist_bins = o->out_hist ? o->hist_bins : 0;
+    A.hist_lo = o->hist_lo;
+    A.hist_width = o->hist_width;
     A.S = S;
     A.nrun = nrun;
     A.R_total = o->num_runs_total;
-    A.run_begin = o->run_begin;
+    A.run_begin = o->run_begin + o->chain_offset;
     A.T = (int32_t)T;
     A.seed = o->seed;
     for (int r = 0; r < 10; ++r) {
@@ -1110,7 +1165,7 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         A.rk[2 * r + 1] = (uint32_t)(o->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
 
-    SP_CUDA(sc.in(x_init, (size_t)S * n, &A.x_init));
+    SP_CUDA(sc.in(x_init, (size_t)(x_shared ? 1 : S) * n, &A.x_init));
     const double* d_t;
     SP_CUDA(sc.in(t_eval, (size_t)T, &d_t));
     // interval schedule
@@ -1120,12 +1175,21 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
         } else {
             int64_t* d_c;
             SP_CUDA(sc.alloc((void**)&d_c, (size_t)num_chains * (T - 1) * sizeof(int64_t)));
+            const double* d_rates = nullptr;
+            if (sweep) {  // one event rate per state slot
+                double* d_r;
+                SP_CUDA(sc.alloc((void**)&d_r, (size_t)P * sizeof(double)));
+                SP_CUDA(cudaMemcpyAsync(d_r, rates.data(), (size_t)P * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
+                SP_CUDA(cudaStreamSynchronize(sc.stream));
+                d_rates = d_r;
+            }
             SP_TRY(sp_launch_event_counts(sc.stream, o->seed, 0, num_chains, nrun, o->num_runs_total,
-                                          o->run_begin, d_t, (int)T, next_event_rate, d_c));
+                                          o->run_begin + o->chain_offset, d_t, (int)T, rates[0], d_c, d_rates));
             A.counts = d_c;
         }
     }
-    SP_CUDA(sc.out(out_x, (size_t)num_chains * T * n, &A.out_x));
+    SP_CUDA(sc.out(out_x, (size_t)num_chains * (A.final_only ? 1 : T) * n, &A.out_x));
+    SP_CUDA(sc.out((unsigned long long*)o->out_hist, (size_t)S * T * cvd.D * (size_t)(A.hist_bins > 0 ? A.hist_bins : 0), &A.out_hist, true));
     SP_CUDA(sc.out(out_cv, (size_t)num_chains * T * cvd.D, &A.out_cv));
     SP_CUDA(sc.out((unsigned long long*)out_sum, (size_t)S * T * cvd.D, &A.out_sum, true));
     SP_CUDA(sc.out((unsigned long long*)out_sumsq, (size_t)S * T * cvd.D, &A.out_sumsq, true));
@@ -1133,49 +1197,56 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
 
     // ---- launch geometry ----
     // slots = chains resident per CTA (one warp each, or a ring of warps_per_chain warps); shared memory per CTA =
-    // thresholds + [mbarriers] + counters + Bloom filters + packed states.
+    // thresholds + [reduction words] + counters + packed states.
     const int bits = M <= 2 ? 1 : M <= 4 ? 2 : M <= 16 ? 4 : 8;
     A.words = (int32_t)((n * bits + 31) / 32);
     SpDeviceLimits prop;
     SP_CUDA(sp_device_limits(dev, &prop));
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     const size_t chain_bytes = (size_t)A.words * 4;
-    const size_t fixed = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);
+    const size_t fixed = 0;
+    const size_t thr_bytes = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);  // per chain slot
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
-    const size_t per_slot_min = cnt_bytes + 16 * 8;              // counters + (possible) mbarrier ring
+    const size_t per_slot_min = cnt_bytes + 16 + thr_bytes;      // + the reduction words of a COOP chain
     bool smem_state = !o->force_global_state;
+    const int max_warps = SP_RING_MAX_THREADS / 32;
     int slots = 0;
     if (smem_state) {
-        if (smem_max > fixed + 64) slots = (int)std::min<size_t>(16, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
-        if (slots < 1) smem_state = false;
-        // (A chain that fills an SM's shared memory alone is served by all 16 warps of the CTA, 512 events per
-        // super-step; states in global memory are the fallback for chains beyond 227 KB only.)
+        if (smem_max > fixed + 64)
+            slots = (int)std::min<size_t>((size_t)max_warps, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
+        if (slots < 1) smem_state = false;  // a chain beyond 227 KB: states in global memory
     }
     int wpc = 1;  // warps per chain
     if (smem_state) {
         // no more slots than there are chains to run on this many SMs
         const int64_t need = (num_chains + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-        slots = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
-        // Large chains leave only a few warps per SM: give each chain several warps that take its steps
-        // (COOP: super-steps of 32 * wpc events).  At most 512 threads per CTA (128 registers each).
-        const int max_warps = SP_RING_MAX_THREADS / 32;
+        const int fit = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
         if (o->warps_per_chain > 0) {
-            wpc = std::min(o->warps_per_chain, 16);
+            wpc = std::min(o->warps_per_chain, max_warps);
+            slots = std::max(1, std::min(fit, max_warps / wpc));
         } else {
-            if (slots == 9 && chain_bytes >= 8192) slots = 8;  // 8 x 2 warps beat 9 x 1 (A/B on H)
-            if (slots <= 8) wpc = std::min(16, max_warps / slots);
+            // Fill the CTA with warps: of all (slots <= fit, warps per chain) the pair with the most warps, more
+            // chains on a tie (H, 512 threads: 9 chains fit, 8 x 2 warps beat 9 x 1; a chain that fills the SM's
+            // shared memory alone gets every warp of the CTA: COOP super-steps of 32 * wpc events).
+            int best = 0;
+            for (int sl = fit; sl >= 1; --sl) {
+                int w = max_warps / sl;
+                if (w > 1 && sl > 15) w = 1;  // named barriers 1..15 identify the chains of a CTA
+                if (sl * w > best) {
+                    best = sl * w;
+                    slots = sl;
+                    wpc = w;
+                }
+            }
         }
-        while (wpc > 1 && slots * wpc > max_warps) --slots;  // explicit request: trade slots for warps
-        if (slots < 1) slots = 1;
-        if (slots * wpc > max_warps) wpc = max_warps / slots;
-        if (slots > 15) wpc = 1;  // named barriers 1..15 identify the rings
+        if (wpc > 1 && slots > 15) slots = 15;
     } else {
         slots = 8;
     }
     const bool pair = wpc > 1;
     const int warps = slots * wpc;
     A.warps_per_chain = wpc;
-    size_t smem_bytes = fixed + (pair ? (size_t)warps * 8 : 0) + (size_t)slots * cnt_bytes +
+    size_t smem_bytes = fixed + (size_t)slots * thr_bytes + (pair ? (size_t)slots * 16 : 0) + (size_t)slots * cnt_bytes +
                         (smem_state ? (size_t)slots * chain_bytes : 0);
     A.warps_per_cta = warps;
     const int threads = warps * 32;
@@ -1194,6 +1265,26 @@ extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const 
     SP_CUDA(cudaGetLastError());
     SP_CUDA(sc.finish());
     return SPONET_OK;
+}
+
+extern "C" int sponet_cnvm_run(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* p,
+                               const uint8_t* x_init, int64_t S, const double* t_eval, int64_t T,
+                               const sponet_native_opts* o, const sponet_shares_cv* cv, uint8_t* out_x,
+                               double* out_cv, int64_t* out_sum, int64_t* out_sumsq, uint64_t* counters,
+                               void* cuda_stream) {
+    return cnvm_run_impl(g, num_agents, p, 1, false, x_init, false, S, t_eval, T, o, cv, out_x, out_cv, out_sum, out_sumsq,
+                         counters, cuda_stream);
+}
+
+extern "C" int sponet_cnvm_run_sweep(const sponet_graph* g, int64_t num_agents, const sponet_cnvm_params* p,
+                                     int64_t P, const uint8_t* x_init, int32_t x_init_shared,
+                                     const double* t_eval, int64_t T, const sponet_native_opts* o,
+                                     const sponet_shares_cv* cv, uint8_t* out_x, double* out_cv,
+                                     int64_t* out_sum, int64_t* out_sumsq, uint64_t* counters,
+                                     void* cuda_stream) {
+    SP_REQUIRE(P >= 1, "cnvm_run_sweep: need at least one parameter set");
+    return cnvm_run_impl(g, num_agents, p, P, true, x_init, x_init_shared != 0, P, t_eval, T, o, cv, out_x, out_cv, out_sum,
+                         out_sumsq, counters, cuda_stream);
 }
 
 extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_cnvm_params* p,
@@ -1230,7 +1321,12 @@ extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_
     SP_TRY(sponet_cnvm_event_rates(nullptr, num_agents, p->degree_alpha[0], p->r_imit, p->r_noise,
                                    &next_event_rate, &noise_probability));
     A.noise_thr = sp_prob_to_thr(noise_probability);
-    SP_TRY(stage_thresholds(sc, p, &A.thr));
+    {
+        const uint32_t* d_noise;
+        SP_TRY(stage_thresholds(sc, p, 1, std::vector<double>(1, noise_probability), &A.thr, &d_noise));
+    }
+    SP_REQUIRE(!o->out_hist || (o->hist_bins >= 1 && o->hist_width >= 1), "out_hist needs hist_bins >= 1 and hist_width >= 1");
+    SP_REQUIRE(!o->final_state_only, "count-only path: there are no agent states to return");
     SpCvDev cvd;
     SP_TRY(sp_stage_cv(sc, cv, M, &cvd, 0));
     if (cvd.d_divisors)
@@ -1241,7 +1337,7 @@ extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_
     A.S = S;
     A.nrun = nrun;
     A.R_total = o->num_runs_total;
-    A.run_begin = o->run_begin;
+    A.run_begin = o->run_begin + o->chain_offset;
     A.T = (int32_t)T;
     A.seed = o->seed;
     SP_CUDA(sc.in(counts_init, (size_t)S * M, &A.counts_init));
@@ -1254,7 +1350,7 @@ extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_
             int64_t* d_c;
             SP_CUDA(sc.alloc((void**)&d_c, (size_t)num_chains * (T - 1) * sizeof(int64_t)));
             SP_TRY(sp_launch_event_counts(sc.stream, o->seed, 0, num_chains, nrun, o->num_runs_total,
-                                          o->run_begin, d_t, (int)T, next_event_rate, d_c));
+                                          o->run_begin + o->chain_offset, d_t, (int)T, next_event_rate, d_c, nullptr));
             A.counts = d_c;
         }
     }
@@ -1262,6 +1358,10 @@ extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_
     SP_CUDA(sc.out((unsigned long long*)out_sum, (size_t)S * T * cvd.D, &A.out_sum, true));
     SP_CUDA(sc.out((unsigned long long*)out_sumsq, (size_t)S * T * cvd.D, &A.out_sumsq, true));
     SP_CUDA(sc.out((unsigned long long*)counters, SPONET_NUM_COUNTERS, &A.counters, true));
+    A.hist_bins = o->out_hist ? o->hist_bins : 0;
+    A.hist_lo = o->hist_lo;
+    A.hist_width = o->hist_width;
+    SP_CUDA(sc.out((unsigned long long*)o->out_hist, (size_t)S * T * cvd.D * (size_t)A.hist_bins, &A.out_hist, true));
     const int block = 128;
     const int64_t grid = (num_chains + block - 1) / block;
     SP_REQUIRE(grid < ((int64_t)1 << 31), "too many chains for one launch");

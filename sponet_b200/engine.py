@@ -206,9 +206,36 @@ def _alloc(shape, dtype, like):
     if like is not None and hasattr(like, "data_ptr") and like.is_cuda:
         import torch
 
-        tdt = {np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64}[dtype]
+        tdt = {np.uint8: torch.uint8, np.float64: torch.float64, np.int64: torch.int64, np.uint64: torch.uint64}[dtype]
         return torch.empty(shape, dtype=tdt, device=like.device)
     return np.empty(shape, dtype=dtype)
+
+
+class Histogram:
+    """Request for the in-kernel histogram of a CV over the runs (sponet_native_opts.hist_*): ``bins`` equal-width
+    bins over the RAW integer CV values (counts before the divisor): bin = clamp((c - lo) // width, 0, bins - 1).
+    ``out`` is the uint64 array [S, T, D, bins] the kernel ACCUMULATES into (numpy or CUDA tensor)."""
+
+    def __init__(self, bins: int, lo: int, width: int, out):
+        self.bins, self.lo, self.width, self.out = int(bins), int(lo), max(1, int(width)), out
+
+    @staticmethod
+    def for_counts(bins: int, max_count: int):
+        """(lo, width) covering raw values 0 .. max_count with ``bins`` bins."""
+        return 0, max(1, -(-(int(max_count) + 1) // int(bins)))
+
+    def edges(self, divisor: float = 1.0) -> np.ndarray:
+        """Bin edges in units of the CV (raw edges divided by the divisor); the last bin is closed on the right."""
+        return (self.lo + self.width * np.arange(self.bins + 1)) / float(divisor)
+
+
+def _native_opts(seed, num_runs_total, run_begin, run_end, event_counts, force_global_state, warps_per_chain,
+                 final_state_only, hist, chain_offset=0):
+    return _lib.sponet_native_opts(
+        seed & (2**64 - 1), num_runs_total, run_begin, run_end, _lib.ptr(event_counts), int(force_global_state),
+        int(warps_per_chain), int(final_state_only), 0 if hist is None else hist.bins, 0 if hist is None else hist.lo,
+        1 if hist is None else hist.width, None if hist is None else _lib.ptr(hist.out), int(chain_offset),
+    )
 
 
 def run_native(
@@ -231,12 +258,16 @@ def run_native(
     force_global_state: bool = False,
     counts_init=None,
     warps_per_chain: int = 0,
+    final_state_only: bool = False,
+    hist: Histogram | None = None,
+    chain_offset: int = 0,
 ):
     """One C-ABI call of the native ensemble path.
 
     kind: "cnvm" | "cnvm_counts" | "cntm".  ``x_init`` is (S, N) uint8, numpy or CUDA tensor; outputs
-    are allocated on the same side.  ``sums`` = (sum, sumsq) int64 arrays [S, T, D] accumulated into.
-    Returns (out_x or None, out_cv or None).
+    are allocated on the same side.  ``sums`` = (sum, sumsq) int64 arrays [S, T, D] accumulated into;
+    ``hist`` an in-kernel histogram request; ``final_state_only`` returns out_x as [S, nrun, N] (the state at
+    the last output time).  Returns (out_x or None, out_cv or None).
     """
     L = _lib.lib()
     t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
@@ -246,12 +277,11 @@ def run_native(
     S = like.shape[0]
     cvs, cv_keep = cv_struct(cv_spec)
     D = 0 if cv_spec is None else cv_keep.dimension
-    out_x = _alloc((S, nrun, T, num_agents), np.uint8, like) if want_x else None
+    x_shape = (S, nrun, num_agents) if final_state_only else (S, nrun, T, num_agents)
+    out_x = _alloc(x_shape, np.uint8, like) if want_x else None
     out_cv = _alloc((S, nrun, T, D), np.float64, like) if want_cv else None
-    opts = _lib.sponet_native_opts(
-        seed & (2**64 - 1), num_runs_total, run_begin, run_end, _lib.ptr(event_counts), int(force_global_state),
-        int(warps_per_chain),
-    )
+    opts = _native_opts(seed, num_runs_total, run_begin, run_end, event_counts, force_global_state, warps_per_chain,
+                        final_state_only, hist, chain_offset)
     sum_p = sumsq_p = None
     if sums is not None:
         sum_p, sumsq_p = _lib.ptr(sums[0]), _lib.ptr(sums[1])
@@ -277,6 +307,53 @@ def run_native(
         raise ValueError(kind)
     _lib.check(rc)
     return out_x, out_cv
+
+
+def run_native_sweep(
+    graph: GraphHandle | None,
+    num_agents: int,
+    model_structs: list,
+    x_init,
+    t_eval: np.ndarray,
+    seed: int,
+    num_runs_total: int,
+    run_begin: int,
+    run_end: int,
+    cv_spec=None,
+    want_cv: bool = False,
+    sums=None,
+    counters=None,
+    warps_per_chain: int = 0,
+    hist: Histogram | None = None,
+    chain_offset: int = 0,
+):
+    """sponet_cnvm_run_sweep: P parameter sets (``model_structs``: sponet_cnvm_params sharing one degree_alpha) on
+    one network in one launch; point p replaces the initial-state index in every output ([P, nrun, T, D],
+    sums [P, T, D]).  ``x_init`` is (N,) / (1, N) (shared by all points) or (P, N)."""
+    L = _lib.lib()
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    T, P = t_eval.size, len(model_structs)
+    nrun = run_end - run_begin
+    if x_init.ndim == 1:
+        x_init = x_init[None, :]
+    shared = x_init.shape[0] == 1 and P >= 1
+    if not shared and x_init.shape[0] != P:
+        raise ValueError("x_init must hold one initial state, or one per parameter set")
+    arr = (_lib.sponet_cnvm_params * P)(*model_structs)
+    cvs, cv_keep = cv_struct(cv_spec)
+    D = 0 if cv_spec is None else cv_keep.dimension
+    out_cv = _alloc((P, nrun, T, D), np.float64, x_init) if want_cv else None
+    opts = _native_opts(seed, num_runs_total, run_begin, run_end, None, False, warps_per_chain, False, hist, chain_offset)
+    sum_p = sumsq_p = None
+    if sums is not None:
+        sum_p, sumsq_p = _lib.ptr(sums[0]), _lib.ptr(sums[1])
+    rc = L.sponet_cnvm_run_sweep(
+        graph.handle if graph is not None else None, num_agents, arr, P, _lib.ptr(x_init), int(shared), _lib.ptr(t_eval), T,
+        C.byref(opts), None if cvs is None else C.byref(cvs), None, _lib.ptr(out_cv), sum_p, sumsq_p, _lib.ptr(counters),
+        _lib.current_stream_ptr(),
+    )
+    _lib.check(rc)
+    return out_cv
 
 
 # ---------------------------------------------------------------------------------------------

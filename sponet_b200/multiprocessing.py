@@ -200,6 +200,11 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
     rb, re = int(bounds[rank]), int(bounds[rank + 1])
     states = np.ascontiguousarray(states)
     pbar = _progress(progress_bar, S * (re - rb))
+    k_states = states  # what the kernel call gets: under NCCL a device copy, so that its output stays on the GPU
+    if world > 1 and _nccl():
+        import torch
+
+        k_states = torch.as_tensor(states, device="cuda")
 
     spec = _kernel_cv_spec(cv, N)
     if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
@@ -214,7 +219,7 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
                                          cv_spec=spec, want_cv=True, counts_init=counts0)
             del keep
         else:
-            _, local = _native_call(model, kind, states, t_out, seed, num_runs, rb, re, cv_spec=spec, want_cv=True)
+            _, local = _native_call(model, kind, k_states, t_out, seed, num_runs, rb, re, cv_spec=spec, want_cv=True)
         _tick(pbar, S * (re - rb))
     elif cv is None:
         # full trajectories: produced in run chunks so that the device-side staging stays bounded
@@ -297,6 +302,15 @@ def _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, p
     return out
 
 
+def _nccl() -> bool:
+    try:
+        import torch.distributed as dist
+
+        return dist.get_backend() == "nccl"
+    except Exception:
+        return False
+
+
 def _broadcast_seed(seed: int) -> int:
     import torch
     import torch.distributed as dist
@@ -307,21 +321,31 @@ def _broadcast_seed(seed: int) -> int:
     return int(t[0].item()) | (int(t[1].item()) << 63)
 
 
-def _gather_runs(local: np.ndarray, bounds: np.ndarray, world: int) -> np.ndarray:
-    """All-gather the per-rank run slices (axis 1) into the full array on every rank."""
+def _gather_runs(local, bounds: np.ndarray, world: int) -> np.ndarray:
+    """All-gather the per-rank run slices (axis 1) into the full array on every rank.  ``local`` is this rank's
+    slab, a numpy array or -- on the native path under NCCL -- the CUDA tensor the kernel wrote: it goes into the
+    all-gather as it is and the full array is copied to the host once."""
     import torch
     import torch.distributed as dist
 
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
     sizes = np.diff(bounds)
     width = int(sizes.max())
-    shape = list(local.shape)
+    loc = local if hasattr(local, "data_ptr") else torch.from_numpy(np.ascontiguousarray(local))
+    shape = list(loc.shape)
     shape[1] = width
-    pad = torch.zeros(shape, dtype=torch.from_numpy(local[:0]).dtype, device=dev)
-    pad[:, : local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
-    pieces = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(pieces, pad)
-    return np.concatenate([pc[:, : int(sizes[r])].cpu().numpy() for r, pc in enumerate(pieces)], axis=1)
+    if loc.shape[1] == width and str(loc.device).startswith(dev):
+        pad = loc.contiguous()
+    else:
+        pad = torch.zeros(shape, dtype=loc.dtype, device=dev)
+        pad[:, : loc.shape[1]] = loc.to(dev)
+    flat = torch.empty([world * shape[0]] + shape[1:], dtype=loc.dtype, device=dev)  # concatenated along axis 0
+    dist.all_gather_into_tensor(flat, pad)
+    full = flat.view([world] + shape)
+    if all(int(sz) == width for sz in sizes):  # equal shares: [world, S, w, ...] -> [S, world * w, ...] in one copy
+        return full.movedim(0, 1).reshape([shape[0], world * width] + shape[2:]).cpu().numpy()
+    host = full.cpu().numpy()
+    return np.concatenate([host[r][:, : int(sizes[r])] for r in range(world)], axis=1)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -28,6 +28,14 @@ def main():
     _, m_dist, v_dist, n_dist = sample_moments(params, x0, 2.0, T, 64, rel_tol=1e9, collective_variable=cv,
                                                rng=np.random.default_rng(7))
 
+    # parameter sweep: points dealt to the ranks, moments + histograms all-reduced on device buffers
+    from sponet_b200 import estimate_steady_state, sample_moments_sweep
+
+    plist = [CNVMParameters(num_opinions=3, network=params.network, r=workloads.R3 * (1 + 0.2 * q), r_tilde=workloads.RT3)
+             for q in range(3)]
+    sw_dist = sample_moments_sweep(plist, x0, 1.0, 4, 21, cv, rng=np.random.default_rng(8), hist_bins=12)
+    ss_dist = estimate_steady_state(plist[0], cv, tol_abs=0.02, rng=np.random.default_rng(9), verbose=False, num_chains=16)
+
     # the same calls on ONE GPU (sharding switched off locally)
     real = smp._dist
     smp._dist = lambda: (0, 1)
@@ -38,8 +46,13 @@ def main():
     _, x_one = sample_many_runs(params, x0, 1.0, 3, 5, rng=np.random.default_rng(6))
     _, m_one, v_one, n_one = sample_moments(params, x0, 2.0, T, 64, rel_tol=1e9, collective_variable=cv,
                                             rng=np.random.default_rng(7))
+    sw_one = sample_moments_sweep(plist, x0, 1.0, 4, 21, cv, rng=np.random.default_rng(8), hist_bins=12)
+    ss_one = estimate_steady_state(plist[0], cv, tol_abs=0.02, rng=np.random.default_rng(9), verbose=False, num_chains=16)
     smp._dist = real
     sm._dist = real
+    for a, b in zip(sw_dist, sw_one):
+        assert np.array_equal(a, b), "sharded sweep differs from the single-GPU sweep"
+    assert np.array_equal(ss_dist, ss_one), "sharded steady-state estimate differs"
 
     assert c_dist.shape == (R, T, 3) and np.array_equal(c_dist, c_one), "sharded CV ensemble differs"
     assert np.array_equal(x_dist, x_one), "sharded state ensemble differs"

@@ -57,9 +57,48 @@ def _worker(rank, world, port, out_dir):
         ref = _fake_cv(seed, S, range(R), T, D)[0].astype(np.int64)
         np.testing.assert_array_equal(s1, ref.sum(0))
         np.testing.assert_array_equal(s2, (ref * ref).sum(0))
+        # parameter sweep: the (point, run) range dealt to the ranks in at most three pieces each; the integer
+        # partials of all ranks meet in one all-reduce of (CPU stand-ins of) the device buffers
+        import torch
+
+        from sponet_b200.sample_moments import _allreduce_device_, sweep_pieces
+
+        P, Rs = 5, 9  # 45 work items over 2 ranks: 23 + 22 -> rank 0 ends inside point 2
+        pieces = sweep_pieces(P, Rs, rank, world)
+        assert len(pieces) <= 3
+        sums = torch.zeros((2, P, 4, 3), dtype=torch.int64)
+        hist = torch.zeros((P, 4, 3, 8), dtype=torch.int64)
+        for (pb, pe, r0, r1) in pieces:
+            for pt in range(pb, pe):
+                for run in range(r0, r1):
+                    v = 100 * pt + run  # stand-in of a chain's CV value
+                    sums[0, pt] += v
+                    sums[1, pt] += v * v
+                    hist[pt, :, :, v % 8] += 1
+        _allreduce_device_([sums, hist])
+        for pt in range(P):
+            vals = np.array([100 * pt + run for run in range(Rs)])
+            assert int(sums[0, pt, 0, 0]) == vals.sum() and int(sums[1, pt, 3, 2]) == (vals * vals).sum()
+            np.testing.assert_array_equal(hist[pt, 0, 0].numpy(), np.bincount(vals % 8, minlength=8))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
+
+
+def test_sweep_pieces_cover_every_item_once():
+    from sponet_b200.sample_moments import sweep_pieces
+
+    for P, R, world in [(256, 100000, 8), (5, 9, 2), (3, 10, 8), (1, 7, 3), (16, 4, 5), (2, 1, 4)]:
+        seen = np.zeros((P, R), dtype=int)
+        for rank in range(world):
+            pieces = sweep_pieces(P, R, rank, world)
+            assert len(pieces) <= 3
+            for (pb, pe, r0, r1) in pieces:
+                assert 0 <= pb < pe <= P and 0 <= r0 < r1 <= R and (pe - pb == 1 or (r0, r1) == (0, R))
+                seen[pb:pe, r0:r1] += 1
+        assert (seen == 1).all(), (P, R, world)
+    # 256 points on 8 ranks: whole points only, 32 each
+    assert sweep_pieces(256, 100000, 3, 8) == [(96, 128, 0, 100000)]
 
 
 def test_two_rank_gloo_sharding(tmp_path):

@@ -34,28 +34,33 @@ def warp(x, lanes, table, rng):
             ev.append((m, nw, acc))
         order = [i for i in range(L) if ev[i][2]]
         rng.shuffle(order)  # the hardware serializes the atomics of one instruction in some order
-        old = {}
-        for i in order:
+        won = [False] * L
+        lost = [False] * L
+        for i in order:  # compare-and-swap on the field: the first writer of a field wins, the others write nothing
             a = lanes[i][1]
-            old[i] = x[a]
-            x[a] ^= ev[i][0] ^ ev[i][1]
+            if ev[i][0] == ev[i][1]:
+                continue
+            if x[a] == ev[i][0]:
+                x[a] = ev[i][1]
+                won[i] = True
+            else:
+                lost[i] = True
         bad = [False] * L
-        multi = [False] * L
         for i, (noise, a, nbr, newop, r3) in enumerate(lanes):
             m, nw, acc = ev[i]
-            chk = x[a] ^ (nw if acc else m)
+            chk = x[a] ^ (nw if (acc and not lost[i]) else m)
             if not noise:
                 chk |= x[nbr] ^ nw
-            bad[i] = pending[i] and chk != 0
-            multi[i] = acc and old[i] != m
-        if not any(bad) and not any(multi):
+            bad[i] = (pending[i] and chk != 0) or lost[i]
+        if not any(bad):
             acc_n += sum(1 for e in ev if e[2])
             return x, acc_n, rounds
-        for i in order:  # roll back
-            x[lanes[i][1]] ^= ev[i][0] ^ ev[i][1]
+        for i in range(L):  # roll back
+            if won[i]:
+                x[lanes[i][1]] ^= ev[i][0] ^ ev[i][1]
         writers = [i for i in range(L) if ev[i][2] and ev[i][0] != ev[i][1]]
         w0 = writers[0] if writers else -1
-        f = 0 if (any(multi) or not any(bad)) else bad.index(True)
+        f = bad.index(True)
         g = max(f, w0 + 1)
         for i in range(g):
             if ev[i][2]:
