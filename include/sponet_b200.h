@@ -299,6 +299,19 @@ int sponet_propensities(const sponet_graph* g, int64_t num_agents, const uint8_t
  * (sponet/sample_moments.py:107-108), fixed-order reduction. */
 int sponet_moments(const double* x, int64_t R, int64_t L, double* sum, double* sumsq, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Initial-state samplers (sponet/states.py:45-164), native RNG (Philox keyed by `seed`)
+ * ------------------------------------------------------------------------------------------- */
+
+/* out uint8 [num_states, n] (host or device).
+ *   counts == NULL: sponet/states.py:45-77 sample_states_uniform -- every agent uniform in {0..M-1}.
+ *   counts [num_states, M] (or [1, M] with counts_shared): states.py:80-164 sample_states_uniform_shares /
+ *   sample_states_target_shares -- state s is a uniformly random arrangement of counts[s][m] agents of opinion m
+ *   (the reference shuffles np.repeat(opinions, counts); here: sequential draws without replacement).
+ * The target counts themselves (counts_from_shares, Dirichlet shares) are host arithmetic of the caller. */
+int sponet_sample_states(int64_t num_agents, int32_t num_opinions, const int64_t* counts, int32_t counts_shared,
+                         int64_t num_states, uint64_t seed, uint8_t* out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -447,3 +447,17 @@ def cntm_native(x, row_ptr, col, noise_thr, threshold_01, threshold_10, counts, 
     ev = f(x, n, row_ptr, col, int(noise_thr), threshold_01, threshold_10, counts, T, seed, chain,
            None if out_x is None else out_x.ctypes.data, out_c, C.byref(acc))
     return out_x, out_c, ev, acc.value
+
+
+def sample_states(n, M, counts, S, seed):
+    """oracle_sample_states: counts None (uniform opinions) or int64 [S, M] / [1, M] (shared)."""
+    out = np.empty((S, n), dtype=np.uint8)
+    f = lib().oracle_sample_states
+    f.restype = None
+    f.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, _u8]
+    if counts is None:
+        f(n, M, None, 0, S, seed, out)
+    else:
+        c = np.ascontiguousarray(np.atleast_2d(counts), dtype=np.int64)
+        f(n, M, c.ctypes.data, int(c.shape[0] == 1), S, seed, out)
+    return out

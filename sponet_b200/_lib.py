@@ -112,6 +112,7 @@ _SIGNATURES = {
     "sponet_cnvm_run_complete_counts": (C.c_int, [_i64, C.POINTER(sponet_cnvm_params), _vp, _i64, _vp, _i64, C.POINTER(sponet_native_opts), C.POINTER(sponet_shares_cv), _vp, _vp, _vp, _vp, _vp]),
     "sponet_cntm_run": (C.c_int, [_vp, C.POINTER(sponet_cntm_params), _vp, _i64, _vp, _i64, C.POINTER(sponet_native_opts), C.POINTER(sponet_shares_cv), _vp, _vp, _vp, _vp, _vp, _vp]),
     "sponet_native_event_counts": (C.c_int, [_u64, _i64, _i64, _vp, _i64, _f64, _vp, _vp]),
+    "sponet_sample_states": (C.c_int, [_i64, _i32, _vp, _i32, _i64, _u64, _vp, _vp]),
     "sponet_opinion_shares": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "sponet_moments": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "sponet_interfaces": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -87,6 +87,39 @@ extern "C" int sponet_cnvm_event_rates(const double* degree_alpha, int64_t n, do
     return SPONET_OK;
 }
 
+// Derived graph layouts, one thread per (agent, slot) -- or per agent when there is no table:
+//   col4   rows padded to multiples of four; the padding entries of row i hold i itself (an agent never counts
+//          as a neighbour of the opposite opinion of itself, so the CNTM row scan needs no validity test)
+//   nbtab  neighbour sampler table: agent i, slot j of L = 2^lg.  Neighbour k owns the slot interval
+//          [k L / d, (k+1) L / d); slot j belongs to its primary neighbour floor(j d / L) up to the boundary
+//          b = (primary + 1) L / d and to the next neighbour beyond it.  thr = floor(share * 2^24).
+__global__ void graph_build_kernel(int64_t n, const int2* row, const int32_t* col, const int2* row4, int4* col4,
+                                   uint2* nbtab, int lg) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t L = nbtab ? ((int64_t)1 << lg) : 1;
+    const int64_t i = tid / L, j = tid - i * L;
+    if (i >= n) return;
+    const int2 r = row[i];
+    if (j == 0) {  // the padded row
+        int32_t* dst = reinterpret_cast<int32_t*>(col4 + row4[i].x);
+        const int32_t padded = (r.y + 3) / 4 * 4;
+        for (int32_t k = 0; k < r.y; ++k) dst[k] = col[r.x + k];
+        for (int32_t k = r.y; k < padded; ++k) dst[k] = (int32_t)i;
+    }
+    if (nbtab) {
+        const int64_t d = r.y;
+        const int32_t* nb = col + r.x;
+        const int64_t k = j * d / L;              // primary neighbour of slot j
+        const int64_t num = (k + 1) * L - j * d;  // share of the slot owned by k, times d
+        uint32_t id0 = (uint32_t)nb[k], id1 = id0, thr = 0xFFFFFFu;
+        if (num < d) {  // the slot continues into neighbour k + 1
+            id1 = (uint32_t)nb[k + 1];
+            thr = (uint32_t)((num << 24) / d);
+        }
+        nbtab[i * L + j] = make_uint2(id0 | ((thr >> 12) << 20), id1 | ((thr & 0xFFFu) << 20));
+    }
+}
+
 extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int32_t* col,
                                    sponet_graph** out) {
     SP_REQUIRE(out && row_ptr && n >= 1 && n < (int64_t)1 << 31, "graph_create: bad arguments");
@@ -106,7 +139,9 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     }
     for (int64_t e = 0; e < nnz; ++e)
         SP_REQUIRE(col[e] >= 0 && col[e] < n, "graph_create: neighbour index %d out of range", col[e]);
-    // padded copy: rows aligned to 16 bytes
+    // padded copy (rows aligned to 16 bytes) and neighbour sampler table: derived ON THE DEVICE from the uploaded
+    // CSR (graph_build_kernel below) -- at N = 1e5 the table alone is 3.2e6 entries / 25.6 MB, which a serial host
+    // loop plus upload made the dominant cost of every new graph (per-run networks: one graph per realization).
     std::vector<int2> row4(n);
     int64_t n4 = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -114,40 +149,9 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
         n4 += (row[i].y + 3) / 4;
     }
     SP_REQUIRE(n4 < ((int64_t)1 << 31), "graph_create: network too large");
-    // The padding entries of row i hold i itself: an agent never counts as a neighbour of the opposite
-    // opinion of itself, so the CNTM row scan needs no validity test per entry.
-    std::vector<int4> col4((size_t)std::max<int64_t>(n4, 1), make_int4(0, 0, 0, 0));
-    for (int64_t i = 0; i < n; ++i) {
-        int32_t* dst = reinterpret_cast<int32_t*>(col4.data() + row4[i].x);
-        const int32_t padded = (row[i].y + 3) / 4 * 4;
-        for (int32_t k = 0; k < row[i].y; ++k) dst[k] = col[row[i].x + k];
-        for (int32_t k = row[i].y; k < padded; ++k) dst[k] = (int32_t)i;
-    }
-    // neighbour sampler table: agent i, slot j of L = 2^lg.  Neighbour k owns the slot interval
-    // [k L / d, (k+1) L / d); slot j belongs to its primary neighbour floor(j d / L) up to the boundary
-    // b = (primary + 1) L / d and to the next neighbour beyond it.  thr = floor(share * 2^24).
     int lg = 1;
     while ((1 << lg) < dmax) ++lg;
     const bool use_tab = dmin >= 1 && dmax <= 64 && n <= (1 << 20) && ((int64_t)n << lg) * 8 <= ((int64_t)64 << 20);
-    std::vector<uint2> nbtab;
-    if (use_tab) {
-        const int64_t L = (int64_t)1 << lg;
-        nbtab.resize((size_t)(n * L));
-        for (int64_t i = 0; i < n; ++i) {
-            const int64_t d = row[i].y;
-            const int32_t* nb = col + row[i].x;
-            for (int64_t j = 0; j < L; ++j) {
-                const int64_t k = j * d / L;                 // primary neighbour of slot j
-                const int64_t num = (k + 1) * L - j * d;     // share of the slot owned by k, times d
-                uint32_t id0 = (uint32_t)nb[k], id1 = id0, thr = 0xFFFFFFu;
-                if (num < d) {                               // the slot continues into neighbour k + 1
-                    id1 = (uint32_t)nb[k + 1];
-                    thr = (uint32_t)((num << 24) / d);
-                }
-                nbtab[(size_t)(i * L + j)] = make_uint2(id0 | ((thr >> 12) << 20), id1 | ((thr & 0xFFFu) << 20));
-            }
-        }
-    }
     sponet_graph* g = new sponet_graph();
     g->d_nbtab = nullptr;
     g->nbtab_log2 = use_tab ? lg : 0;
@@ -169,11 +173,17 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     if (e == cudaSuccess) e = cudaMemcpy(g->d_row, row.data(), n * sizeof(int2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && nnz) e = cudaMemcpy(g->d_col, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row4, n * sizeof(int2));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col4, col4.size() * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col4, (size_t)std::max<int64_t>(n4, 1) * sizeof(int4));
     if (e == cudaSuccess) e = cudaMemcpy(g->d_row4, row4.data(), n * sizeof(int2), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(g->d_col4, col4.data(), col4.size() * sizeof(int4), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && use_tab) e = cudaMalloc((void**)&g->d_nbtab, nbtab.size() * sizeof(uint2));
-    if (e == cudaSuccess && use_tab) e = cudaMemcpy(g->d_nbtab, nbtab.data(), nbtab.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && use_tab) e = cudaMalloc((void**)&g->d_nbtab, ((size_t)n << lg) * sizeof(uint2));
+    if (e == cudaSuccess) {
+        const int64_t work = use_tab ? ((int64_t)n << lg) : n;
+        graph_build_kernel<<<(unsigned)((work + 255) / 256), 256>>>(n, g->d_row, g->d_col, g->d_row4, g->d_col4,
+                                                                   use_tab ? g->d_nbtab : nullptr, lg);
+        e = cudaGetLastError();
+        // (the legacy default stream: does not wait for work on the non-blocking streams other graphs' chains run on)
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    }
     if (e != cudaSuccess) {
         cudaFree(g->d_nbtab);
         cudaFree(g->d_row_ptr);

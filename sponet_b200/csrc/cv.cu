@@ -229,3 +229,74 @@ extern "C" int sponet_moments(const double* x, int64_t R, int64_t L, double* sum
     SP_CUDA(sc.finish());
     return SPONET_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Initial-state samplers (sponet/states.py:45-164) on the device.  Native RNG: Philox4x32-10 keyed by the seed,
+// counter (agent, state, tag 2).  One thread per state walks the agents in order.
+//   counts == NULL   sample_states_uniform: x[s, i] = mulhi(r0, M), every opinion with probability 1 / M
+//   counts != NULL   a uniformly random arrangement of the multiset with counts[s][m] agents of opinion m
+//                    (sample_states_target_shares / sample_states_uniform_shares): sequential draws WITHOUT
+//                    replacement from the urn -- agent i takes opinion m with probability left[m] / left_total --
+//                    which is exactly the distribution of a shuffled multiset.  The position in the urn comes
+//                    from a 64-bit uniform (mul64hi), so the quantisation is left_total / 2^64.
+// The sequential statement is oracle_sample_states (oracle/oracle_native.inc).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void sample_states_kernel(int64_t n, int M, const int64_t* counts, int counts_shared, int64_t S,
+                                     uint64_t seed, uint8_t* out) {
+    extern __shared__ long long s_left[];  // [blockDim.x][M] remaining counts, thread-major
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    uint8_t* x = out + s * n;
+    if (!counts) {
+        for (int64_t i = 0; i < n; ++i) x[i] = (uint8_t)__umulhi(sp_native_draw(seed, (uint64_t)s, 2u, (uint64_t)i).x, (uint32_t)M);
+        return;
+    }
+    long long* left = s_left + (size_t)threadIdx.x * M;
+    const int64_t* c = counts + (counts_shared ? 0 : s * M);
+    long long total = 0;
+    for (int m = 0; m < M; ++m) {
+        left[m] = c[m];
+        total += c[m];
+    }
+    for (int64_t i = 0; i < n; ++i, --total) {
+        const uint4 r = sp_native_draw(seed, (uint64_t)s, 2u, (uint64_t)i);
+        unsigned long long pos = __umul64hi(((unsigned long long)r.x << 32) | r.y, (unsigned long long)total);
+        int m = 0;
+        while (pos >= (unsigned long long)left[m]) pos -= (unsigned long long)left[m++];
+        --left[m];
+        x[i] = (uint8_t)m;
+    }
+}
+}  // namespace
+
+extern "C" int sponet_sample_states(int64_t num_agents, int32_t num_opinions, const int64_t* counts,
+                                    int32_t counts_shared, int64_t num_states, uint64_t seed, uint8_t* out,
+                                    void* cuda_stream) {
+    SP_REQUIRE(out && num_agents >= 1 && num_opinions >= 1 && num_opinions <= 256 && num_states >= 0, "sample_states: bad arguments");
+    if (num_states == 0) return SPONET_OK;
+    const int64_t rows = counts_shared ? 1 : num_states;
+    if (counts && !sp_is_device_ptr(counts))
+        for (int64_t j = 0; j < rows; ++j) {
+            int64_t tot = 0;
+            for (int v = 0; v < num_opinions; ++v) {
+                SP_REQUIRE(counts[j * num_opinions + v] >= 0, "sample_states: counts must be non-negative");
+                tot += counts[j * num_opinions + v];
+            }
+            SP_REQUIRE(tot == num_agents, "sample_states: counts row %lld sums to %lld, expected %lld", (long long)j,
+                       (long long)tot, (long long)num_agents);
+        }
+    SpScratch sc((cudaStream_t)cuda_stream);
+    const int64_t* d_c;
+    uint8_t* d_out;
+    SP_CUDA(sc.in(counts, (size_t)rows * num_opinions, &d_c));
+    SP_CUDA(sc.out(out, (size_t)num_states * num_agents, &d_out));
+    int block = 32;  // threads (states) per CTA; the remaining counts of a state sit in shared memory (8 M bytes each)
+    while (counts && block > 1 && (size_t)block * num_opinions * sizeof(long long) > 40960) block >>= 1;
+    const size_t smem = counts ? (size_t)block * num_opinions * sizeof(long long) : 0;
+    sample_states_kernel<<<(unsigned)((num_states + block - 1) / block), block, smem, sc.stream>>>(
+        num_agents, num_opinions, d_c, counts_shared, num_states, seed, d_out);
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(sc.finish());
+    return SPONET_OK;
+}

@@ -36,6 +36,7 @@ struct NativeCnvmArgs {
     int64_t x_stride;      // n, or 0 when all state slots share one initial state (sweep)
     const int64_t* counts;  // [S*nrun, T-1]
     int64_t S, nrun, R_total, run_begin;
+    int64_t cl_begin, cl_end;  // local chains [cl_begin, cl_end) of the S * nrun of the call run in this launch
     int32_t T;
     uint64_t seed;
     uint8_t* out_x;
@@ -109,7 +110,11 @@ __device__ __forceinline__ uint2 sp_lds2(uint32_t saddr) {  // 8-byte variant
     return v;
 }
 __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named barrier of one chain's warps
+#ifdef SP_FIXED_W
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * SP_FIXED_W) : "memory");
+#else
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#endif
 }
 // the same barrier with a vote: true iff `pred` holds for any of the participating threads
 __device__ __forceinline__ bool sp_ring_any(int id, int threads, bool pred) {
@@ -122,7 +127,11 @@ __device__ __forceinline__ bool sp_ring_any(int id, int threads, bool pred) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(r)
+#ifdef SP_FIXED_W
+        : "r"(id), "n"(32 * SP_FIXED_W), "r"((uint32_t)pred)
+#else
         : "r"(id), "r"(threads), "r"((uint32_t)pred)
+#endif
         : "memory");
     return r != 0u;
 }
@@ -183,11 +192,10 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
     else state = A.gstate + ((size_t)blockIdx.x * slots + slot) * A.words;
     __syncthreads();
 
-    const int64_t num_chains = A.S * A.nrun;
     unsigned long long ev_total = 0, acc_total = 0, step_total = 0, extra_total = 0;
     const int T = A.T;
 
-    for (int64_t cl = (int64_t)blockIdx.x * slots + slot; cl < num_chains; cl += (int64_t)gridDim.x * slots) {
+    for (int64_t cl = A.cl_begin + (int64_t)blockIdx.x * slots + slot; cl < A.cl_end; cl += (int64_t)gridDim.x * slots) {
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
@@ -648,6 +656,15 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
                             if (rem == stop) break;
+#ifdef SP_ISSUE1_TOP
+                            if (ALIAS) {
+                                resolve((u + 2) % 3);
+                                draw(e_pre);
+                            } else {
+                                issue1((u + 2) % 3, e_pre);
+                            }
+                            e_pre += e_stride;
+#endif
                             issue2((u + 1) % 3);  // the next own step's neighbour, out of the entry gathered a step ago
                             const bool active = rem != 1 || in_last;
                             const bool active_next = rem > 2 || (rem == 2 && in_last);
@@ -659,6 +676,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                             // The draws of the step after the next one sit in the read phase on purpose: its block
                             // holds the shared-memory round trips (re-reads, next decision, threshold), and the
                             // Philox rounds are independent work to issue while those are in flight.
+#ifndef SP_ISSUE1_TOP
                             if (ALIAS) {
                                 resolve((u + 2) % 3);  // two own steps ahead: agent + entry gather
                                 draw(e_pre);           // three own steps ahead: Philox + alias gather
@@ -666,6 +684,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                                 issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
                             }
                             e_pre += e_stride;
+#endif
                             const bool bad = changed(u, active, cur);
                             evaluate((u + 1) % 3, active_next, nxt);
                             if (!coop_any(bad)) {
@@ -1208,61 +1227,87 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     const size_t thr_bytes = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);  // per chain slot
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
     const size_t per_slot_min = cnt_bytes + 16 + thr_bytes;      // + the reduction words of a COOP chain
-    bool smem_state = !o->force_global_state;
     const int max_warps = SP_RING_MAX_THREADS / 32;
-    int slots = 0;
-    if (smem_state) {
-        if (smem_max > fixed + 64)
-            slots = (int)std::min<size_t>((size_t)max_warps, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
-        if (slots < 1) smem_state = false;  // a chain beyond 227 KB: states in global memory
-    }
-    int wpc = 1;  // warps per chain
-    if (smem_state) {
-        // no more slots than there are chains to run on this many SMs
-        const int64_t need = (num_chains + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-        const int fit = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
-        if (o->warps_per_chain > 0) {
-            wpc = std::min(o->warps_per_chain, max_warps);
-            slots = std::max(1, std::min(fit, max_warps / wpc));
-        } else {
-            // Fill the CTA with warps: of all (slots <= fit, warps per chain) the pair with the most warps, more
-            // chains on a tie (H, 512 threads: 9 chains fit, 8 x 2 warps beat 9 x 1; a chain that fills the SM's
-            // shared memory alone gets every warp of the CTA: COOP super-steps of 32 * wpc events).
-            int best = 0;
-            for (int sl = fit; sl >= 1; --sl) {
-                int w = max_warps / sl;
-                if (w > 1 && sl > 15) w = 1;  // named barriers 1..15 identify the chains of a CTA
-                if (sl * w > best) {
-                    best = sl * w;
-                    slots = sl;
-                    wpc = w;
+    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
+    // Launches the local chains [c0, c1) with the geometry that suits their number; returns the chains one wave
+    // of that geometry holds (resident chain slots on the whole device).
+    auto launch_range = [&](int64_t c0, int64_t c1, bool launch, int64_t* wave) -> int {
+        const int64_t count = c1 - c0;
+        bool smem_state = !o->force_global_state;
+        int slots = 0;
+        if (smem_state) {
+            if (smem_max > fixed + 64)
+                slots = (int)std::min<size_t>((size_t)max_warps, (smem_max - fixed - 64) / (chain_bytes + per_slot_min));
+            if (slots < 1) smem_state = false;  // a chain beyond 227 KB: states in global memory
+        }
+        int wpc = 1;  // warps per chain
+        if (smem_state) {
+            // no more slots than there are chains to run on this many SMs
+            const int64_t need = (count + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
+            const int fit = (int)std::max<int64_t>(1, std::min<int64_t>(slots, need));
+            if (o->warps_per_chain > 0) {
+                wpc = std::min(o->warps_per_chain, max_warps);
+                slots = std::max(1, std::min(fit, max_warps / wpc));
+            } else {
+                // Fill the CTA with warps: of all (slots <= fit, warps per chain) the pair with the most warps, more
+                // chains on a tie (H, 512 threads: 9 chains fit, 8 x 2 warps beat 9 x 1; a chain that fills the SM's
+                // shared memory alone gets every warp of the CTA: COOP super-steps of 32 * wpc events).
+                // More warps per chain mean more events per super-step and more hazard rounds: a chain runs fastest
+                // with about sqrt(0.7 N) events in flight (measured: N = 1e4 -> 2 warps, 1e5 -> 8, 1e6 -> 16+).
+                int w_cap = 1;
+                while (w_cap < 16 && (double)(64 * w_cap) * (double)(64 * w_cap) <= 0.7 * (double)n) w_cap *= 2;
+                int best = 0;
+                for (int sl = fit; sl >= 1; --sl) {
+                    int w = std::min(max_warps / sl, w_cap);
+                    if (w > 1 && sl > 15) w = 1;  // named barriers 1..15 identify the chains of a CTA
+                    if (sl * w > best) {
+                        best = sl * w;
+                        slots = sl;
+                        wpc = w;
+                    }
                 }
             }
+            if (wpc > 1 && slots > 15) slots = 15;
+        } else {
+            slots = 8;
         }
-        if (wpc > 1 && slots > 15) slots = 15;
-    } else {
-        slots = 8;
+        const bool pair = wpc > 1;
+        const int warps = slots * wpc;
+        NativeCnvmArgs B = A;
+        B.cl_begin = c0;
+        B.cl_end = c1;
+        B.warps_per_chain = wpc;
+        size_t smem_bytes = fixed + (size_t)slots * thr_bytes + (pair ? (size_t)slots * 16 : 0) + (size_t)slots * cnt_bytes +
+                            (smem_state ? (size_t)slots * chain_bytes : 0);
+        B.warps_per_cta = warps;
+        const int threads = warps * 32;
+        cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, graph_kind, A.alias_tab != nullptr, pair);
+        SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int blocks_per_sm = 1;
+        SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem_bytes));
+        SP_REQUIRE(blocks_per_sm >= 1, "cnvm_run: kernel does not fit on an SM (smem %zu B, %d threads)", smem_bytes, threads);
+        const int64_t ctas_needed = (count + slots - 1) / slots;
+        const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)prop.multiProcessorCount * blocks_per_sm);
+        if (wave) *wave = (int64_t)prop.multiProcessorCount * blocks_per_sm * slots;
+        if (!launch || c1 <= c0) return SPONET_OK;  // (geometry query only)
+        if (!smem_state) SP_CUDA(sc.alloc((void**)&B.gstate, (size_t)grid * slots * chain_bytes));
+        kern<<<grid, threads, smem_bytes, sc.stream>>>(B);
+        SP_CUDA(cudaGetLastError());
+        return SPONET_OK;
+    };
+    // Chains are dealt to the resident slots in waves.  A last wave that fills less than three quarters of the
+    // slots would leave most of the device idle for a whole wave (1250 chains on 1184 slots: two waves for the work
+    // of 1.06): that remainder runs as a launch of its own, whose geometry gives every chain more warps.  Explicit
+    // warps_per_chain (tests, A/B runs) keeps the single launch.
+    int64_t wave = 0;
+    SP_TRY(launch_range(0, num_chains, false, &wave));  // geometry of the whole call
+    int64_t tail_begin = num_chains;
+    if (o->warps_per_chain == 0 && !o->force_global_state && num_chains > wave && wave > 0) {
+        const int64_t full = num_chains / wave * wave, rem = num_chains - full;
+        if (rem > 0 && 4 * rem < 3 * wave) tail_begin = full;
     }
-    const bool pair = wpc > 1;
-    const int warps = slots * wpc;
-    A.warps_per_chain = wpc;
-    size_t smem_bytes = fixed + (size_t)slots * thr_bytes + (pair ? (size_t)slots * 16 : 0) + (size_t)slots * cnt_bytes +
-                        (smem_state ? (size_t)slots * chain_bytes : 0);
-    A.warps_per_cta = warps;
-    const int threads = warps * 32;
-    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
-    cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, graph_kind, A.alias_tab != nullptr, pair);
-    SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    int blocks_per_sm = 1;
-    SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem_bytes));
-    SP_REQUIRE(blocks_per_sm >= 1, "cnvm_run: kernel does not fit on an SM (smem %zu B, %d threads)", smem_bytes, threads);
-    const int64_t ctas_needed = (num_chains + slots - 1) / slots;
-    const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)prop.multiProcessorCount * blocks_per_sm);
-    if (!smem_state) {
-        SP_CUDA(sc.alloc((void**)&A.gstate, (size_t)grid * slots * chain_bytes));
-    }
-    kern<<<grid, threads, smem_bytes, sc.stream>>>(A);
-    SP_CUDA(cudaGetLastError());
+    SP_TRY(launch_range(0, tail_begin, true, nullptr));
+    SP_TRY(launch_range(tail_begin, num_chains, true, nullptr));
     SP_CUDA(sc.finish());
     return SPONET_OK;
 }

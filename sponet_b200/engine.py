@@ -94,6 +94,14 @@ class GraphCache:
         self._handles = {}
         self._obj = None
 
+    def detach(self) -> list:
+        """Hands the current handles to the caller (who closes them once the kernels using them are done):
+        per-run networks keep several graphs alive on different streams while the model moves on."""
+        hs = list(self._handles.values())
+        self._handles = {}
+        self._obj = None
+        return hs
+
 
 # ---------------------------------------------------------------------------------------------
 # struct marshalling

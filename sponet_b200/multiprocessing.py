@@ -7,7 +7,8 @@ call instead of a process pool of numba loops.
 native mode (default)
     Chain (j, i) = (initial state j, run i) draws from the Philox stream keyed by one uint64 taken
     from ``rng`` and countered by ``j * num_runs + i``: results depend on the seed only -- not on
-    ``n_jobs`` (accepted, ignored), not on how runs are sharded over GPUs.  An unweighted
+    ``n_jobs``, not on how runs are sharded over GPUs.  In a single process ``n_jobs`` selects how many of
+    the visible GPUs share the runs (None / 1: the current one, -1: all), one host thread per device.  An unweighted
     ``OpinionShares`` CV is reduced inside the simulation kernel (complete graphs take the count-only
     kernel); other CVs are evaluated on the GPU from snapshot slabs, run-chunk by run-chunk.
     Under ``torch.distributed`` (one process per GPU) the runs are split over the ranks like
@@ -137,6 +138,9 @@ def sample_many_runs(
     the opinions) or ``(S, R, T, D)`` float64 with a collective variable; the leading axis is dropped
     for a single 1-D initial state.
     """
+    on_device = hasattr(initial_states, "is_cuda") and initial_states.is_cuda
+    if on_device:  # states sampled on the GPU (sponet_b200.states, device=True): no host copy
+        return _sample_device_states(params, initial_states, t_max, t_eval, num_runs, collective_variable, rng, progress_bar, mode)
     initial_states = np.array(initial_states, ndmin=1)
     is_1d = initial_states.ndim == 1
     if is_1d:
@@ -157,8 +161,39 @@ def sample_many_runs(
             dtype if collective_variable is None else np.float64, copy=False)
     else:
         x_out = _sample_native(model, kind, initial_states.astype(np.uint8), t_out, num_runs,
-                               collective_variable, rng, progress_bar).astype(
+                               collective_variable, rng, progress_bar, n_jobs).astype(
             dtype if collective_variable is None else np.float64, copy=False)
+    return t_out, (x_out[0] if is_1d else x_out)
+
+
+def _sample_device_states(params, d_states, t_max, t_eval, num_runs, cv, rng, progress_bar, mode):
+    """sample_many_runs for initial states that already live on the GPU (CUDA uint8 tensor [S, N] or [N]): native
+    mode with an in-kernel collective variable only -- the case the device-side samplers exist for."""
+    import torch
+
+    model, kind = _make_model(params)
+    if engine.resolve_mode(mode) != "native" or getattr(params, "network_generator", None) is not None:
+        raise ValueError("device-resident initial states need native mode and a fixed network")
+    spec = _kernel_cv_spec(cv, params.num_agents) if cv is not None else None
+    if spec is not None and (spec.grouped or spec.divisors is not None) and kind != "cnvm":
+        spec = None
+    if spec is None:
+        raise ValueError("device-resident initial states need a collective variable the kernels evaluate")
+    if d_states.dtype != torch.uint8:
+        raise ValueError("device-resident initial states must be uint8")
+    is_1d = d_states.ndim == 1
+    st = (d_states[None, :] if is_1d else d_states).contiguous()
+    if int(st.max().item()) >= params.num_opinions:
+        raise ValueError(f"initial states must hold opinions in [0, {params.num_opinions})")
+    t_out = t_eval_to_ndarray(t_eval, t_max)
+    seed = engine.draw_seed(rng)
+    rank, world = _dist()
+    if world > 1:
+        seed = _broadcast_seed(seed)
+    bounds = np.concatenate(([0], np.cumsum(_split_runs(num_runs, world))))
+    rb, re = int(bounds[rank]), int(bounds[rank + 1])
+    _, local = _native_call(model, kind, st, t_out, seed, num_runs, rb, re, cv_spec=spec, want_cv=True)
+    x_out = _gather_runs(local, bounds, world) if world > 1 else local.cpu().numpy()
     return t_out, (x_out[0] if is_1d else x_out)
 
 
@@ -189,7 +224,53 @@ def _native_call(model, kind, x_init, t_out, seed, R_total, rb, re, **kw):
     return engine.run_native("cntm", model._graph(), p.num_agents, model._struct(), x_init, t_out, seed, R_total, rb, re, **kw)
 
 
-def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
+def _local_devices(n_jobs) -> int:
+    """GPUs a SINGLE process spreads an ensemble over: ``n_jobs`` keeps its meaning of "how many workers" --
+    None / 1: the current device only (like the reference's serial path), -1: every visible device, k: k devices.
+    (Under torch.distributed every rank owns one device and ``n_jobs`` is ignored.)"""
+    if n_jobs is None or n_jobs == 1:
+        return 1
+    try:
+        import torch
+
+        have = torch.cuda.device_count()
+    except Exception:
+        return 1
+    return have if n_jobs == -1 else max(1, min(int(n_jobs), have))
+
+
+def _multi_device_runs(model, kind, states, t_out, seed, num_runs, rb, re, spec, num_devices):
+    """Runs [rb, re) split like ``_split_runs`` over ``num_devices`` GPUs of this process: one host thread per
+    device (the C-ABI call releases the GIL and is re-entrant per device; the graph is uploaded once per device),
+    host buffers in and out, slabs concatenated in run order -- chain ids do not depend on the split, so the result
+    equals the single-device one bit for bit."""
+    import threading
+
+    import torch
+
+    b = rb + np.concatenate(([0], np.cumsum(_split_runs(re - rb, num_devices))))
+    parts, errors = [None] * num_devices, []
+    cur = torch.cuda.current_device()
+
+    def work(d):
+        try:
+            torch.cuda.set_device(d)
+            _, parts[d] = _native_call(model, kind, states, t_out, seed, num_runs, int(b[d]), int(b[d + 1]), cv_spec=spec, want_cv=True)
+        except Exception as e:  # re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in range(num_devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.set_device(cur)
+    if errors:
+        raise errors[0]
+    return np.concatenate(parts, axis=1)
+
+
+def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar, n_jobs=None):
     p = model.params
     S, N, T = states.shape[0], p.num_agents, t_out.size
     seed = engine.draw_seed(rng)
@@ -218,6 +299,8 @@ def _sample_native(model, kind, states, t_out, num_runs, cv, rng, progress_bar):
             _, local = engine.run_native("cnvm_counts", None, N, struct, None, t_out, seed, num_runs, rb, re,
                                          cv_spec=spec, want_cv=True, counts_init=counts0)
             del keep
+        elif world == 1 and _local_devices(n_jobs) > 1 and re - rb >= 2:
+            local = _multi_device_runs(model, kind, states, t_out, seed, num_runs, rb, re, spec, _local_devices(n_jobs))
         else:
             _, local = _native_call(model, kind, k_states, t_out, seed, num_runs, rb, re, cv_spec=spec, want_cv=True)
         _tick(pbar, S * (re - rb))
@@ -255,29 +338,77 @@ def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng
     D = N if cv is None else cv.dimension
     flat = np.zeros((pairs, T, D), dtype=np.uint8 if cv is None else np.float64)
     pbar = _progress(progress_bar, hi - lo)
-    for c in range(pairs):
-        model.update_network()  # every rank walks the same generator sequence
-        if not (lo <= c < hi):
-            continue
-        j = c // num_runs
-        x0 = np.ascontiguousarray(states[j : j + 1])
-        spec = _kernel_cv_spec(cv, N) if cv is not None else None
-        if spec is not None and (spec.edge and p.num_opinions != 2):
-            raise ValueError("Interfaces / Propensities can only be used for 2 opinions.")
-        if cv is None:
+    spec = _kernel_cv_spec(cv, N) if cv is not None else None
+    if spec is not None and (spec.edge and p.num_opinions != 2):
+        raise ValueError("Interfaces / Propensities can only be used for 2 opinions.")
+    if spec is not None and spec.edge:
+        spec = None  # an edge CV carries its own (fixed) graph; evaluated from the returned states below
+    if spec is not None:
+        flat[lo:hi] = _per_run_network_pipeline(model, kind, states, t_out, seed, pairs, lo, hi, cv, pbar)
+    else:
+        for c in range(pairs):
+            model.update_network()  # every rank walks the same generator sequence
+            if not (lo <= c < hi):
+                continue
+            j = c // num_runs
+            x0 = np.ascontiguousarray(states[j : j + 1])
             out, _ = _native_call(model, kind, x0, t_out, seed, pairs, c, c + 1, want_x=True)
-            flat[c] = out[0, 0]
-        elif spec is not None:
-            _, out = _native_call(model, kind, x0, t_out, seed, pairs, c, c + 1, cv_spec=spec, want_cv=True)
-            flat[c] = out[0, 0]
-        else:
-            out, _ = _native_call(model, kind, x0, t_out, seed, pairs, c, c + 1, want_x=True)
-            flat[c] = np.asarray(cv(out[0, 0]))
-        _tick(pbar, 1)
+            flat[c] = out[0, 0] if cv is None else np.asarray(cv(out[0, 0]))
+            _tick(pbar, 1)
     _close(pbar)
     if world > 1:
         flat = _gather_runs(flat[None, lo:hi], bounds, world)[0]
     return flat.reshape(S, num_runs, T, D)
+
+
+_NETWORK_STREAMS = 8
+
+
+def _per_run_network_pipeline(model, kind, states, t_out, seed, pairs, lo, hi, cv, pbar):
+    """Chains c in [lo, hi), each on the c-th network of the generator, with the CV reduced in-kernel.
+
+    One chain is one CTA, so a launch per chain would use 1 of 148 SMs: the chains go round-robin onto
+    ``_NETWORK_STREAMS`` CUDA streams with device-resident inputs and outputs -- the C-ABI call returns as soon
+    as the kernel is queued -- so up to that many graphs are simulated concurrently while the host generates
+    (networkx) and uploads the next one.  A graph handle is released when its stream has drained."""
+    import torch
+
+    p = model.params
+    N, T = p.num_agents, t_out.size
+    num_runs = pairs // states.shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    streams = [torch.cuda.Stream(device=dev) for _ in range(_NETWORK_STREAMS)]
+    alive = [[] for _ in streams]  # graph handles (and the buffers their launch reads) per stream
+    d_states = torch.as_tensor(np.ascontiguousarray(states), device=dev)
+    out_d = torch.zeros((max(hi - lo, 1), T, cv.dimension), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for c in range(pairs):
+        model.update_network()  # every rank walks the same generator sequence
+        if not (lo <= c < hi):
+            continue
+        k = (c - lo) % len(streams)
+        st = streams[k]
+        if alive[k]:  # the previous chain of this stream: wait for it, then free its graph
+            st.synchronize()
+            for h in alive[k][0]:
+                h.close()
+            alive[k] = []
+        spec = _kernel_cv_spec(cv, N)  # (per network: degree-weighted CVs depend on it)
+        graph = model._graph()
+        struct, keep = model._struct() if kind == "cnvm" else (model._struct(), None)
+        j = c // num_runs
+        with torch.cuda.stream(st):
+            _, res = engine.run_native(kind, graph, N, struct, d_states[j : j + 1], t_out, seed, pairs, c, c + 1,
+                                       cv_spec=spec, want_cv=True)
+            out_d[c - lo].copy_(res[0, 0], non_blocking=True)
+        alive[k] = [model._graphs.detach(), keep, res, spec]
+        _tick(pbar, 1)
+    torch.cuda.synchronize()
+    for a in alive:
+        if a:
+            for h in a[0]:
+                h.close()
+    return out_d[: hi - lo].cpu().numpy()
 
 
 def _native_generic_cv(model, kind, states, t_out, seed, num_runs, rb, re, cv, pbar):
