@@ -80,26 +80,26 @@ __device__ __forceinline__ uint32_t state_load(const uint32_t* p) {
 // agent-level kernel
 //
 // Per warp step (32 consecutive candidate events of one chain) the work is split into
-//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); CSR row gather issued
-//   stage 2  neighbour slot from the row; column gather issued
-//   commit   read x[a], x[nbr]; accept; accepting lanes write (atomicXor on the packed word); every lane
-//            re-reads its two locations: an input changed by another lane (or two real writers of one
-//            agent) rolls the step back, the exact prefix is committed and the rest re-evaluates
-// Stages 1 and 2 of the NEXT two steps are issued before the commit of the current one (software
-// pipeline of depth 2, unrolled three ways so that the stage registers rotate without copies).
+//   stage 1  Philox draw -> branch, agent (alias table when alpha != 1); gather of the agent's sampler-table
+//            entry (or CSR row) issued
+//   stage 2  neighbour out of the gathered entry (or the column gather issued)
+//   commit   write phase: accepting lanes swap their change into the packed state (compare-and-swap on the
+//            agent's field); read phase: every lane re-reads its two locations -- an input changed by another
+//            lane, or a lost write, rolls the step back, the exact prefix is committed and the rest re-evaluates
+//            -- and reads the locations and the threshold of its NEXT step in the same pass
+// Stage 1 runs two own steps ahead, stage 2 one (software pipeline, unrolled three ways so that the stage
+// registers rotate without copies).
 //
-// RING mode (large chains: only a few fit in an SM's shared memory, i.e. ~2 warps per scheduler):
-// W warps serve one chain and take its steps round-robin (step s belongs to warp s mod W).  Stages
-// 1-3 of a warp's next steps overlap the other warps' commits; the commits themselves stay strictly
-// ordered through a ring of mbarriers, one per warp (arrive = release after the writes, try_wait on
-// the predecessor = acquire before the reads).
+// COOP mode (template flag RING; large chains: only a few fit in an SM's shared memory): W warps serve one chain.
+// Step t of an output interval belongs to warp t mod W; the W steps u W .. u W + W - 1 form a SUPER-STEP whose
+// write and read phases all W warps execute together, separated by named barriers of the chain's 32 W threads
+// (bar.sync after the writes, bar.red.or as the vote on the verification).  Nothing is serialized between the
+// warps of a chain: 8 chains x 2 warps on workload H, one chain x 16 warps at N = 1e6.
+// (Round 1 ordered the warps' commits through a ring of mbarriers; the hand-over latency bounded a chain's rate.)
 // ---------------------------------------------------------------------------------------------
-#ifndef SP_GUARDS
-#define SP_GUARDS 1  // 1: skip stage 1/2 work of steps past the end of the chain
-#endif
-// A/B on B200 (H workload): 9 chains x 2 warps = 576 threads caps the kernel at 96 registers and spills
-// (4.0e10 events/s); 8 x 2 = 512 threads keeps 118 registers (6.3e10, vs 5.9e10 for 9 single warps).
-// Whether every lane or one lane arrives on the mbarrier makes no measurable difference.
+// Threads per CTA.  512 leave 128 registers per thread; with 768 the kernel compiles to 80 registers without
+// spills in the event loop, but 24 warps per SM measured no faster than 16 (the ALU pipe's two-cycle issue, not
+// latency, is the ceiling: profiles/r2_cnvm_h_ncu.md).
 #ifndef SP_RING_MAX_THREADS
 #define SP_RING_MAX_THREADS 512
 #endif
@@ -110,11 +110,7 @@ __device__ __forceinline__ uint2 sp_lds2(uint32_t saddr) {  // 8-byte variant
     return v;
 }
 __device__ __forceinline__ void sp_ring_sync(int id, int threads) {  // named barrier of one chain's warps
-#ifdef SP_FIXED_W
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * SP_FIXED_W) : "memory");
-#else
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-#endif
 }
 // the same barrier with a vote: true iff `pred` holds for any of the participating threads
 __device__ __forceinline__ bool sp_ring_any(int id, int threads, bool pred) {
@@ -127,11 +123,7 @@ __device__ __forceinline__ bool sp_ring_any(int id, int threads, bool pred) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(r)
-#ifdef SP_FIXED_W
-        : "r"(id), "n"(32 * SP_FIXED_W), "r"((uint32_t)pred)
-#else
         : "r"(id), "r"(threads), "r"((uint32_t)pred)
-#endif
         : "memory");
     return r != 0u;
 }
@@ -656,15 +648,6 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
                             if (rem == stop) break;
-#ifdef SP_ISSUE1_TOP
-                            if (ALIAS) {
-                                resolve((u + 2) % 3);
-                                draw(e_pre);
-                            } else {
-                                issue1((u + 2) % 3, e_pre);
-                            }
-                            e_pre += e_stride;
-#endif
                             issue2((u + 1) % 3);  // the next own step's neighbour, out of the entry gathered a step ago
                             const bool active = rem != 1 || in_last;
                             const bool active_next = rem > 2 || (rem == 2 && in_last);
@@ -676,7 +659,6 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                             // The draws of the step after the next one sit in the read phase on purpose: its block
                             // holds the shared-memory round trips (re-reads, next decision, threshold), and the
                             // Philox rounds are independent work to issue while those are in flight.
-#ifndef SP_ISSUE1_TOP
                             if (ALIAS) {
                                 resolve((u + 2) % 3);  // two own steps ahead: agent + entry gather
                                 draw(e_pre);           // three own steps ahead: Philox + alias gather
@@ -684,7 +666,6 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                                 issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
                             }
                             e_pre += e_stride;
-#endif
                             const bool bad = changed(u, active, cur);
                             evaluate((u + 1) % 3, active_next, nxt);
                             if (!coop_any(bad)) {

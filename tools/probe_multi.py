@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-from sponet_b200 import CNVM, engine, workloads
+from sponet_b200 import CNTM, CNVM, engine, workloads
 
 torch.cuda.init()
 models = {}
@@ -23,17 +23,24 @@ for spec_s in sys.argv[1:]:
     n, runs, t_max, T, wpc = parts[:5]
     n, runs, T, wpc, t_max = int(n), int(runs), int(T), int(wpc), float(t_max)
     if (kind, n) not in models:
-        params, x0, rate = workloads.headline_cnvm(n) if kind == "h" else workloads.sis_ws(n)
-        model = CNVM(params)
-        models[(kind, n)] = (params, x0, rate, model, model._struct(), model._graph())
+        if kind == "cntm":
+            params, x0, rate = workloads.ba_cntm(n)
+            model = CNTM(params)
+            models[(kind, n)] = (params, x0, rate, model, (model._struct(), None), model._graph())
+        else:
+            params, x0, rate = workloads.headline_cnvm(n) if kind == "h" else workloads.sis_ws(n)
+            model = CNVM(params)
+            models[(kind, n)] = (params, x0, rate, model, model._struct(), model._graph())
     params, x0, rate, model, (struct, keep), graph = models[(kind, n)]
-    M = params.num_opinions
+    M = 2 if kind == "cntm" else params.num_opinions
+    ek = "cntm" if kind == "cntm" else "cnvm"
+    kw = {} if kind == "cntm" else dict(warps_per_chain=wpc)
     t_eval = np.linspace(0, t_max, T)
     d_x0 = torch.as_tensor(x0[None, :], device="cuda")
     spec = (np.arange(M, dtype=np.int32), 1.0)
     tw = time.time()
     while time.time() - tw < 1.0:
-        engine.run_native("cnvm", graph, n, struct, d_x0, t_eval, 1, runs, 0, runs, cv_spec=spec, want_cv=True, warps_per_chain=wpc, force_global_state=glob)
+        engine.run_native(ek, graph, n, struct, d_x0, t_eval, 1, runs, 0, runs, cv_spec=spec, want_cv=True, force_global_state=glob, **kw)
         torch.cuda.synchronize()
     best = None
     for rep in range(3):
@@ -41,8 +48,8 @@ for spec_s in sys.argv[1:]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        engine.run_native("cnvm", graph, n, struct, d_x0, t_eval, 1234 + rep, runs, 0, runs, cv_spec=spec, want_cv=True,
-                          counters=counters, warps_per_chain=wpc, force_global_state=glob)
+        engine.run_native(ek, graph, n, struct, d_x0, t_eval, 1234 + rep, runs, 0, runs, cv_spec=spec, want_cv=True,
+                          counters=counters, force_global_state=glob, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
