@@ -17,6 +17,7 @@
 //   * sum / sum-of-squares over runs are accumulated with integer atomics (exact, order-free).
 // Chains that do not fit in shared memory use the same code on a global-memory state (L2/HBM).
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -451,15 +452,19 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             if (RING) return sp_ring_any(slot + 1, 32 * W, p);
             return __any_sync(FULL, p);
         };
-        // decision of one lane for one step: locations, what it read, what it wants to write
+        // decision of one lane for one step: locations, what it read, what it wants to write.
+        // (The accepted flag lives across loop iterations.  As a bool ptxas packs it into a byte of a shared register
+        // (PRMT in the loop), as a uint32_t it costs a register; which is faster depends on the instantiation --
+        // measured on a B200: H (2-bit, two warps per chain) +4.9 % with the full register, the one-warp-per-chain and
+        // the 1-bit 16-warp kernels +7 % / +6 % with the bool.)
+        using acc_t = typename std::conditional<(BITS == 2 && RING), uint32_t, bool>::type;
         struct Dec {
             uint32_t wa, wn;    // word index of the agent / of the location imitated (own agent for a noise event)
             uint32_t sa, sn;    // bit offsets within those words
             uint32_t word;      // the agent's packed word as read (the compare value of the write)
             uint32_t m, nw;     // opinion read, new opinion
             uint32_t delta;     // THR4: packed count delta of m -> nw
-            bool acc;           // accepted
-            bool lost;          // write phase: another lane changed this agent first, nothing was written
+            acc_t acc;          // accepted
         };
         auto evaluate = [&](int s, bool active, Dec& d) {
             const uint32_t a = q_a[s], nbr = q_nbr[s], meta = q_meta[s];
@@ -478,8 +483,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 d.delta = e.y;
             } else if (THR_SMEM) th = thr[((meta & 1u) ? MM : 0) + d.m * M + d.nw];
             else th = __ldg(thr + ((meta & 1u) ? MM : 0) + d.m * M + d.nw);
-            d.acc = active && sp_thr_accept(q_r3[s], th);
-            d.lost = false;
+            d.acc = (acc_t)(active && sp_thr_accept(q_r3[s], th));
         };
         auto book = [&](int s, const Dec& d) {  // an accepted event m -> nw of this lane
             ++my_acc;
@@ -490,7 +494,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         // Write phase of one step.  A compare-and-swap on the agent's word, retried while only OTHER agents of the
         // word have changed: the first writer of an agent wins, a later one finds the field changed, writes nothing
         // and is flagged (`lost`).  So an agent is written at most once per write phase and writes cannot cancel.
-        auto write = [&](Dec& d) {
+        auto write = [&](const Dec& d) -> bool {  // returns "lost": another lane changed this agent first, nothing written
+            bool lost = false;
             if (d.acc && d.m != d.nw) {
                 const uint32_t x = xmask_of(d);
                 uint32_t expect = d.word;
@@ -498,30 +503,31 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                     const uint32_t old = atomicCAS(state + d.wa, expect, expect ^ x);
                     if (old == expect) break;
                     if (((old >> d.sa) & P::VM) != d.m) {
-                        d.lost = true;
+                        lost = true;
                         break;
                     }
                     expect = old;
                 }
             }
+            return lost;
         };
         // Between the write phase and the read phase.  Shared memory executes accesses in order: a barrier of the
         // chain's warps is enough.  In global memory (W = 1) the atomics are performed at the L2 and a load issued
         // right behind them could overtake them; every writer has consumed the value its atomic returned, so all
         // of them have been performed once the warp has voted.
-        auto settle_writes = [&](const Dec& d) {
+        auto settle_writes = [&](bool lost) {
             if (SMEM) {
                 coop_sync();
             } else {
-                (void)__any_sync(FULL, d.lost);
+                (void)__any_sync(FULL, lost);
                 __threadfence_block();
             }
         };
         // re-reads the lane's two locations: has an input changed (or has the lane lost its write)?
-        auto changed = [&](int s, bool pending, const Dec& d) -> bool {
-            uint32_t chk = (state_load<SMEM>(state + d.wa) >> d.sa) ^ ((d.acc && !d.lost) ? d.nw : d.m);
+        auto changed = [&](int s, bool pending, const Dec& d, bool lost) -> bool {
+            uint32_t chk = (state_load<SMEM>(state + d.wa) >> d.sa) ^ ((d.acc && !lost) ? d.nw : d.m);
             if (!(q_meta[s] & 1u)) chk |= (state_load<SMEM>(state + d.wn) >> d.sn) ^ d.nw;
-            return (pending && (chk & P::VM) != 0u) || d.lost;
+            return (pending && (chk & P::VM) != 0u) || lost;
         };
         // rare path, plain atomics followed by loads of other lanes
         auto settle_plain = [&]() {
@@ -529,12 +535,12 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             coop_sync();
         };
         // The step in set `s` was flagged: roll back, commit the exact prefix, re-run the rest until clean.
-        auto hazard_rounds = [&](int s, bool active, Dec& d, bool bad) {
+        auto hazard_rounds = [&](int s, bool active, Dec& d, bool bad, bool lost) {
             bool pending = active;
 #pragma unroll 1
             for (;;) {
                 const bool writer = d.acc && d.m != d.nw;
-                if (writer && !d.lost) atomicXor(state + d.wa, xmask_of(d));  // roll back
+                if (writer && !lost) atomicXor(state + d.wa, xmask_of(d));  // roll back
                 const uint32_t writers = __ballot_sync(FULL, writer);
                 const uint32_t badm = __ballot_sync(FULL, bad);
                 uint32_t w0 = writers ? vbase + (uint32_t)__ffs(writers) - 1u : 0xffffffffu;
@@ -568,9 +574,9 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                 ++n_extra;
                 evaluate(s, pending, d);  // the remaining positions against the updated state
                 if (RING) coop_sync();    // all reads before anybody writes
-                write(d);
-                settle_writes(d);
-                bad = changed(s, pending, d);
+                lost = write(d);
+                settle_writes(lost);
+                bad = changed(s, pending, d, lost);
                 if (!coop_any(bad)) {
                     if (d.acc) book(s, d);
                     return;
@@ -654,8 +660,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                             // write phase of this step, read phase: verify it, evaluate the next one
                             Dec& cur = dec[u];
                             Dec& nxt = dec[(u + 1) % 3];
-                            write(cur);
-                            settle_writes(cur);
+                            const bool lost = write(cur);
+                            settle_writes(lost);
                             // The draws of the step after the next one sit in the read phase on purpose: its block
                             // holds the shared-memory round trips (re-reads, next decision, threshold), and the
                             // Philox rounds are independent work to issue while those are in flight.
@@ -666,12 +672,12 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                                 issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
                             }
                             e_pre += e_stride;
-                            const bool bad = changed(u, active, cur);
+                            const bool bad = changed(u, active, cur, lost);
                             evaluate((u + 1) % 3, active_next, nxt);
                             if (!coop_any(bad)) {
                                 if (cur.acc) book(u, cur);
                             } else {
-                                hazard_rounds(u, active, cur, bad);
+                                hazard_rounds(u, active, cur, bad, lost);
                                 evaluate((u + 1) % 3, active_next, nxt);  // the state has moved on
                                 if (RING) coop_sync();
                             }

@@ -41,12 +41,29 @@ def _allreduce_device_(tensors: list) -> None:
         o += t.numel()
 
 
-def sweep_pieces(num_points: int, num_runs: int, rank: int, world: int):
-    """Shard of a P x R sweep for one rank: the flattened (point, run) index range split like `_split_runs`, as
-    at most three pieces [(point_begin, point_end, run_begin, run_end)] -- a partial first point, whole points, a
-    partial last point.  P >= world gives (nearly) whole points per rank, P < world splits the runs of a point."""
+def sweep_pieces(num_points: int, num_runs: int, rank: int, world: int, weights=None):
+    """Shard of a P x R sweep for one rank: a contiguous range of the flattened (point, run) index, as at most
+    three pieces [(point_begin, point_end, run_begin, run_end)] -- a partial first point, whole points, a partial
+    last point.  Without ``weights`` the range is cut like `_split_runs` (equal numbers of chains); with
+    ``weights`` (cost of one run of every point, e.g. its event rate) the cuts fall at equal shares of the
+    total COST, so that ranks whose points are cheap take more of them -- the all-reduce then does not wait for
+    the rank that drew the expensive corner of the grid.  P >= world gives (nearly) whole points per rank,
+    P < world splits the runs of a point."""
     total = num_points * num_runs
-    b = np.concatenate(([0], np.cumsum(_split_runs(total, world))))
+    if weights is None:
+        b = np.concatenate(([0], np.cumsum(_split_runs(total, world))))
+    else:
+        w = np.asarray(weights, dtype=np.float64)
+        cum = np.concatenate(([0.0], np.cumsum(w * num_runs)))  # cost up to the start of every point
+        b = [0]
+        for k in range(1, world):
+            target = cum[-1] * k / world
+            pt = int(np.searchsorted(cum, target, side="right") - 1)
+            pt = min(max(pt, 0), num_points - 1)
+            run = int(round((target - cum[pt]) / w[pt])) if w[pt] > 0 else 0
+            b.append(max(b[-1], min(total, pt * num_runs + min(max(run, 0), num_runs))))
+        b.append(total)
+        b = np.asarray(b)
     lo, hi = int(b[rank]), int(b[rank + 1])
     pieces = []
     while lo < hi:
@@ -136,7 +153,9 @@ def sample_moments_sweep(
     d_x0 = torch.as_tensor(x0, device=dev)
     graph = model._graph()
     t0 = time.perf_counter()
-    for (pb, pe, rb, re) in sweep_pieces(P, num_runs, rank, world):
+    weights = [(q.r_imit * float(np.sum(da)) + q.r_noise * N) if p0.network is not None
+               else N * (q.r_imit * float(da[0]) + q.r_noise) for q in params_list]  # events per unit time of a run
+    for (pb, pe, rb, re) in sweep_pieces(P, num_runs, rank, world, weights):
         h = None if not hist_bins else engine.Histogram(hist_bins, lo, width, hist_t[pb:pe])
         engine.run_native_sweep(graph, N, structs[pb:pe], d_x0, t, seed, num_runs, rb, re, cv_spec=spec,
                                 sums=(sums[0, pb:pe], sums[1, pb:pe]), hist=h, chain_offset=pb * num_runs)

@@ -99,6 +99,18 @@ def test_sweep_pieces_cover_every_item_once():
         assert (seen == 1).all(), (P, R, world)
     # 256 points on 8 ranks: whole points only, 32 each
     assert sweep_pieces(256, 100000, 3, 8) == [(96, 128, 0, 100000)]
+    # cost-weighted cuts: every (point, run) still exactly once, and the ranks' costs are balanced
+    rng = np.random.default_rng(0)
+    for P, R, world in [(256, 1000, 8), (7, 50, 3), (2, 9, 5)]:
+        w = rng.uniform(0.5, 2.0, P)
+        seen = np.zeros((P, R), dtype=int)
+        cost = np.zeros(world)
+        for rank in range(world):
+            for (pb, pe, r0, r1) in sweep_pieces(P, R, rank, world, w):
+                seen[pb:pe, r0:r1] += 1
+                cost[rank] += w[pb:pe].sum() * (r1 - r0)
+        assert (seen == 1).all(), (P, R, world)
+        assert cost.max() - cost.min() <= 2.1 * w.max(), (cost, P, R, world)  # within a run or two of each other
 
 
 def test_two_rank_gloo_sharding(tmp_path):
