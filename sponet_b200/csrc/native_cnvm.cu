@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         // (PRMT in the loop), as a uint32_t it costs a register; which is faster depends on the instantiation --
         // measured on a B200: H (2-bit, two warps per chain) +4.9 % with the full register, the one-warp-per-chain and
         // the 1-bit 16-warp kernels +7 % / +6 % with the bool.)
-        using acc_t = typename std::conditional<(BITS == 2 && RING), uint32_t, bool>::type;
+        constexpr bool FLAGS_IN_DEC = !(BITS == 2 && RING);  // bool acc + bool lost inside Dec, or uint32_t acc + a local
+        using acc_t = typename std::conditional<FLAGS_IN_DEC, bool, uint32_t>::type;
         struct Dec {
             uint32_t wa, wn;    // word index of the agent / of the location imitated (own agent for a noise event)
             uint32_t sa, sn;    // bit offsets within those words
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             uint32_t m, nw;     // opinion read, new opinion
             uint32_t delta;     // THR4: packed count delta of m -> nw
             acc_t acc;          // accepted
+            bool lost;          // (FLAGS_IN_DEC) write phase: another lane changed this agent first, nothing was written
         };
         auto evaluate = [&](int s, bool active, Dec& d) {
             const uint32_t a = q_a[s], nbr = q_nbr[s], meta = q_meta[s];
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             } else if (THR_SMEM) th = thr[((meta & 1u) ? MM : 0) + d.m * M + d.nw];
             else th = __ldg(thr + ((meta & 1u) ? MM : 0) + d.m * M + d.nw);
             d.acc = (acc_t)(active && sp_thr_accept(q_r3[s], th));
+            if (FLAGS_IN_DEC) d.lost = false;
         };
         auto book = [&](int s, const Dec& d) {  // an accepted event m -> nw of this lane
             ++my_acc;
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         // Write phase of one step.  A compare-and-swap on the agent's word, retried while only OTHER agents of the
         // word have changed: the first writer of an agent wins, a later one finds the field changed, writes nothing
         // and is flagged (`lost`).  So an agent is written at most once per write phase and writes cannot cancel.
-        auto write = [&](const Dec& d) -> bool {  // returns "lost": another lane changed this agent first, nothing written
+        auto write = [&](Dec& d) -> bool {  // returns "lost": another lane changed this agent first, nothing written
             bool lost = false;
             if (d.acc && d.m != d.nw) {
                 const uint32_t x = xmask_of(d);
@@ -503,13 +506,14 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
                     const uint32_t old = atomicCAS(state + d.wa, expect, expect ^ x);
                     if (old == expect) break;
                     if (((old >> d.sa) & P::VM) != d.m) {
-                        lost = true;
+                        if (FLAGS_IN_DEC) d.lost = true;
+                        else lost = true;
                         break;
                     }
                     expect = old;
                 }
             }
-            return lost;
+            return FLAGS_IN_DEC ? d.lost : lost;
         };
         // Between the write phase and the read phase.  Shared memory executes accesses in order: a barrier of the
         // chain's warps is enough.  In global memory (W = 1) the atomics are performed at the L2 and a load issued
@@ -524,7 +528,8 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             }
         };
         // re-reads the lane's two locations: has an input changed (or has the lane lost its write)?
-        auto changed = [&](int s, bool pending, const Dec& d, bool lost) -> bool {
+        auto changed = [&](int s, bool pending, const Dec& d, bool lost_arg) -> bool {
+            const bool lost = FLAGS_IN_DEC ? d.lost : lost_arg;
             uint32_t chk = (state_load<SMEM>(state + d.wa) >> d.sa) ^ ((d.acc && !lost) ? d.nw : d.m);
             if (!(q_meta[s] & 1u)) chk |= (state_load<SMEM>(state + d.wn) >> d.sn) ^ d.nw;
             return (pending && (chk & P::VM) != 0u) || lost;
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
 #pragma unroll 1
             for (;;) {
                 const bool writer = d.acc && d.m != d.nw;
-                if (writer && !lost) atomicXor(state + d.wa, xmask_of(d));  // roll back
+                if (writer && !(FLAGS_IN_DEC ? d.lost : lost)) atomicXor(state + d.wa, xmask_of(d));  // roll back
                 const uint32_t writers = __ballot_sync(FULL, writer);
                 const uint32_t badm = __ballot_sync(FULL, bad);
                 uint32_t w0 = writers ? vbase + (uint32_t)__ffs(writers) - 1u : 0xffffffffu;

@@ -1,0 +1,4 @@
+cd $GRAFT_REPO_ROOT
+export PYTHONPATH=$PWD
+python tools/probe_multi.py 100000:10000:10:101:0 10000:10000:10:100:0 10000:2368:10:100:1 sis:1000000:2368:1:11:0 100000:1250:10:101:0
+timeout 600 python -m pytest tests/test_gpu_fuzz.py tests/test_gpu_native.py -m gpu -q -x 2>&1 | tail -2
