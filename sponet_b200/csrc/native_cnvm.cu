@@ -33,8 +33,9 @@ struct NativeCnvmArgs {
     const uint2* alias_tab;  // (threshold, alias) per agent; nullptr = uniform agent weights
     const uint32_t* thr;  // [P][2*M*M]: imitation thresholds, then noise thresholds
     int32_t param_stride;  // 0: one parameter set for all initial states; 1: parameter set j for state slot j (sweep)
-    const uint8_t* x_init;
-    int64_t x_stride;      // n, or 0 when all state slots share one initial state (sweep)
+    const uint32_t* x_packed;  // [Sx, words] initial states bit-packed once per call (pack_states_kernel)
+    const int32_t* cnt_init;   // [Sx, cnt_stride] their opinion (x class) counts
+    int64_t x_stride;          // 1, or 0 when all state slots share one initial state (sweep): index into the two above
     const int64_t* counts;  // [S*nrun, T-1]
     int64_t S, nrun, R_total, run_begin;
     int64_t cl_begin, cl_end;  // local chains [cl_begin, cl_end) of the S * nrun of the call run in this launch
@@ -129,6 +130,38 @@ __device__ __forceinline__ bool sp_ring_any(int id, int threads, bool pred) {
     return r != 0u;
 }
 
+// Bit-packs the initial states once per call and counts their opinions (per class and with the integer weights of a
+// grouped CV): a chain then starts with a copy of `words` 32-bit words instead of reading N bytes -- at N = 1e5 a
+// tenth of the traffic, which matters when chains are short (parameter sweeps, steady-state rounds: ~1e5 events per
+// chain against 1e5 bytes of initial state).  Values >= M (device-resident inputs are not range-checked on the host)
+// are clamped so that they can never spill into a neighbour's bits or another chain's counters.
+template <int BITS>
+__global__ void pack_states_kernel(const uint8_t* x, int64_t num_states, int64_t n, int M, int32_t words, const int2* cw,
+                                   int32_t cnt_stride, uint32_t* packed, int32_t* cnt) {
+    using P = Pack<BITS>;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    for (int64_t j = blockIdx.y; j < num_states; j += gridDim.y) {
+    const uint8_t* x0 = x + j * n;
+    uint32_t out = 0;
+    const uint32_t base = (uint32_t)w * P::APW;
+    for (int q = 0; q < P::APW; ++q) {
+        const uint32_t a = base + q;
+        if (a < (uint32_t)n) {
+            const uint32_t v = min((uint32_t)x0[a], (uint32_t)(M - 1));
+            out |= v << (q * BITS);
+            if (cw) {
+                const int2 c = cw[a];
+                atomicAdd(cnt + j * cnt_stride + c.x * M + v, c.y);
+            } else {
+                atomicAdd(cnt + j * cnt_stride + v, 1);
+            }
+        }
+    }
+    packed[j * words + w] = out;
+    }
+}
+
 // GRAPH: 0 = complete graph (no gather), 1 = CSR (row gather, then column gather), 2 = neighbour sampler
 // table (one gather; bounded-degree graphs whose table fits L2)
 template <int BITS, bool SMEM, int GRAPH, bool ALIAS, bool RING>
@@ -192,7 +225,6 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
         const int64_t j = cl / A.nrun, i = cl - j * A.nrun;
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
-        const uint8_t* x0 = A.x_init + j * A.x_stride;
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
         // the chain's parameter set: noise-branch threshold, acceptance tables (staged per chain slot)
         const int64_t pset = j * A.param_stride;
@@ -215,51 +247,13 @@ __global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(Nat
             }
         }
 
-        // ---- load + pack the initial state, count opinions ----
-        if (role == 0)
-            for (int v = lane; v < A.cnt_stride; v += 32) cnt_mem[v] = 0;
-        if (RING) sp_ring_sync(slot + 1, 32 * W);
-        else __syncwarp();
+        // ---- the initial state: packed once per call (pack_states_kernel), copied per chain ----
         {
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            for (int w = role * 32 + lane; w < A.words; w += 32 * W) {
-                uint32_t packed = 0;
-                const uint32_t base = (uint32_t)w * P::APW;
-#pragma unroll 4
-                for (int q = 0; q < P::APW; ++q) {
-                    const uint32_t a = base + q;
-                    if (a < n) {
-                        // (host inputs are range-checked by sponet_cnvm_run; a device-resident x_init is clamped so
-                        // that a bad value can never spill into a neighbour's bits or another chain's counters)
-                        const uint32_t v = min((uint32_t)x0[a], (uint32_t)(M - 1));
-                        packed |= v << (q * BITS);
-                        if (PACKCNT) {
-                            c0 += (v == 0);
-                            c1 += (v == 1);
-                            c2 += (v == 2);
-                            c3 += (v == 3);
-                        } else if (A.cw) {
-                            const int2 cw = __ldg(A.cw + a);
-                            atomicAdd(&cnt_mem[cw.x * M + v], cw.y);
-                        } else {
-                            atomicAdd(&cnt_mem[v], 1);
-                        }
-                    }
-                }
-                state[w] = packed;
-            }
-            if (PACKCNT) {
-                c0 = __reduce_add_sync(FULL, c0);
-                c1 = __reduce_add_sync(FULL, c1);
-                c2 = __reduce_add_sync(FULL, c2);
-                c3 = __reduce_add_sync(FULL, c3);
-                if (lane == 0) {
-                    atomicAdd(&cnt_mem[0], c0);
-                    if (M > 1) atomicAdd(&cnt_mem[1], c1);
-                    if (M > 2) atomicAdd(&cnt_mem[2], c2);
-                    if (M > 3) atomicAdd(&cnt_mem[3], c3);
-                }
-            }
+            const int64_t jx = j * A.x_stride;
+            const uint32_t* src = A.x_packed + jx * A.words;
+            for (int w = role * 32 + lane; w < A.words; w += 32 * W) state[w] = __ldg(src + w);
+            if (role == 0)
+                for (int v = lane; v < A.cnt_stride; v += 32) cnt_mem[v] = __ldg(A.cnt_init + jx * A.cnt_stride + v);
         }
         if (!SMEM) __threadfence_block();
         if (RING) sp_ring_sync(slot + 1, 32 * W);
@@ -1149,7 +1143,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     }
     SP_TRY(stage_thresholds(sc, p, P, noise_prob, &A.thr, &A.noise_thr));
     A.param_stride = sweep ? 1 : 0;
-    A.x_stride = x_shared ? 0 : n;
+    A.x_stride = x_shared ? 0 : 1;
     SpCvDev cvd;
     SP_TRY(sp_stage_cv(sc, cv, M, &cvd, n));
     A.D = cvd.D;
@@ -1176,7 +1170,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
         A.rk[2 * r + 1] = (uint32_t)(o->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
 
-    SP_CUDA(sc.in(x_init, (size_t)(x_shared ? 1 : S) * n, &A.x_init));
+    const uint8_t* d_x_init;
+    SP_CUDA(sc.in(x_init, (size_t)(x_shared ? 1 : S) * n, &d_x_init));
     const double* d_t;
     SP_CUDA(sc.in(t_eval, (size_t)T, &d_t));
     // interval schedule
@@ -1211,6 +1206,24 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     // thresholds + [reduction words] + counters + packed states.
     const int bits = M <= 2 ? 1 : M <= 4 ? 2 : M <= 16 ? 4 : 8;
     A.words = (int32_t)((n * bits + 31) / 32);
+    {   // pack the initial states and count their opinions, once per call
+        const int64_t Sx = x_shared ? 1 : S;
+        uint32_t* d_packed;
+        int32_t* d_cnt;
+        SP_CUDA(sc.alloc((void**)&d_packed, (size_t)Sx * A.words * sizeof(uint32_t)));
+        SP_CUDA(sc.alloc((void**)&d_cnt, (size_t)Sx * A.cnt_stride * sizeof(int32_t)));
+        SP_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)Sx * A.cnt_stride * sizeof(int32_t), sc.stream));
+        const dim3 pgrid((unsigned)((A.words + 255) / 256), (unsigned)std::min<int64_t>(Sx, 65535));
+        switch (bits) {
+            case 1: pack_states_kernel<1><<<pgrid, 256, 0, sc.stream>>>(d_x_init, Sx, n, M, A.words, A.cw, A.cnt_stride, d_packed, d_cnt); break;
+            case 2: pack_states_kernel<2><<<pgrid, 256, 0, sc.stream>>>(d_x_init, Sx, n, M, A.words, A.cw, A.cnt_stride, d_packed, d_cnt); break;
+            case 4: pack_states_kernel<4><<<pgrid, 256, 0, sc.stream>>>(d_x_init, Sx, n, M, A.words, A.cw, A.cnt_stride, d_packed, d_cnt); break;
+            default: pack_states_kernel<8><<<pgrid, 256, 0, sc.stream>>>(d_x_init, Sx, n, M, A.words, A.cw, A.cnt_stride, d_packed, d_cnt); break;
+        }
+        SP_CUDA(cudaGetLastError());
+        A.x_packed = d_packed;
+        A.cnt_init = d_cnt;
+    }
     SpDeviceLimits prop;
     SP_CUDA(sp_device_limits(dev, &prop));
     const size_t smem_max = prop.sharedMemPerBlockOptin;

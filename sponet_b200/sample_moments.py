@@ -153,8 +153,10 @@ def sample_moments_sweep(
     d_x0 = torch.as_tensor(x0, device=dev)
     graph = model._graph()
     t0 = time.perf_counter()
-    weights = [(q.r_imit * float(np.sum(da)) + q.r_noise * N) if p0.network is not None
-               else N * (q.r_imit * float(da[0]) + q.r_noise) for q in params_list]  # events per unit time of a run
+    # cost of one run of every point: its expected events plus a fixed part per chain (copy of the packed initial
+    # state, T snapshots; ~0.03 N event-equivalents, measured on the 256-point sweep of config 5)
+    weights = [((q.r_imit * float(np.sum(da)) + q.r_noise * N) if p0.network is not None
+                else N * (q.r_imit * float(da[0]) + q.r_noise)) * float(t_max) + 0.03 * N for q in params_list]
     for (pb, pe, rb, re) in sweep_pieces(P, num_runs, rank, world, weights):
         h = None if not hist_bins else engine.Histogram(hist_bins, lo, width, hist_t[pb:pe])
         engine.run_native_sweep(graph, N, structs[pb:pe], d_x0, t, seed, num_runs, rb, re, cv_spec=spec,
