@@ -164,8 +164,13 @@ __global__ void pack_states_kernel(const uint8_t* x, int64_t num_states, int64_t
 
 // GRAPH: 0 = complete graph (no gather), 1 = CSR (row gather, then column gather), 2 = neighbour sampler
 // table (one gather; bounded-degree graphs whose table fits L2)
-template <int BITS, bool SMEM, int GRAPH, bool ALIAS, bool RING>
-__global__ void __launch_bounds__(SP_RING_MAX_THREADS, 1) cnvm_native_kernel(NativeCnvmArgs A) {
+// MAXT: threads per CTA the kernel is compiled for.  512 (16 warps, up to 128 registers) is the default; the COOP
+// kernels also exist for 576 threads (18 warps, 96 registers: the register file is per scheduler, a fifth warp on a
+// scheduler leaves 102 per thread), which lets a NINTH chain of workload H run with two warps like the other eight.
+// Per SM that is 2 % slower than 8 x 2, but 1 332 resident chains instead of 1 184 save a whole wave when the chain
+// count falls just above a multiple of 1 184 (1 250 chains per GPU when 8 GPUs share 1e4 realizations: +19 %).
+template <int BITS, bool SMEM, int GRAPH, bool ALIAS, bool RING, int MAXT = SP_RING_MAX_THREADS>
+__global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
     constexpr bool THR4 = (BITS <= 2);      // M <= 4: threshold table padded to 4 x 4 per branch
     // M <= 4 and plain counts: count deltas packed per lane, folded lazily; a grouped / weighted CV
@@ -1003,34 +1008,39 @@ namespace {
 typedef void (*cnvm_kernel_t)(NativeCnvmArgs);
 
 #ifdef SP_FAST_BUILD  // development builds: only the kernels of workload H (2-bit states in shared memory, sampler table)
-cnvm_kernel_t pick_cnvm_kernel(int, bool, int, bool, bool ring) {
+cnvm_kernel_t pick_cnvm_kernel(int, bool, int, bool, bool ring, bool wide) {
+    if (ring && wide) return cnvm_native_kernel<2, true, 2, false, true, 576>;
     return ring ? cnvm_native_kernel<2, true, 2, false, true> : cnvm_native_kernel<2, true, 2, false, false>;
 }
 #else
 template <int BITS, bool SMEM, int GRAPH>
-cnvm_kernel_t pick_cnvm(bool alias, bool ring) {
+cnvm_kernel_t pick_cnvm(bool alias, bool ring, bool wide) {
+    // the 576-thread build exists for the COOP kernels on networks (shared-memory states)
+    if (SMEM && GRAPH != 0 && ring && wide)
+        return alias ? cnvm_native_kernel<BITS, SMEM, GRAPH, true, SMEM, (SMEM && GRAPH != 0) ? 576 : SP_RING_MAX_THREADS>
+                     : cnvm_native_kernel<BITS, SMEM, GRAPH, false, SMEM, (SMEM && GRAPH != 0) ? 576 : SP_RING_MAX_THREADS>;
     if (SMEM && ring) return alias ? cnvm_native_kernel<BITS, SMEM, GRAPH, true, SMEM> : cnvm_native_kernel<BITS, SMEM, GRAPH, false, SMEM>;
     return alias ? cnvm_native_kernel<BITS, SMEM, GRAPH, true, false> : cnvm_native_kernel<BITS, SMEM, GRAPH, false, false>;
 }
 
 template <int BITS, bool SMEM>
-cnvm_kernel_t pick_cnvm_g(int graph, bool alias, bool ring) {
-    if (graph == 2) return pick_cnvm<BITS, SMEM, 2>(alias, ring);
-    if (graph == 1) return pick_cnvm<BITS, SMEM, 1>(alias, ring);
-    return pick_cnvm<BITS, SMEM, 0>(alias, ring);
+cnvm_kernel_t pick_cnvm_g(int graph, bool alias, bool ring, bool wide) {
+    if (graph == 2) return pick_cnvm<BITS, SMEM, 2>(alias, ring, wide);
+    if (graph == 1) return pick_cnvm<BITS, SMEM, 1>(alias, ring, wide);
+    return pick_cnvm<BITS, SMEM, 0>(alias, ring, false);
 }
 
 template <int BITS>
-cnvm_kernel_t pick_cnvm_b(bool smem, int graph, bool alias, bool ring) {
-    return smem ? pick_cnvm_g<BITS, true>(graph, alias, ring) : pick_cnvm_g<BITS, false>(graph, alias, false);
+cnvm_kernel_t pick_cnvm_b(bool smem, int graph, bool alias, bool ring, bool wide) {
+    return smem ? pick_cnvm_g<BITS, true>(graph, alias, ring, wide) : pick_cnvm_g<BITS, false>(graph, alias, false, false);
 }
 
-cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, int graph, bool alias, bool ring) {
+cnvm_kernel_t pick_cnvm_kernel(int bits, bool smem, int graph, bool alias, bool ring, bool wide) {
     switch (bits) {
-        case 1: return pick_cnvm_b<1>(smem, graph, alias, ring);
-        case 2: return pick_cnvm_b<2>(smem, graph, alias, ring);
-        case 4: return pick_cnvm_b<4>(smem, graph, alias, ring);
-        default: return pick_cnvm_b<8>(smem, graph, alias, ring);
+        case 1: return pick_cnvm_b<1>(smem, graph, alias, ring, wide);
+        case 2: return pick_cnvm_b<2>(smem, graph, alias, ring, wide);
+        case 4: return pick_cnvm_b<4>(smem, graph, alias, ring, wide);
+        default: return pick_cnvm_b<8>(smem, graph, alias, ring, wide);
     }
 }
 #endif
@@ -1232,12 +1242,12 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     const size_t thr_bytes = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);  // per chain slot
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
     const size_t per_slot_min = cnt_bytes + 16 + thr_bytes;      // + the reduction words of a COOP chain
-    const int max_warps = SP_RING_MAX_THREADS / 32;
     const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
     // Launches the local chains [c0, c1) with the geometry that suits their number; returns the chains one wave
     // of that geometry holds (resident chain slots on the whole device).
-    auto launch_range = [&](int64_t c0, int64_t c1, bool launch, int64_t* wave) -> int {
+    auto launch_range = [&](int64_t c0, int64_t c1, bool wide, bool launch, int64_t* wave, int* wpc_out) -> int {
         const int64_t count = c1 - c0;
+        const int max_warps = (wide ? 576 : SP_RING_MAX_THREADS) / 32;
         bool smem_state = !o->force_global_state;
         int slots = 0;
         if (smem_state) {
@@ -1273,6 +1283,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
                 }
             }
             if (wpc > 1 && slots > 15) slots = 15;
+            // the 18-warp build exists for the COOP kernels only
+            if (wpc == 1 && slots > SP_RING_MAX_THREADS / 32) slots = SP_RING_MAX_THREADS / 32;
         } else {
             slots = 8;
         }
@@ -1286,7 +1298,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
                             (smem_state ? (size_t)slots * chain_bytes : 0);
         B.warps_per_cta = warps;
         const int threads = warps * 32;
-        cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, graph_kind, A.alias_tab != nullptr, pair);
+        if (wpc_out) *wpc_out = wpc;
+        cnvm_kernel_t kern = pick_cnvm_kernel(bits, smem_state, graph_kind, A.alias_tab != nullptr, pair, wide && warps > 16);
         SP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         int blocks_per_sm = 1;
         SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem_bytes));
@@ -1304,15 +1317,47 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     // slots would leave most of the device idle for a whole wave (1250 chains on 1184 slots: two waves for the work
     // of 1.06): that remainder runs as a launch of its own, whose geometry gives every chain more warps.  Explicit
     // warps_per_chain (tests, A/B runs) keeps the single launch.
-    int64_t wave = 0;
-    SP_TRY(launch_range(0, num_chains, false, &wave));  // geometry of the whole call
-    int64_t tail_begin = num_chains;
-    if (o->warps_per_chain == 0 && !o->force_global_state && num_chains > wave && wave > 0) {
-        const int64_t full = num_chains / wave * wave, rem = num_chains - full;
-        if (rem > 0 && 4 * rem < 3 * wave) tail_begin = full;
+    // Two plans: 16 warps per CTA, or (COOP kernels on networks) 18.  Each is a number of full waves plus a tail
+    // launch; times are estimated in units of one 16-warp wave -- an 18-warp wave takes 1.15x as long (measured on H:
+    // 30.3 vs 26.3 ms), a tail whose chains have W warps instead of 2 runs about {3: 0.74, 4: 0.6, >= 8: 0.45} of a
+    // wave -- and the cheaper plan is taken.
+    auto plan = [&](bool wide, int64_t* tail_begin, double* cost) -> int {
+        int64_t wave = 0;
+        int wpc_main = 1, wpc_tail = 1;
+        SP_TRY(launch_range(0, num_chains, wide, false, &wave, &wpc_main));  // geometry of the whole call
+        *tail_begin = num_chains;
+        double t = (double)((num_chains + wave - 1) / std::max<int64_t>(wave, 1));
+        if (o->warps_per_chain == 0 && !o->force_global_state && num_chains > wave && wave > 0) {
+            const int64_t full = num_chains / wave * wave, rem = num_chains - full;
+            if (rem > 0 && 4 * rem < 3 * wave) {
+                *tail_begin = full;
+                SP_TRY(launch_range(full, num_chains, wide, false, nullptr, &wpc_tail));
+                const double ratio = (double)wpc_tail / (double)std::max(wpc_main, 1);
+                const double tail = ratio >= 4.0 ? 0.45 : ratio >= 2.0 ? 0.6 : ratio >= 1.5 ? 0.74 : 1.0;
+                t = (double)(full / wave) + tail;
+            }
+        }
+        *cost = t * (wide ? 1.15 : 1.0);
+        return SPONET_OK;
+    };
+    int64_t tail_begin = num_chains, tail_wide = num_chains;
+    double cost = 0.0, cost_wide = 1e300;
+    SP_TRY(plan(false, &tail_begin, &cost));
+    bool wide = false;
+    if (o->warps_per_chain == 0 && !o->force_global_state && graph_kind != 0) {
+        int64_t wave_n = 0, wave_w = 0;
+        SP_TRY(launch_range(0, num_chains, false, false, &wave_n, nullptr));
+        SP_TRY(launch_range(0, num_chains, true, false, &wave_w, nullptr));
+        if (wave_w > wave_n) {  // the two extra warps buy resident chains (not just warps per chain)
+            SP_TRY(plan(true, &tail_wide, &cost_wide));
+            if (cost_wide < cost) {
+                wide = true;
+                tail_begin = tail_wide;
+            }
+        }
     }
-    SP_TRY(launch_range(0, tail_begin, true, nullptr));
-    SP_TRY(launch_range(tail_begin, num_chains, true, nullptr));
+    SP_TRY(launch_range(0, tail_begin, wide, true, nullptr, nullptr));
+    SP_TRY(launch_range(tail_begin, num_chains, wide, true, nullptr, nullptr));
     SP_CUDA(sc.finish());
     return SPONET_OK;
 }
