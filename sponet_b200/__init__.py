@@ -18,7 +18,7 @@ from .collective_variables import (
 )
 from .engine import set_default_mode
 from .multiprocessing import sample_many_runs
-from .parameters import Parameters, load_params, save_params
+from .parameters import Parameters
 from .sample_moments import sample_histogram, sample_moments, sample_moments_sweep
 from .states import sample_states_target_shares, sample_states_uniform, sample_states_uniform_shares
 from .steady_state import estimate_steady_state
@@ -27,7 +27,7 @@ from .stochastic_approximation import sample_stochastic_approximation
 __all__ = [
     "CNTM", "CNTMParameters", "CNVM", "CNVMParameters", "CollectiveVariable",
     "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "Interfaces", "OpinionShares",
-    "OpinionSharesByDegree", "Parameters", "Propensities", "load_params", "save_params", "sample_many_runs",
+    "OpinionSharesByDegree", "Parameters", "Propensities", "sample_many_runs",
     "sample_moments", "sample_moments_sweep", "sample_histogram", "estimate_steady_state", "set_default_mode", "sample_states_uniform", "sample_states_uniform_shares",
     "sample_states_target_shares", "sample_stochastic_approximation",
 ]

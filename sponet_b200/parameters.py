@@ -1,20 +1,13 @@
-"""Parameter protocol and pickle helpers (reference: sponet/parameters.py)."""
+"""Parameter protocol shared by the CNVM and CNTM parameter classes (reference: sponet/parameters.py:1-20).
+
+The reference's pickle helpers (`save_params` / `load_params`) are out of scope: parameter
+objects here are plain dataclasses and pickle like any other.
+"""
 from __future__ import annotations
 
-import pickle
 from typing import Protocol
 
 
 class Parameters(Protocol):
     num_opinions: int
     num_agents: int
-
-
-def save_params(filename: str, params: Parameters) -> None:
-    with open(filename, "wb") as fh:
-        pickle.dump(params, fh)
-
-
-def load_params(filename: str) -> Parameters:
-    with open(filename, "rb") as fh:
-        return pickle.load(fh)
