@@ -309,6 +309,44 @@ def test_headline_size_pair_vs_single_and_conservation(oracle):
     del keep
 
 
+def test_launch_plans_agree_on_h(oracle):
+    """The launch policy picks its plan from the chain count: 1 250 chains of H run as ONE wave of the 576-thread
+    build (9 chains x 2 warps per SM), 1 500 as a full 16-warp wave plus a separate last-wave launch with more warps
+    per chain.  Both must equal the plain one-warp-per-chain launch bit for bit (CVs, moment sums, counters), and a
+    chain from the tail of each against the sequential oracle."""
+    from sponet_b200 import CNVM, _lib, engine, workloads
+
+    params, x0, rate = workloads.headline_cnvm(100_000)
+    model = CNVM(params)
+    struct, keep = model._struct()
+    n, T = 100_000, 4
+    t_eval = np.linspace(0, 0.15, T)
+    spec = (np.arange(3, dtype=np.int32), 1.0)
+    rp, col = oracle.neighbor_list_to_csr(params.network)
+    _, noise_p = model.event_rates()
+    nbtab, nblg = _nbtab(oracle, model, rp, col)
+    for R in (1250, 1500):
+        res = {}
+        for wpc in (1, 0):
+            counters = np.zeros(4, dtype=np.uint64)
+            sums = (np.zeros((1, T, 3), dtype=np.int64), np.zeros((1, T, 3), dtype=np.int64))
+            _, cv = engine.run_native("cnvm", model._graph(), n, struct, x0[None, :], t_eval, 7, R, 0, R, cv_spec=spec,
+                                      want_cv=True, sums=sums, counters=counters, warps_per_chain=wpc)
+            res[wpc] = (cv[0], sums, counters)
+        np.testing.assert_array_equal(res[1][0], res[0][0])
+        np.testing.assert_array_equal(res[1][1][0], res[0][1][0])
+        np.testing.assert_array_equal(res[1][1][1], res[0][1][1])
+        np.testing.assert_array_equal(res[1][2][:2], res[0][2][:2])
+        sched = np.empty((R, T - 1), dtype=np.int64)
+        _lib.check(_lib.lib().sponet_native_event_counts(7, 0, R, _lib.ptr(t_eval), T, 1.0 / rate, _lib.ptr(sched), None))
+        for i in (R - 1, R - 40):
+            _, oc, _, _ = oracle.cnvm_native(x0, 3, rp, col, int(oracle.prob_to_thr(noise_p)), oracle.prob_to_thr(params.prob_imit),
+                                             oracle.prob_to_thr(params.prob_noise), None, None, sched[i], 7, i, nbtab=nbtab,
+                                             nbtab_log2=nblg)
+            np.testing.assert_array_equal(res[0][0][i], oc.astype(float))
+    del keep
+
+
 def test_config4_sis_ws_1e6_pair_vs_single():
     """BASELINE config 4 shape: SIS-as-CNVM on a Watts-Strogatz ring with N = 1e6 (one chain per SM,
     125 KB of packed state in shared memory).  Pair schedule == single schedule, and the infected share
