@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPONET_ABI_VERSION 3
+#define SPONET_ABI_VERSION 4
 
 enum {
     SPONET_OK = 0,
@@ -79,6 +79,32 @@ int sponet_graph_info(const sponet_graph* g, int64_t* num_agents, int64_t* nnz, 
  * up to 2^-24 per slot.  *log2_slots = -1 when the graph has no table (the kernel then uses the CSR:
  * nbr = col[begin + mulhi(r2, d)]).  `table` (HOST, [n << log2_slots]) may be NULL. */
 int sponet_graph_neighbor_table(const sponet_graph* g, int32_t* log2_slots, uint64_t* table);
+
+/* A BATCH of Erdos-Renyi graphs G(num_agents, p), generated on the device: one graph per chain of the native call
+ * that covers the same (num_states, runs [run_begin, run_end) of num_runs_total) -- chain (state j, run i) runs on
+ * graph index c = j * num_runs_total + i.  Replaces the per-run `update_network()` of the reference
+ * (sponet/cnvm/model.py:95-96 with sponet/network_generator.py:26-85 ErdosRenyiGenerator.__call__, called once per
+ * realization by sponet/multiprocessing.py:173-178), i.e. ~0.7 s of networkx per realization at N = 1e5.
+ * Graph c depends on (seed, c) only: not on the batch it is part of, nor on the number of GPUs.
+ * Construction (restated sequentially by oracle/oracle_native.inc, bit-identical): vertex i owns the pairs (i, j > i);
+ * from j = i repeat j += 1 + floor(log1p(-v) / log1p(-p)), v = 53 random bits * 2^-53, edge {i, j} while j < n; draw k
+ * of vertex i = words (2 (k & 1), 2 (k & 1) + 1) of Philox4x32-10(counter (k >> 1, i, c_lo, c_hi[16] | attempt << 16 |
+ * 3 << 24), key seed).  force_no_isolates = 0: a graph with an isolated vertex is rejected and drawn again (attempt + 1;
+ * SPONET_ERR_INVALID "Timeout. ..." after max_attempts, the reference's RuntimeError :75-78).  force_no_isolates = 1
+ * (reference :446-454): vertices in order, one that is still isolated gets an edge to j = mulhi(word 0 of Philox(counter
+ * (k, i, c_lo, c_hi | 4 << 24)), n), k = 0, 1, ... until j != i.  Rows sorted by neighbour id.
+ * padded_rows != 0 also builds the padded row layout the CNTM kernel scans.
+ * The handle is accepted by sponet_cnvm_run / sponet_cntm_run in native mode (uniform degree_alpha, i.e. alpha = 1; no
+ * degree-weighted and no edge collective variables) when it holds num_states * (run_end - run_begin) graphs, and is
+ * released with sponet_graph_destroy.  num_states * (run_end - run_begin) * num_agents must stay below 2^32.  A caller
+ * that covers the states in blocks adds first_state * num_runs_total to run_begin / run_end (as it adds it to
+ * sponet_native_opts.chain_offset of the run call). */
+int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isolates, uint64_t seed,
+                                 int64_t num_states, int64_t num_runs_total, int64_t run_begin, int64_t run_end,
+                                 int32_t max_attempts, int padded_rows, sponet_graph** out);
+
+/* Graph `slot` of a batch as a host CSR (row_ptr [n+1]; col may be NULL to query row_ptr[n] first). */
+int sponet_graph_batch_get(const sponet_graph* g, int64_t slot, int32_t* row_ptr, int32_t* col, int64_t col_capacity);
 
 /* ---------------------------------------------------------------------------------------------
  * Model parameters as the reference loops receive them

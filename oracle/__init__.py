@@ -461,3 +461,22 @@ def sample_states(n, M, counts, S, seed):
         c = np.ascontiguousarray(np.atleast_2d(counts), dtype=np.int64)
         f(n, M, c.ctypes.data, int(c.shape[0] == 1), S, seed, out)
     return out
+
+
+def er_graph(n, p, seed, c, force_no_isolates=False, max_attempts=64):
+    """oracle_er_graph: graph index c of the device-side Erdos-Renyi generator as (row_ptr, col, attempts)."""
+    f = lib().oracle_er_graph
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int64, C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.c_int32, _i32, _i32, C.c_int64,
+                  C.POINTER(C.c_int32)]
+    row_ptr = np.empty(n + 1, dtype=np.int32)
+    cap = int(max(1024, 2 * (n * (n - 1) * p / 2 + 8 * np.sqrt(n * n * p) + 2 * n)))
+    cap = min(cap, n * (n - 1) + 2 * n)
+    col = np.empty(cap, dtype=np.int32)
+    used = C.c_int32(0)
+    nnz = f(n, float(p), int(bool(force_no_isolates)), seed, c, max_attempts, row_ptr, col, cap, C.byref(used))
+    if nnz == -1:
+        raise RuntimeError("Timeout. Could not generate a graph without isolated vertices.")
+    if nnz < 0:
+        raise RuntimeError("oracle_er_graph: column buffer too small")
+    return row_ptr, col[:nnz].copy(), used.value

@@ -18,6 +18,13 @@ from .collective_variables import (
 )
 from .engine import set_default_mode
 from .multiprocessing import sample_many_runs
+from .network_generator import (
+    BarabasiAlbertGenerator,
+    ErdosRenyiGenerator,
+    NetworkGenerator,
+    RandomRegularGenerator,
+    WattsStrogatzGenerator,
+)
 from .parameters import Parameters
 from .sample_moments import sample_histogram, sample_moments, sample_moments_sweep
 from .states import sample_states_target_shares, sample_states_uniform, sample_states_uniform_shares
@@ -29,6 +36,7 @@ __all__ = [
     "CompositeCollectiveVariable", "DegreeWeightedOpinionShares", "Interfaces", "OpinionShares",
     "OpinionSharesByDegree", "Parameters", "Propensities", "sample_many_runs",
     "sample_moments", "sample_moments_sweep", "sample_histogram", "estimate_steady_state", "set_default_mode", "sample_states_uniform", "sample_states_uniform_shares",
-    "sample_states_target_shares", "sample_stochastic_approximation",
+    "sample_states_target_shares", "sample_stochastic_approximation", "NetworkGenerator", "ErdosRenyiGenerator",
+    "RandomRegularGenerator", "BarabasiAlbertGenerator", "WattsStrogatzGenerator",
 ]
 __version__ = "0.1.0"

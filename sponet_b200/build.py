@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsponet_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 
-SOURCES = ["api.cu", "replay.cu", "native_cnvm.cu", "native_cntm.cu", "cv.cu"]
+SOURCES = ["api.cu", "replay.cu", "native_cnvm.cu", "native_cntm.cu", "cv.cu", "graphgen.cu"]
 HEADERS = ["common.cuh", "sponet_log1p.h", "ziggurat_tables.h", os.path.join("..", "..", "include", "sponet_b200.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

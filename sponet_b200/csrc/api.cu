@@ -154,6 +154,7 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     const bool use_tab = dmin >= 1 && dmax <= 64 && n <= (1 << 20) && ((int64_t)n << lg) * 8 <= ((int64_t)64 << 20);
     sponet_graph* g = new sponet_graph();
     g->d_nbtab = nullptr;
+    g->batch = 1;
     g->nbtab_log2 = use_tab ? lg : 0;
     g->n_col4 = n4;
     g->n = n;

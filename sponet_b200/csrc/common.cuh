@@ -58,6 +58,9 @@ struct sponet_graph {
     // instead of the dependent row -> column pair (see sponet_graph_neighbor_table in the header).
     uint2* d_nbtab;      // [n << nbtab_log2] or nullptr
     int32_t nbtab_log2;
+    // A BATCH of `batch` graphs over the same n agents (graphgen.cu: one graph per chain of a native call):
+    // d_row is [batch * n] with ABSOLUTE 32-bit offsets into the shared d_col / d_col4; no d_row_ptr, no table.
+    int64_t batch;       // 1 for an ordinary graph
 };
 
 // ---------------------------------------------------------------------------------------------

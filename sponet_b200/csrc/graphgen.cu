@@ -1,0 +1,391 @@
+// Batches of Erdős–Rényi graphs G(n, p) generated ON the device, one per chain of a native call.
+//
+// What this replaces: sponet/network_generator.py:26-85 (ErdosRenyiGenerator.__call__: networkx
+// fast_gnp_random_graph, isolates rejected or patched by _unisolate_vertices :446-454) called once per run by
+// cnvm/model.py:95-96 (update_network inside simulate) from sample_many_runs (multiprocessing.py:173-178).
+// On the host that is ~0.7 s per graph at N = 1e5 -- several times the GPU time of the chain itself.
+//
+// The graphs are not networkx's (the reference pins no graph either: its generators draw from a numpy Generator
+// through Python's random module); they are G(n, p) by the same geometric-skip construction, keyed by
+// (seed, graph index, attempt, vertex), so a graph does not depend on the batch it is generated in nor on the
+// number of GPUs.  oracle/oracle_native.inc (oracle_er_graph) restates the construction sequentially; the two
+// agree bit for bit (the logarithm is sponet_log1p.h's, identical on both sides).
+//
+// Construction of graph c, attempt a:
+//   vertex i owns the pairs (i, j), j > i.  Starting from j = i, repeat: v = 53 random bits * 2^-53,
+//   j += 1 + floor(log1p(-v) / log1p(-p)); while j < n: edge {i, j}.  Draw k of vertex i is half of
+//   Philox4x32-10(counter = (k / 2, i, c_lo, c_hi[16] | a[8] << 16 | 3 << 24), key = seed).
+//   Without force_no_isolates a graph with an isolated vertex is rejected and attempt a + 1 is generated
+//   (reference :64-69); with it, vertices 0 .. n-1 are visited in order and one that is (still) isolated gets an
+//   edge to j = floor(u n) != i, u from counter (k, i, c_lo, c_hi | 4 << 24), k = 0, 1, ... until j != i
+//   (reference :446-454).
+//   Rows are sorted by neighbour id.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "sponet_log1p.h"
+
+namespace {
+
+struct ErArgs {
+    int64_t n, count;            // vertices per graph, graphs in the batch
+    int64_t nrun, R_total, run_begin;  // slot b = j * nrun + i  ->  graph index c = j * R_total + run_begin + i
+    double log1mp;               // log1p(-p) (< 0), or 0 for p >= 1 (complete graph)
+    uint64_t seed;
+};
+
+__device__ __forceinline__ uint64_t er_graph_index(const ErArgs& A, int64_t b) {
+    const int64_t j = b / A.nrun, i = b - j * A.nrun;
+    return (uint64_t)(j * A.R_total + A.run_begin + i);
+}
+
+// the upper-triangle neighbours of vertex i of graph c, attempt a: calls f(j) for each, in increasing order
+template <typename F>
+__device__ __forceinline__ void er_row(const ErArgs& A, uint64_t c, uint32_t attempt, int64_t i, F&& f) {
+    const uint32_t c2 = (uint32_t)c, c3 = ((uint32_t)(c >> 32) & 0xFFFFu) | ((attempt & 0xFFu) << 16) | (3u << 24);
+    int64_t j = i;
+    const int64_t n = A.n;
+    for (uint32_t k = 0;; ++k) {
+        const uint4 r = sp_philox4x32_10(k, (uint32_t)i, c2, c3, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t hi = h ? r.z : r.x, lo = h ? r.w : r.y;
+            int64_t skip = 0;
+            if (A.log1mp != 0.0) {
+                const double v = (double)((((uint64_t)hi >> 5) << 26) | ((uint64_t)lo >> 6)) * (1.0 / 9007199254740992.0);
+                const double q = __ddiv_rn(sponet_log1p(-v), A.log1mp);  // >= 0
+                if (!(q < (double)(n - j))) return;                      // beyond the last vertex
+                skip = (int64_t)q;                                        // floor
+            }
+            j += 1 + skip;
+            if (j >= n) return;
+            f(j);
+        }
+    }
+}
+
+__global__ void er_degree_kernel(ErArgs A, const uint8_t* dirty, const uint32_t* attempt, uint32_t* deg) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    const int64_t b = tid / A.n, i = tid - b * A.n;
+    if (!dirty[b]) return;
+    uint32_t* d = deg + b * A.n;
+    uint32_t up = 0;
+    er_row(A, er_graph_index(A, b), attempt[b], i, [&](int64_t j) {
+        ++up;
+        atomicAdd(d + j, 1u);
+    });
+    if (up) atomicAdd(d + i, up);
+}
+
+// isolated vertices per graph (of the dirty slots)
+__global__ void er_isolates_kernel(ErArgs A, const uint8_t* dirty, const uint32_t* deg, uint32_t* isolates) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    const int64_t b = tid / A.n;
+    if (dirty[b] && deg[tid] == 0) atomicAdd(isolates + b, 1u);
+}
+
+// rejected graphs: next attempt, degrees cleared
+__global__ void er_reset_kernel(ErArgs A, const uint8_t* dirty, uint32_t* deg) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    if (dirty[tid / A.n]) deg[tid] = 0;
+}
+
+// force_no_isolates: one warp per graph walks the vertices in order (reference :446-454)
+__global__ void er_patch_kernel(ErArgs A, uint32_t* deg, int2* patch, uint32_t* n_patch, int64_t cap) {
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= A.count) return;
+    uint32_t* d = deg + b * A.n;
+    const uint64_t c = er_graph_index(A, b);
+    uint32_t np = 0;
+    for (int64_t i0 = 0; i0 < A.n; i0 += 32) {
+        const int64_t i = i0 + lane;
+        uint32_t zero = __ballot_sync(0xffffffffu, i < A.n && d[i] == 0);
+        if (lane == 0) {
+            while (zero) {
+                const int64_t v = i0 + __ffs(zero) - 1;
+                zero &= zero - 1;
+                if (d[v] != 0) continue;  // an earlier patch reached it
+                int64_t j = v;
+                for (uint32_t k = 0; j == v; ++k) {
+                    const uint4 r = sp_philox4x32_10(k, (uint32_t)v, (uint32_t)c, ((uint32_t)(c >> 32) & 0xFFFFu) | (4u << 24),
+                                                     (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                    j = (int64_t)__umulhi(r.x, (uint32_t)A.n);
+                }
+                d[v] += 1;
+                d[j] += 1;
+                if ((int64_t)np < cap) patch[b * cap + np] = make_int2((int)v, (int)j);
+                ++np;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) n_patch[b] = np;
+}
+
+__global__ void er_fill_kernel(ErArgs A, const uint32_t* attempt, const uint32_t* off, uint32_t* cursor, int32_t* col) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    const int64_t b = tid / A.n, i = tid - b * A.n;
+    const uint32_t* o = off + b * A.n;
+    uint32_t* cur = cursor + b * A.n;
+    er_row(A, er_graph_index(A, b), attempt[b], i, [&](int64_t j) {
+        col[o[i] + atomicAdd(cur + i, 1u)] = (int32_t)j;
+        col[o[j] + atomicAdd(cur + j, 1u)] = (int32_t)i;
+    });
+}
+
+__global__ void er_fill_patch_kernel(ErArgs A, const int2* patch, const uint32_t* n_patch, int64_t cap, const uint32_t* off,
+                                     uint32_t* cursor, int32_t* col) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * cap) return;
+    const int64_t b = tid / cap, k = tid - b * cap;
+    if (k >= (int64_t)n_patch[b]) return;
+    const int2 e = patch[tid];
+    const uint32_t* o = off + b * A.n;
+    uint32_t* cur = cursor + b * A.n;
+    col[o[e.x] + atomicAdd(cur + e.x, 1u)] = e.y;
+    col[o[e.y] + atomicAdd(cur + e.y, 1u)] = e.x;
+}
+
+// sorts every row (the atomics above fill them in arbitrary order), writes the (begin, degree) descriptors
+__global__ void er_finish_kernel(ErArgs A, const uint32_t* off, const uint32_t* deg, int32_t* col, int2* row,
+                                 uint32_t* dmin, uint32_t* dmax) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tid < A.count * A.n;
+    const uint32_t d = live ? deg[tid] : 0u;
+    int32_t* r = col + (live ? off[tid] : 0u);
+    for (uint32_t a = 1; a < d; ++a) {  // insertion sort: rows are short (np for sparse graphs)
+        const int32_t key = r[a];
+        uint32_t q = a;
+        while (q > 0 && r[q - 1] > key) {
+            r[q] = r[q - 1];
+            --q;
+        }
+        r[q] = key;
+    }
+    if (live) row[tid] = make_int2((int)off[tid], (int)d);
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, live ? d : 0xFFFFFFFFu), hi = __reduce_max_sync(0xffffffffu, d);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(dmin, lo);
+        atomicMax(dmax, hi);
+    }
+}
+
+// padded rows of the whole batch for the row-scanning CNTM kernel: see graph_build_kernel (api.cu)
+__global__ void er_pad_kernel(int64_t rows, int64_t n, const int2* row, const int32_t* col, const uint32_t* off4, int2* row4,
+                              int4* col4) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= rows) return;
+    const int2 r = row[tid];
+    int32_t* dst = reinterpret_cast<int32_t*>(col4 + off4[tid]);
+    const int32_t padded = (r.y + 3) / 4 * 4;
+    const int32_t self = (int32_t)(tid % n);
+    for (int32_t k = 0; k < r.y; ++k) dst[k] = col[(uint32_t)r.x + k];
+    for (int32_t k = r.y; k < padded; ++k) dst[k] = self;
+    row4[tid] = make_int2((int)off4[tid], r.y);
+}
+
+__global__ void quarter_kernel(int64_t rows, const uint32_t* deg, uint32_t* q) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < rows) q[tid] = (deg[tid] + 3) / 4;
+}
+
+__global__ void sum_u32_kernel(int64_t rows, const uint32_t* v, unsigned long long* total) {
+    unsigned long long acc = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows; t += (int64_t)gridDim.x * blockDim.x) acc += v[t];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+
+struct Freer {
+    std::vector<void*> p;
+    ~Freer() {
+        for (void* q : p) cudaFree(q);
+    }
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+        if (e == cudaSuccess) p.push_back(*out);
+        return e;
+    }
+};
+
+}  // namespace
+
+extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isolates, uint64_t seed,
+                                            int64_t num_states, int64_t num_runs_total, int64_t run_begin,
+                                            int64_t run_end, int32_t max_attempts, int padded_rows,
+                                            sponet_graph** out) {
+    SP_REQUIRE(out, "graph_batch_create_er: out is NULL");
+    *out = nullptr;
+    const int64_t n = num_agents, nrun = run_end - run_begin, B = num_states * nrun;
+    SP_REQUIRE(n >= 2 && n < ((int64_t)1 << 31), "graph_batch_create_er: num_agents out of range");
+    SP_REQUIRE(p > 0.0 && p <= 1.0, "graph_batch_create_er: p must be in (0, 1]");
+    SP_REQUIRE(num_states >= 1 && nrun >= 1 && run_begin >= 0 && num_runs_total >= 1, "graph_batch_create_er: bad run range");
+    SP_REQUIRE(B * n < ((int64_t)1 << 32), "graph_batch_create_er: %lld graphs of %lld agents exceed 2^32 rows; use smaller batches",
+               (long long)B, (long long)n);
+    SP_REQUIRE(max_attempts >= 1 && max_attempts <= 256, "graph_batch_create_er: max_attempts must be in [1, 256]");
+    ErArgs A;
+    A.n = n;
+    A.count = B;
+    A.nrun = nrun;
+    A.R_total = num_runs_total;
+    A.run_begin = run_begin;
+    A.log1mp = p >= 1.0 ? 0.0 : log1p(-p);
+    A.seed = seed;
+    const int64_t rows = B * n;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+
+    Freer tmp;
+    uint32_t *d_deg, *d_attempt, *d_iso, *d_off, *d_cursor, *d_mm;
+    uint8_t* d_dirty;
+    SP_CUDA(tmp.alloc((void**)&d_deg, rows * 4));
+    SP_CUDA(tmp.alloc((void**)&d_attempt, B * 4));
+    SP_CUDA(tmp.alloc((void**)&d_iso, B * 4));
+    SP_CUDA(tmp.alloc((void**)&d_dirty, B));
+    SP_CUDA(tmp.alloc((void**)&d_mm, 8));
+    SP_CUDA(cudaMemset(d_deg, 0, rows * 4));
+    SP_CUDA(cudaMemset(d_attempt, 0, B * 4));
+    std::vector<uint8_t> dirty((size_t)B, 1);
+    std::vector<uint32_t> attempt((size_t)B, 0), iso((size_t)B);
+    uint32_t max_iso = 0;
+    for (;;) {
+        SP_CUDA(cudaMemcpy(d_dirty, dirty.data(), B, cudaMemcpyHostToDevice));
+        SP_CUDA(cudaMemset(d_iso, 0, B * 4));
+        er_degree_kernel<<<grid, 256>>>(A, d_dirty, d_attempt, d_deg);
+        er_isolates_kernel<<<grid, 256>>>(A, d_dirty, d_deg, d_iso);
+        SP_CUDA(cudaGetLastError());
+        SP_CUDA(cudaMemcpy(iso.data(), d_iso, B * 4, cudaMemcpyDeviceToHost));
+        bool any = false;
+        for (int64_t b = 0; b < B; ++b) {
+            if (!dirty[b]) continue;
+            if (iso[b] == 0 || force_no_isolates) {
+                dirty[b] = 0;
+                max_iso = std::max(max_iso, iso[b]);
+            } else {
+                if ((int32_t)attempt[b] + 1 >= max_attempts)  // reference :75-78 (a time limit there)
+                    return sponet_fail(SPONET_ERR_INVALID, "Timeout. Could not generate a graph without isolated vertices.");
+                ++attempt[b];
+                any = true;
+            }
+        }
+        if (!any) break;
+        SP_CUDA(cudaMemcpy(d_dirty, dirty.data(), B, cudaMemcpyHostToDevice));
+        SP_CUDA(cudaMemcpy(d_attempt, attempt.data(), B * 4, cudaMemcpyHostToDevice));
+        er_reset_kernel<<<grid, 256>>>(A, d_dirty, d_deg);
+    }
+    int2* d_patch = nullptr;
+    uint32_t* d_npatch = nullptr;
+    const int64_t cap = max_iso;
+    if (cap > 0) {
+        SP_CUDA(tmp.alloc((void**)&d_patch, (size_t)B * cap * sizeof(int2)));
+        SP_CUDA(tmp.alloc((void**)&d_npatch, B * 4));
+        er_patch_kernel<<<(unsigned)((B * 32 + 255) / 256), 256>>>(A, d_deg, d_patch, d_npatch, cap);
+        SP_CUDA(cudaGetLastError());
+    }
+    // row offsets of the whole batch (absolute, 32-bit)
+    uint64_t* d_total;
+    SP_CUDA(tmp.alloc((void**)&d_total, 8));
+    SP_CUDA(cudaMemset(d_total, 0, 8));
+    sum_u32_kernel<<<1184, 256>>>(rows, d_deg, (unsigned long long*)d_total);
+    SP_CUDA(cudaGetLastError());
+    uint64_t nnz = 0;
+    SP_CUDA(cudaMemcpy(&nnz, d_total, 8, cudaMemcpyDeviceToHost));
+    SP_REQUIRE(nnz < ((uint64_t)1 << 32), "graph_batch_create_er: %llu adjacency entries exceed 2^32; use smaller batches", (unsigned long long)nnz);
+    SP_CUDA(tmp.alloc((void**)&d_off, rows * 4));
+    SP_CUDA(tmp.alloc((void**)&d_cursor, rows * 4));
+    SP_CUDA(cudaMemset(d_cursor, 0, rows * 4));
+    {
+        void* d_ws = nullptr;
+        size_t ws = 0;
+        SP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, ws, d_deg, d_off, rows));
+        SP_CUDA(tmp.alloc(&d_ws, ws));
+        SP_CUDA(cub::DeviceScan::ExclusiveSum(d_ws, ws, d_deg, d_off, rows));
+    }
+    sponet_graph* g = new sponet_graph();
+    memset(g, 0, sizeof(*g));
+    g->batch = B;
+    g->n = n;
+    g->nnz = (int64_t)nnz;
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row, rows * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col, std::max<uint64_t>(nnz, 1) * sizeof(int32_t));
+    if (e == cudaSuccess) {
+        er_fill_kernel<<<grid, 256>>>(A, d_attempt, d_off, d_cursor, g->d_col);
+        if (cap > 0)
+            er_fill_patch_kernel<<<(unsigned)((B * cap + 255) / 256), 256>>>(A, d_patch, d_npatch, cap, d_off, d_cursor, g->d_col);
+        const uint32_t mm[2] = {0xFFFFFFFFu, 0u};
+        e = cudaMemcpy(d_mm, mm, 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            er_finish_kernel<<<grid, 256>>>(A, d_off, d_deg, g->d_col, g->d_row, d_mm, d_mm + 1);
+            e = cudaGetLastError();
+        }
+    }
+    uint32_t mm[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(mm, d_mm, 8, cudaMemcpyDeviceToHost);
+    g->min_degree = (int32_t)mm[0];
+    g->max_degree = (int32_t)mm[1];
+    if (e == cudaSuccess && padded_rows) {  // the CNTM kernels' layout
+        uint32_t *d_q, *d_off4;
+        uint64_t n4 = 0;
+        e = tmp.alloc((void**)&d_q, rows * 4);
+        if (e == cudaSuccess) e = tmp.alloc((void**)&d_off4, rows * 4);
+        if (e == cudaSuccess) {
+            quarter_kernel<<<grid, 256>>>(rows, d_deg, d_q);
+            e = cudaMemset(d_total, 0, 8);
+            sum_u32_kernel<<<1184, 256>>>(rows, d_q, (unsigned long long*)d_total);
+            if (e == cudaSuccess) e = cudaMemcpy(&n4, d_total, 8, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && n4 >= ((uint64_t)1 << 31)) {
+                sponet_graph_destroy(g);
+                return sponet_fail(SPONET_ERR_INVALID, "graph_batch_create_er: padded rows exceed 2^31 entries; use smaller batches");
+            }
+            void* d_ws2 = nullptr;
+            size_t ws2 = 0;
+            if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, ws2, d_q, d_off4, rows);
+            if (e == cudaSuccess) e = tmp.alloc(&d_ws2, ws2);
+            if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_ws2, ws2, d_q, d_off4, rows);
+        }
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row4, rows * sizeof(int2));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col4, std::max<uint64_t>(n4, 1) * sizeof(int4));
+        if (e == cudaSuccess) {
+            g->n_col4 = (int64_t)n4;
+            er_pad_kernel<<<grid, 256>>>(rows, n, g->d_row, g->d_col, d_off4, g->d_row4, g->d_col4);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        sponet_graph_destroy(g);
+        cudaGetLastError();
+        return sponet_fail(SPONET_ERR_CUDA, "graph_batch_create_er: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return SPONET_OK;
+}
+
+extern "C" int sponet_graph_batch_get(const sponet_graph* g, int64_t slot, int32_t* row_ptr, int32_t* col, int64_t col_capacity) {
+    SP_REQUIRE(g && row_ptr, "graph_batch_get: bad arguments");
+    SP_REQUIRE(slot >= 0 && slot < g->batch, "graph_batch_get: slot %lld outside the batch of %lld", (long long)slot, (long long)g->batch);
+    int cur = 0;
+    SP_CUDA(cudaGetDevice(&cur));
+    if (cur != g->device) SP_CUDA(cudaSetDevice(g->device));
+    std::vector<int2> row((size_t)g->n);
+    cudaError_t e = cudaMemcpy(row.data(), g->d_row + slot * g->n, (size_t)g->n * sizeof(int2), cudaMemcpyDeviceToHost);
+    int64_t total = 0;
+    if (e == cudaSuccess) {
+        for (int64_t i = 0; i < g->n; ++i) {
+            row_ptr[i] = (int32_t)total;
+            total += row[i].y;
+        }
+        row_ptr[g->n] = (int32_t)total;
+        if (col && total <= col_capacity && total > 0)  // rows of one graph are contiguous in the batch
+            e = cudaMemcpy(col, g->d_col + (uint32_t)row[0].x, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    }
+    if (cur != g->device) cudaSetDevice(cur);
+    SP_CUDA(e);
+    SP_REQUIRE(!col || total <= col_capacity, "graph_batch_get: graph has %lld entries, capacity %lld", (long long)total, (long long)col_capacity);
+    return SPONET_OK;
+}

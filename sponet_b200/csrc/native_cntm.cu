@@ -31,6 +31,7 @@ struct NativeCntmArgs {
     int32_t n;
     const int2* row4;  // (first int4 index, degree)
     const int4* col4;  // rows padded to multiples of four with the row's own agent
+    uint32_t graph_stride;  // n for a BATCH of graphs (chain cl of the call runs on graph cl), else 0
     uint32_t noise_thr;
     const int32_t* need01;  // [max_degree + 1] minimum count of ones for a 0 -> 1 flip (INT_MAX = never)
     const int32_t* need10;  // [max_degree + 1] minimum count of zeros for a 1 -> 0 flip
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;
         const uint8_t* x0 = A.x_init + j * (int64_t)n;
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
+        const uint32_t grow = (uint32_t)cl * A.graph_stride;  // first row of the chain's own graph (batch)
 
         int c1 = 0;  // number of ones (warp-uniform, exact at snapshots)
         for (int w = lane; w < A.words; w += 32) {
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(32 * SP_CNTM_MAX_WARPS, 1) cntm_native_kernel(
             const uint4 r = sp_philox4x32_10_rk((uint32_t)e, (uint32_t)(e >> 32), ctr2, ctr3, A.rk);
             a = __umulhi(r.y, n);
             meta = (uint32_t)(r.x < noise_thr) | ((r.z >> 31) << 1);  // bit 0 noise, bit 1 the noise opinion
-            row = __ldg(A.row4 + a);
+            row = __ldg(A.row4 + (grow + a));
         };
         auto gather = [&](const int2& row, int4& c0, int4& c1) {
             const int chunks = (row.y + 3) >> 2;
@@ -459,6 +461,10 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.n = (int32_t)n;
     A.row4 = g->d_row4;
     A.col4 = g->d_col4;
+    SP_REQUIRE(g->batch == 1 || g->batch == num_chains, "graph batch holds %lld graphs, the call has %lld chains",
+               (long long)g->batch, (long long)num_chains);
+    SP_REQUIRE(g->d_row4 && g->d_col4, "cntm_run: the graph batch was created without padded rows");
+    A.graph_stride = g->batch > 1 ? (uint32_t)n : 0u;
     A.noise_thr = sp_prob_to_thr(p->noise_prob);
     {
         std::vector<int32_t> need((size_t)2 * (g->max_degree + 1));
@@ -485,6 +491,8 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.hist_lo = o->hist_lo;
     A.hist_width = o->hist_width;
     A.ecv = cvd.ecv;
+    if (g->batch > 1 && cvd.ecv.kind != 0)
+        return sponet_fail(SPONET_ERR_UNSUPPORTED, "edge collective variables are not evaluated on a graph batch");
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
     A.cv_div = cvd.divisor;

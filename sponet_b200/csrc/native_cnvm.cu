@@ -27,6 +27,7 @@ struct NativeCnvmArgs {
     int32_t n, M;
     const int2* row;  // (begin, degree); nullptr = complete graph
     const int32_t* col;
+    uint32_t graph_stride;  // n for a BATCH of graphs (chain cl of the call runs on graph cl: rows [cl n, (cl+1) n)), else 0
     const uint2* nbtab;  // neighbour sampler table (GRAPH == 2): [n << nbtab_log2]
     int32_t nbtab_log2;
     const uint32_t* noise_thr;  // [P] noise-branch threshold of the chain's parameter set
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
+        const uint32_t grow = GRAPH == 1 ? (uint32_t)cl * A.graph_stride : 0u;  // first row of the chain's own graph (batch)
         // the chain's parameter set: noise-branch threshold, acceptance tables (staged per chain slot)
         const int64_t pset = j * A.param_stride;
         const uint32_t noise_thr = __ldg(A.noise_thr + pset);
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         uint2 z_at = make_uint2(0u, 0u);
         auto gather_entry = [&](int s, uint32_t a, uint32_t r2) {
             // every lane gathers (no divergence); noise lanes ignore the result
-            if (GRAPH == 1) q_row[s] = __ldg(A.row + a);
+            if (GRAPH == 1) q_row[s] = __ldg(A.row + (grow + a));
             if (GRAPH == 2) {
                 // slot index (a << lg) | (top lg bits of r2) in one funnel shift; the table has < 2^26 entries
                 const uint2 t = __ldg(A.nbtab + __funnelshift_l(r2, a, (uint32_t)A.nbtab_log2));
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         auto issue2 = [&](int s) {
             uint32_t nbr;
             if (GRAPH == 1) {
-                nbr = (uint32_t)__ldg(A.col + q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y));
+                nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
             } else if (GRAPH == 2) {
                 const uint32_t w0 = (uint32_t)q_row[s].x, w1 = (uint32_t)q_row[s].y;
                 const uint32_t thr = ((w0 >> 20) << 12) | (w1 >> 20);
@@ -940,7 +942,7 @@ int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, 
         if (n <= 0)
             return sponet_fail(SPONET_ERR_UNSUPPORTED, "cv: edge collective variables need the agent states (not the count-only kernel)");
         SP_REQUIRE(M == 2, "cv: Interfaces / Propensities are defined for 2 opinions (model has %d)", M);
-        SP_REQUIRE(cv->graph && cv->graph->n == n, "cv: edge collective variable needs a graph over the model's %lld agents", (long long)n);
+        SP_REQUIRE(cv->graph && cv->graph->n == n && cv->graph->batch == 1, "cv: edge collective variable needs a graph over the model's %lld agents", (long long)n);
         SP_REQUIRE(cv->dimension == (cv->kind == SPONET_CV_INTERFACES ? 1 : 2), "cv: dimension %d does not match the kind", cv->dimension);
         SP_REQUIRE(cv->divisor != 0.0, "cv: divisor must be non-zero");
         out->ecv.kind = cv->kind;
@@ -1113,6 +1115,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     if (g) {
         SP_REQUIRE(g->n == n, "graph has %lld agents, expected %lld", (long long)g->n, (long long)n);
         SP_REQUIRE(g->min_degree >= 1, "Isolated vertices in the network are not allowed.");
+        SP_REQUIRE(g->batch == 1 || g->batch == S * nrun, "graph batch holds %lld graphs, the call has %lld chains",
+                   (long long)g->batch, (long long)(S * nrun));
     }
     int dev = 0;
     SP_CUDA(cudaGetDevice(&dev));
@@ -1134,6 +1138,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     bool uniform = true;
     if (g) {
         for (int64_t i = 1; i < n && uniform; ++i) uniform = (p->degree_alpha[i] == p->degree_alpha[0]);
+        if (!uniform && g->batch > 1)
+            return sponet_fail(SPONET_ERR_UNSUPPORTED, "a graph batch needs uniform degree_alpha (alpha = 1): agent weights depend on the graph");
         if (!uniform) {
             std::vector<double> prob(n);
             std::vector<int32_t> alias(n);
@@ -1148,6 +1154,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
         }
         A.row = g->d_row;
         A.col = g->d_col;
+        A.graph_stride = g->batch > 1 ? (uint32_t)n : 0u;
         A.nbtab = g->d_nbtab;
         A.nbtab_log2 = g->nbtab_log2;
     }
@@ -1162,6 +1169,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     A.cv_divs = cvd.d_divisors;
     A.cw = cvd.d_cw;
     A.ecv = cvd.ecv;
+    if (g && g->batch > 1 && cvd.ecv.kind != 0)
+        return sponet_fail(SPONET_ERR_UNSUPPORTED, "edge collective variables are not evaluated on a graph batch");
     SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq && !o->out_hist),
                "cnvm_run: integer moment sums / histograms are not defined for Propensities");
     A.cnt_stride = cvd.num_classes * M;

@@ -72,6 +72,55 @@ class GraphHandle:
     __del__ = close
 
 
+class GraphBatch:
+    """A batch of Erdos-Renyi graphs generated on the device (sponet_graph_batch_create_er), one per chain of the native
+    call over the same (states, run range): chain (state j, run i) runs on graph index j * num_runs_total + i, which is a
+    function of (seed, index) only.  Stands in for the reference's per-run ``update_network()`` (cnvm/model.py:95-96)."""
+
+    def __init__(self, num_agents, p, seed, num_states, num_runs_total, run_begin, run_end, force_no_isolates=False,
+                 max_attempts=64, padded_rows=False):
+        _lib.require_device()
+        h = C.c_void_p()
+        rc = _lib.lib().sponet_graph_batch_create_er(int(num_agents), float(p), int(bool(force_no_isolates)), int(seed),
+                                                     int(num_states), int(num_runs_total), int(run_begin), int(run_end),
+                                                     int(max_attempts), int(bool(padded_rows)), C.byref(h))
+        if rc == _lib.ERR_INVALID and _lib.last_error().startswith("Timeout"):
+            raise RuntimeError(_lib.last_error())  # network_generator.py:75-78
+        _lib.check(rc)
+        self._h = h
+        self.num_agents = int(num_agents)
+        self.count = int(num_states) * (int(run_end) - int(run_begin))
+        self.device = current_device()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def csr(self, slot: int):
+        """Graph `slot` of the batch as host (row_ptr, col)."""
+        row_ptr = np.empty(self.num_agents + 1, dtype=np.int32)
+        L = _lib.lib()
+        _lib.check(L.sponet_graph_batch_get(self._h, int(slot), _lib.ptr(row_ptr), None, 0))
+        col = np.empty(max(int(row_ptr[-1]), 1), dtype=np.int32)
+        _lib.check(L.sponet_graph_batch_get(self._h, int(slot), _lib.ptr(row_ptr), _lib.ptr(col), col.size))
+        return row_ptr, col[: int(row_ptr[-1])]
+
+    def info(self):
+        n, nnz, dmin, dmax, dev = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32(), C.c_int()
+        _lib.check(_lib.lib().sponet_graph_info(self._h, C.byref(n), C.byref(nnz), C.byref(dmin), C.byref(dmax), C.byref(dev)))
+        return {"num_agents": n.value, "nnz": nnz.value, "min_degree": dmin.value, "max_degree": dmax.value, "device": dev.value}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                _lib.lib().sponet_graph_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    __del__ = close
+
+
 class GraphCache:
     """One GraphHandle per (network identity, device); rebuilt when the adjacency object changes."""
 

@@ -333,16 +333,21 @@ def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng
     if world > 1:
         seed = _broadcast_seed(seed)
     pairs = S * num_runs
-    bounds = np.concatenate(([0], np.cumsum(_split_runs(pairs, world))))
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    D = N if cv is None else cv.dimension
-    flat = np.zeros((pairs, T, D), dtype=np.uint8 if cv is None else np.float64)
-    pbar = _progress(progress_bar, hi - lo)
     spec = _kernel_cv_spec(cv, N) if cv is not None else None
     if spec is not None and (spec.edge and p.num_opinions != 2):
         raise ValueError("Interfaces / Propensities can only be used for 2 opinions.")
     if spec is not None and spec.edge:
         spec = None  # an edge CV carries its own (fixed) graph; evaluated from the returned states below
+    gen = p.network_generator
+    if (kind == "cnvm" and hasattr(gen, "device_batch") and p.alpha == 1 and (cv is None or spec is not None)
+            and not _FORCE_HOST_NETWORKS):
+        # the generator makes its graphs on the GPU: the whole ensemble in a few launches, one graph per chain
+        return _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar)
+    bounds = np.concatenate(([0], np.cumsum(_split_runs(pairs, world))))
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    D = N if cv is None else cv.dimension
+    flat = np.zeros((pairs, T, D), dtype=np.uint8 if cv is None else np.float64)
+    pbar = _progress(progress_bar, hi - lo)
     if spec is not None:
         flat[lo:hi] = _per_run_network_pipeline(model, kind, states, t_out, seed, pairs, lo, hi, cv, pbar)
     else:
@@ -362,6 +367,55 @@ def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng
 
 
 _NETWORK_STREAMS = 8
+_FORCE_HOST_NETWORKS = False  # tests: take the host-generated pipeline although the generator has device_batch
+_BATCH_BYTES = 24 << 30       # device memory one batch of generated graphs may take
+
+
+def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar):
+    """Per-run networks from a generator with ``device_batch`` (network_generator.ErdosRenyiGenerator, alpha = 1): the
+    graphs of a block of (initial state, run) pairs are generated on the GPU and the block's chains run in ONE launch,
+    chain (j, i) on graph index j * num_runs + i.  Graph and Philox stream of a pair depend on the two seeds and on the
+    pair's index only: the result is the same for every block size and number of ranks.  Runs are split over ranks
+    like ``_split_runs`` (multiprocessing.py:190-196)."""
+    p = model.params
+    gen = p.network_generator
+    S, N, T = states.shape[0], p.num_agents, t_out.size
+    gseed = gen.draw_batch_seed()
+    rank, world = _dist()
+    if world > 1:
+        gseed = _broadcast_seed(gseed)
+    bounds = np.concatenate(([0], np.cumsum(_split_runs(num_runs, world))))
+    rb, re = int(bounds[rank]), int(bounds[rank + 1])
+    D = N if cv is None else cv.dimension
+    local = np.empty((S, re - rb, T, D), dtype=np.uint8 if cv is None else np.float64)
+    # graphs per block: device memory (rows 8 B + adjacency 4 B per entry + 12 B of build scratch per vertex), the
+    # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
+    mean_entries = N * (getattr(gen, "p", 0.0) * (N - 1) + 2.0)
+    per_graph = 20.0 * N + 4.0 * mean_entries + (T * N if cv is None else 0)
+    max_graphs = int(min(_BATCH_BYTES // per_graph, (2**32 - 1) // N, (2**32 - 1) // (1.2 * mean_entries)))
+    max_graphs = max(1, max_graphs)
+    s_blk = min(S, max_graphs)
+    r_blk = max(1, max_graphs // s_blk)
+    struct, keep = model._struct()
+    pbar = _progress(progress_bar, S * (re - rb))
+    for s0 in range(0, S, s_blk):
+        s1 = min(S, s0 + s_blk)
+        st = np.ascontiguousarray(states[s0:s1])
+        for lo in range(rb, re, r_blk):
+            hi = min(re, lo + r_blk)
+            # (state block offset folded into the run offset: index = (s0 + j) * num_runs + i for the block's j)
+            batch = gen.device_batch(gseed, s1 - s0, num_runs, s0 * num_runs + lo, s0 * num_runs + hi)
+            try:
+                out_x, out_cv = engine.run_native("cnvm", batch, N, struct, st, t_out, seed, num_runs, lo, hi,
+                                                  cv_spec=spec, want_cv=cv is not None, want_x=cv is None,
+                                                  chain_offset=s0 * num_runs)
+            finally:
+                batch.close()
+            local[s0:s1, lo - rb : hi - rb] = out_x if cv is None else out_cv
+            _tick(pbar, (s1 - s0) * (hi - lo))
+    del keep
+    _close(pbar)
+    return _gather_runs(local, bounds, world) if world > 1 else local
 
 
 def _per_run_network_pipeline(model, kind, states, t_out, seed, pairs, lo, hi, cv, pbar):

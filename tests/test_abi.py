@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"libsponet_b200.so does not export {name}"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert L.sponet_abi_version() == 3
+    assert L.sponet_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():

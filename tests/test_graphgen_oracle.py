@@ -1,0 +1,94 @@
+"""CPU: the sequential statement of the device-side Erdos-Renyi generator (oracle_er_graph) and the host generators.
+
+The reference pins no generated graph (its generators are networkx calls on a numpy Generator, sponet/network_generator.py:
+26-183), so the bar for the generator is distributional: G(n, p) is defined by independent edges with probability p, which
+gives exact moments to test against (tolerances below are 5 sigma of the respective estimator)."""
+import numpy as np
+import pytest
+
+
+def _check_simple_graph(row_ptr, col, n):
+    deg = np.diff(row_ptr)
+    src = np.repeat(np.arange(n), deg)
+    assert (src != col).all()  # no self loops
+    key = src.astype(np.int64) * n + col
+    assert (np.diff(key) > 0).all()  # rows sorted, no duplicate entries
+    assert np.array_equal(np.sort(col.astype(np.int64) * n + src), key)  # symmetric
+    return deg
+
+
+@pytest.mark.parametrize("n,p", [(2000, 0.01), (500, 0.3), (50, 1.0), (20000, 5e-4)])
+def test_er_oracle_is_a_simple_graph_without_isolates(oracle, n, p):
+    rp, col, attempts = oracle.er_graph(n, p, seed=11, c=5, force_no_isolates=True)
+    deg = _check_simple_graph(rp, col, n)
+    assert deg.min() >= 1 and attempts == 1
+    rp2, col2, _ = oracle.er_graph(n, p, seed=11, c=5, force_no_isolates=True)
+    assert np.array_equal(rp, rp2) and np.array_equal(col, col2)  # a function of (seed, c)
+    rp3, col3, _ = oracle.er_graph(n, p, seed=11, c=6, force_no_isolates=True)
+    assert p == 1.0 or not (np.array_equal(rp, rp3) and np.array_equal(col, col3))
+
+
+def test_er_oracle_edge_statistics(oracle):
+    """Edge count ~ Binomial(n(n-1)/2, p); degrees ~ Binomial(n-1, p); the two halves of a row are independent."""
+    n, p, G = 1500, 0.004, 40  # mean degree 6: exp(-6) n = 3.7 isolates per graph, patched
+    pairs = n * (n - 1) / 2
+    edges, degs, iso = [], [], 0
+    for c in range(G):
+        rp, col, _ = oracle.er_graph(n, p, seed=3, c=c, force_no_isolates=True)
+        d = np.diff(rp)
+        # the patch adds one edge per (initially) isolated vertex; recover the unpatched edge count bound
+        edges.append(rp[-1] / 2)
+        degs.append(d)
+    edges = np.array(edges)
+    exp_iso = n * (1 - p) ** (n - 1)  # each isolate adds at most one edge
+    assert abs(edges.mean() - pairs * p - exp_iso / 2) < 5 * np.sqrt(pairs * p * (1 - p) / G) + exp_iso / 2 + 1
+    d = np.concatenate(degs).astype(float)
+    assert abs(d.mean() - (n - 1) * p) < 5 * np.sqrt((n - 1) * p / d.size) + exp_iso / n
+    assert abs(d.var() - (n - 1) * p * (1 - p)) < 0.05 * (n - 1) * p
+    # P(degree = k) against the binomial pmf, k = 2 .. 10 (patched isolates only move mass from 0 to 1)
+    from math import comb
+
+    for k in range(2, 11):
+        pk = comb(n - 1, k) * p**k * (1 - p) ** (n - 1 - k)
+        assert abs((d == k).mean() - pk) < 5 * np.sqrt(pk * (1 - pk) / d.size) + 2 * exp_iso / n
+
+
+def test_er_oracle_rejects_or_repairs_isolates(oracle):
+    n, p = 400, 0.012  # mean degree 4.8: a sample has isolates with probability ~0.96
+    with pytest.raises(RuntimeError, match="Timeout"):
+        oracle.er_graph(n, p, seed=1, c=0, force_no_isolates=False, max_attempts=3)
+    rp, col, attempts = oracle.er_graph(n, p, seed=1, c=0, force_no_isolates=True)
+    assert np.diff(rp).min() >= 1 and attempts == 1
+    _check_simple_graph(rp, col, n)
+    # denser: rejection succeeds after a few attempts and returns a graph that needed no repair
+    n, p = 300, 0.025  # 300 exp(-7.5) = 0.17 isolates per sample
+    got = [oracle.er_graph(n, p, seed=2, c=c, force_no_isolates=False, max_attempts=64) for c in range(30)]
+    assert all(np.diff(rp).min() >= 1 for rp, _, _ in got)
+    assert 1 < np.mean([a for _, _, a in got]) < 1.6  # 1 / (1 - 0.155) = 1.18 expected attempts
+    for (rp, col, a), c in zip(got, range(30)):
+        if a == 1:  # an accepted first attempt is the graph the repairing variant returns as well
+            rp2, col2, _ = oracle.er_graph(n, p, seed=2, c=c, force_no_isolates=True)
+            assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
+
+
+def test_host_generators_follow_the_reference_protocol():
+    nx = pytest.importorskip("networkx")
+    from sponet_b200.network_generator import (BarabasiAlbertGenerator, ErdosRenyiGenerator, RandomRegularGenerator,
+                                               WattsStrogatzGenerator)
+
+    rng = np.random.default_rng(0)
+    er = ErdosRenyiGenerator(200, 0.02, rng=rng, force_no_isolates=True)
+    g = er()
+    assert g.number_of_nodes() == 200 and nx.number_of_isolates(g) == 0
+    assert repr(er) == "Erdos-Renyi random graph with p=0.02 on 200 nodes" and er.abrv() == "ER_p2_N200"
+    with pytest.raises(RuntimeError, match="Timeout"):
+        ErdosRenyiGenerator(300, 0.005, max_sample_time=0.05, rng=rng)()
+    rr = RandomRegularGenerator(50, 4, rng=rng)
+    assert all(d == 4 for _, d in rr().degree()) and rr.abrv() == "regular_d4_N50"
+    ba = BarabasiAlbertGenerator(60, 3, rng=rng)
+    assert ba().number_of_nodes() == 60 and ba.abrv() == "barabasi_m3_N60"
+    ws = WattsStrogatzGenerator(40, 4, 0.25, rng=rng)
+    assert nx.is_connected(ws()) and ws.abrv() == "watts_k4_p25_N40"
+    s1 = ErdosRenyiGenerator(10, 0.5, rng=np.random.default_rng(5)).draw_batch_seed()
+    s2 = ErdosRenyiGenerator(10, 0.5, rng=np.random.default_rng(5)).draw_batch_seed()
+    assert s1 == s2 and 0 <= s1 < 2**63
