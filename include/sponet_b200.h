@@ -93,7 +93,11 @@ int sponet_graph_neighbor_table(const sponet_graph* g, int32_t* log2_slots, uint
  * SPONET_ERR_INVALID "Timeout. ..." after max_attempts, the reference's RuntimeError :75-78).  force_no_isolates = 1
  * (reference :446-454): vertices in order, one that is still isolated gets an edge to j = mulhi(word 0 of Philox(counter
  * (k, i, c_lo, c_hi | 4 << 24)), n), k = 0, 1, ... until j != i.  Rows sorted by neighbour id.
- * padded_rows != 0 also builds the padded row layout the CNTM kernel scans.
+ * layouts: SPONET_BATCH_PADDED_ROWS also builds the padded rows the CNTM kernel scans; SPONET_BATCH_RECORDS also builds
+ * one 64-byte record per agent (degree, offset of its row, first 15 neighbours) for the CNVM kernel: the graphs of a
+ * batch do not fit the L2, and with the record the degree and the sampled neighbour of most agents come out of one
+ * DRAM burst instead of two (skipped silently when a degree exceeds 255).  The neighbour rule is the same with and
+ * without records: entry mulhi(r2, degree) of the sorted row.
  * The handle is accepted by sponet_cnvm_run / sponet_cntm_run in native mode (uniform degree_alpha, i.e. alpha = 1; no
  * degree-weighted and no edge collective variables) when it holds num_states * (run_end - run_begin) graphs, and is
  * released with sponet_graph_destroy.  num_states * (run_end - run_begin) * num_agents must stay below 2^32.  A caller
@@ -101,7 +105,9 @@ int sponet_graph_neighbor_table(const sponet_graph* g, int32_t* log2_slots, uint
  * sponet_native_opts.chain_offset of the run call). */
 int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isolates, uint64_t seed,
                                  int64_t num_states, int64_t num_runs_total, int64_t run_begin, int64_t run_end,
-                                 int32_t max_attempts, int padded_rows, sponet_graph** out);
+                                 int32_t max_attempts, int layouts, sponet_graph** out);
+#define SPONET_BATCH_PADDED_ROWS 1
+#define SPONET_BATCH_RECORDS 2
 
 /* Graph `slot` of a batch as a host CSR (row_ptr [n+1]; col may be NULL to query row_ptr[n] first). */
 int sponet_graph_batch_get(const sponet_graph* g, int64_t slot, int32_t* row_ptr, int32_t* col, int64_t col_capacity);

@@ -155,6 +155,7 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     sponet_graph* g = new sponet_graph();
     g->d_nbtab = nullptr;
     g->batch = 1;
+    g->d_rec = nullptr;
     g->nbtab_log2 = use_tab ? lg : 0;
     g->n_col4 = n4;
     g->n = n;
@@ -211,6 +212,7 @@ extern "C" int sponet_graph_destroy(sponet_graph* g) {
     cudaFree(g->d_row4);
     cudaFree(g->d_col4);
     cudaFree(g->d_nbtab);
+    cudaFree(g->d_rec);
     if (cur != g->device) cudaSetDevice(cur);
     delete g;
     return SPONET_OK;

@@ -189,6 +189,23 @@ __global__ void er_pad_kernel(int64_t rows, int64_t n, const int2* row, const in
     row4[tid] = make_int2((int)off4[tid], r.y);
 }
 
+// 64-byte agent records of the CNVM kernel (common.cuh, sponet_graph::d_rec)
+__global__ void er_record_kernel(int64_t rows, int64_t n, const int2* row, const int32_t* col, uint32_t* rec) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per record word
+    const int64_t a = t >> 4;
+    const int w = (int)(t & 15);
+    if (a >= rows) return;
+    const int2 r = row[a];
+    uint32_t v;
+    if (w == 0) {
+        const uint32_t first = (uint32_t)row[a - a % n].x;  // the graph's first adjacency entry
+        v = (uint32_t)r.y | (((uint32_t)r.x - first) << 8);
+    } else {
+        v = (w - 1 < r.y) ? (uint32_t)col[(uint32_t)r.x + (uint32_t)(w - 1)] : 0u;
+    }
+    rec[t] = v;
+}
+
 __global__ void quarter_kernel(int64_t rows, const uint32_t* deg, uint32_t* q) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < rows) q[tid] = (deg[tid] + 3) / 4;
@@ -217,7 +234,7 @@ struct Freer {
 
 extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isolates, uint64_t seed,
                                             int64_t num_states, int64_t num_runs_total, int64_t run_begin,
-                                            int64_t run_end, int32_t max_attempts, int padded_rows,
+                                            int64_t run_end, int32_t max_attempts, int layouts,
                                             sponet_graph** out) {
     SP_REQUIRE(out, "graph_batch_create_er: out is NULL");
     *out = nullptr;
@@ -328,7 +345,15 @@ extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int fo
     if (e == cudaSuccess) e = cudaMemcpy(mm, d_mm, 8, cudaMemcpyDeviceToHost);
     g->min_degree = (int32_t)mm[0];
     g->max_degree = (int32_t)mm[1];
-    if (e == cudaSuccess && padded_rows) {  // the CNTM kernels' layout
+    if (e == cudaSuccess && (layouts & SPONET_BATCH_RECORDS) && mm[1] <= 255u && (uint64_t)n * mm[1] < ((uint64_t)1 << 24) &&
+        (uint64_t)rows * 16 < ((uint64_t)1 << 32)) {
+        e = cudaMalloc((void**)&g->d_rec, (size_t)rows * 64);
+        if (e == cudaSuccess) {
+            er_record_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256>>>(rows, n, g->d_row, g->d_col, g->d_rec);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess && (layouts & SPONET_BATCH_PADDED_ROWS)) {  // the CNTM kernels' layout
         uint32_t *d_q, *d_off4;
         uint64_t n4 = 0;
         e = tmp.alloc((void**)&d_q, rows * 4);

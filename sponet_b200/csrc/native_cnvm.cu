@@ -28,6 +28,7 @@ struct NativeCnvmArgs {
     const int2* row;  // (begin, degree); nullptr = complete graph
     const int32_t* col;
     uint32_t graph_stride;  // n for a BATCH of graphs (chain cl of the call runs on graph cl: rows [cl n, (cl+1) n)), else 0
+    const uint32_t* rec;    // batch: 64-byte agent records (sponet_graph::d_rec) or nullptr
     const uint2* nbtab;  // neighbour sampler table (GRAPH == 2): [n << nbtab_log2]
     int32_t nbtab_log2;
     const uint32_t* noise_thr;  // [P] noise-branch threshold of the chain's parameter set
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
         const uint32_t grow = GRAPH == 1 ? (uint32_t)cl * A.graph_stride : 0u;  // first row of the chain's own graph (batch)
+        const uint32_t gcol = (GRAPH == 1 && A.rec) ? (uint32_t)__ldg(&A.row[grow].x) : 0u;  // ... and its first adjacency entry
         // the chain's parameter set: noise-branch threshold, acceptance tables (staged per chain slot)
         const int64_t pset = j * A.param_stride;
         const uint32_t noise_thr = __ldg(A.noise_thr + pset);
@@ -370,7 +372,14 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         uint2 z_at = make_uint2(0u, 0u);
         auto gather_entry = [&](int s, uint32_t a, uint32_t r2) {
             // every lane gathers (no divergence); noise lanes ignore the result
-            if (GRAPH == 1) q_row[s] = __ldg(A.row + (grow + a));
+            if (GRAPH == 1) {
+                if (A.rec) {  // (word index of the agent's record, its header)
+                    const uint32_t base = (grow + a) << 4;
+                    q_row[s] = make_int2((int)base, (int)__ldg(A.rec + base));
+                } else {
+                    q_row[s] = __ldg(A.row + (grow + a));
+                }
+            }
             if (GRAPH == 2) {
                 // slot index (a << lg) | (top lg bits of r2) in one funnel shift; the table has < 2^26 entries
                 const uint2 t = __ldg(A.nbtab + __funnelshift_l(r2, a, (uint32_t)A.nbtab_log2));
@@ -408,7 +417,14 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         auto issue2 = [&](int s) {
             uint32_t nbr;
             if (GRAPH == 1) {
-                nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
+                if (A.rec) {  // neighbour k < 15 out of the record (same DRAM burst as the header), else out of the row
+                    const uint32_t hdr = (uint32_t)q_row[s].y, k = __umulhi(q_r2[s], hdr & 0xFFu);
+                    const bool in_rec = k < 15u;
+                    const uint32_t* src = in_rec ? A.rec : (const uint32_t*)A.col;
+                    nbr = __ldg(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> 8)) + k));
+                } else {
+                    nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
+                }
             } else if (GRAPH == 2) {
                 const uint32_t w0 = (uint32_t)q_row[s].x, w1 = (uint32_t)q_row[s].y;
                 const uint32_t thr = ((w0 >> 20) << 12) | (w1 >> 20);
@@ -1155,6 +1171,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
         A.row = g->d_row;
         A.col = g->d_col;
         A.graph_stride = g->batch > 1 ? (uint32_t)n : 0u;
+        A.rec = g->batch > 1 ? g->d_rec : nullptr;
         A.nbtab = g->d_nbtab;
         A.nbtab_log2 = g->nbtab_log2;
     }

@@ -78,12 +78,12 @@ class GraphBatch:
     function of (seed, index) only.  Stands in for the reference's per-run ``update_network()`` (cnvm/model.py:95-96)."""
 
     def __init__(self, num_agents, p, seed, num_states, num_runs_total, run_begin, run_end, force_no_isolates=False,
-                 max_attempts=64, padded_rows=False):
+                 max_attempts=64, padded_rows=False, records=True):
         _lib.require_device()
         h = C.c_void_p()
         rc = _lib.lib().sponet_graph_batch_create_er(int(num_agents), float(p), int(bool(force_no_isolates)), int(seed),
                                                      int(num_states), int(num_runs_total), int(run_begin), int(run_end),
-                                                     int(max_attempts), int(bool(padded_rows)), C.byref(h))
+                                                     int(max_attempts), int(bool(padded_rows)) | 2 * int(bool(records)), C.byref(h))
         if rc == _lib.ERR_INVALID and _lib.last_error().startswith("Timeout"):
             raise RuntimeError(_lib.last_error())  # network_generator.py:75-78
         _lib.check(rc)

@@ -388,14 +388,15 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
     rb, re = int(bounds[rank]), int(bounds[rank + 1])
     D = N if cv is None else cv.dimension
     local = np.empty((S, re - rb, T, D), dtype=np.uint8 if cv is None else np.float64)
-    # graphs per block: device memory (rows 8 B + adjacency 4 B per entry + 12 B of build scratch per vertex), the
+    # graphs per block: device memory (rows 8 B + record 64 B + 12 B of build scratch per vertex, 4 B per entry), the
     # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
     mean_entries = N * (getattr(gen, "p", 0.0) * (N - 1) + 2.0)
-    per_graph = 20.0 * N + 4.0 * mean_entries + (T * N if cv is None else 0)
-    max_graphs = int(min(_BATCH_BYTES // per_graph, (2**32 - 1) // N, (2**32 - 1) // (1.2 * mean_entries)))
+    per_graph = 84.0 * N + 4.0 * mean_entries + (T * N if cv is None else 0)
+    max_graphs = int(min(_BATCH_BYTES // per_graph, (2**32 - 1) // (16 * N), (2**32 - 1) // (1.2 * mean_entries)))
     max_graphs = max(1, max_graphs)
     s_blk = min(S, max_graphs)
     r_blk = max(1, max_graphs // s_blk)
+    r_blk = max(1, -(-(re - rb) // max(1, -(-(re - rb) // r_blk))))  # equal blocks instead of full ones and a remainder
     struct, keep = model._struct()
     pbar = _progress(progress_bar, S * (re - rb))
     for s0 in range(0, S, s_blk):

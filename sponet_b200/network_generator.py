@@ -85,13 +85,13 @@ class ErdosRenyiGenerator:
         return int(self.rng.integers(0, 2**63, dtype=np.int64))
 
     def device_batch(self, seed: int, num_states: int, num_runs_total: int, run_begin: int, run_end: int,
-                     padded_rows: bool = False):
+                     padded_rows: bool = False, records: bool = True):
         """The graphs of realizations [run_begin, run_end) of every initial state, generated on the current GPU."""
         from . import engine
 
         return engine.GraphBatch(self.num_agents, self.p, seed, num_states, num_runs_total, run_begin, run_end,
                                  force_no_isolates=self.force_no_isolates, max_attempts=self.max_device_attempts,
-                                 padded_rows=padded_rows)
+                                 padded_rows=padded_rows, records=records)
 
     def __repr__(self) -> str:
         return f"Erdos-Renyi random graph with p={self.p} on {self.num_agents} nodes"

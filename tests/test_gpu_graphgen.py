@@ -93,8 +93,11 @@ def _oracle_chain(oracle, kw, rp, col, x0, t_eval, seed, c):
     return ox, oc
 
 
-@pytest.mark.parametrize("M,n,p", [(2, 600, 0.01), (3, 2000, 0.004), (5, 400, 0.03), (2, 300, 0.4)])
-def test_cnvm_chains_on_a_batch_equal_single_graph_chains(oracle, M, n, p):
+@pytest.mark.parametrize("records", [True, False])
+@pytest.mark.parametrize("M,n,p", [(2, 600, 0.01), (3, 2000, 0.004), (5, 400, 0.03), (2, 300, 0.4), (3, 700, 0.5), (2, 3000, 0.006)])
+def test_cnvm_chains_on_a_batch_equal_single_graph_chains(oracle, M, n, p, records):
+    """(records: the 64-byte agent records, neighbours 0..14 inside, the rest out of the row -- mean degrees 6 .. 350 here
+    cover both sides and the fallback without records above degree 255.)"""
     from sponet_b200 import CNVM, CNVMParameters, OpinionShares, engine
     from sponet_b200.multiprocessing import _kernel_cv_spec
 
@@ -106,7 +109,7 @@ def test_cnvm_chains_on_a_batch_equal_single_graph_chains(oracle, M, n, p):
     states = rng.integers(0, M, (S, n)).astype(np.uint8)
     t_eval = np.linspace(0.0, 4.0, T)
     seed, gseed = 4242, 777
-    batch = engine.GraphBatch(n, p, gseed, S, R, rb, re, force_no_isolates=True)
+    batch = engine.GraphBatch(n, p, gseed, S, R, rb, re, force_no_isolates=True, records=records)
     model = CNVM(CNVMParameters(num_agents=n, **kw))  # alpha = 1: uniform agent weights whatever the graph
     struct, keep = model._struct()
     spec = _kernel_cv_spec(OpinionShares(M), n)
@@ -191,7 +194,7 @@ def test_sample_many_runs_with_a_device_generator(oracle):
     # small blocks (1 state x 2 runs per launch)
     old = mp._BATCH_BYTES
     try:
-        mp._BATCH_BYTES = int(2.5 * (20.0 * n + 4.0 * n * (p * (n - 1) + 2.0)))
+        mp._BATCH_BYTES = int(2.5 * (84.0 * n + 4.0 * n * (p * (n - 1) + 2.0)))
         _, c2 = sample_many_runs(params(8), states, 2.0, T, R, collective_variable=cv, rng=np.random.default_rng(1))
     finally:
         mp._BATCH_BYTES = old

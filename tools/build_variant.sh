@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 NAME=$1; shift
 SRC=${SRC:-sponet_b200/csrc}
 mkdir -p sponet_b200/_variants/obj_$NAME
-for f in api replay native_cnvm native_cntm cv; do
+for f in api replay native_cnvm native_cntm cv graphgen; do
   EXTRA=""; [ $f = replay ] && EXTRA="-fmad=false"
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off --expt-relaxed-constexpr $EXTRA "$@" -c $SRC/$f.cu -o sponet_b200/_variants/obj_$NAME/$f.o &
 done

@@ -29,6 +29,29 @@ for n_graphs in (148, 1184, 2368):
     print(f"generate {n_graphs} graphs G({N}, {p:.2e}): {dt * 1e3:.1f} ms = {dt / n_graphs * 1e6:.1f} us per graph, nnz {info['nnz']}, degrees {info['min_degree']}..{info['max_degree']}")
     b.close()
 
+# the simulation kernel alone on a resident batch (CUDA events)
+from sponet_b200 import CNVM
+
+model = CNVM(CNVMParameters(num_agents=N, **kw))
+struct, keep = model._struct()
+spec = (np.arange(M, dtype=np.int32), 1.0)
+d_x0 = torch.as_tensor(x0[None, :].astype(np.uint8), device="cuda")
+for n_graphs in (1184, min(R, 2368)):
+    b = engine.GraphBatch(N, p, 5, 1, n_graphs, 0, n_graphs, force_no_isolates=True)
+    t_eval = np.linspace(0, t_max, 11)
+    best = 0.0
+    for rep in range(4):
+        counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        engine.run_native("cnvm", b, N, struct, d_x0, t_eval, 77 + rep, n_graphs, 0, n_graphs, cv_spec=spec, want_cv=True, counters=counters)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, counters[0].item() / e0.elapsed_time(e1) * 1e3)
+    print(f"kernel on a batch of {n_graphs} graphs, t_max={t_max}: {best:.4g} events/s")
+    b.close()
+
 
 def params():
     return CNVMParameters(network_generator=ErdosRenyiGenerator(N, p, rng=np.random.default_rng(1), force_no_isolates=True), **kw)
