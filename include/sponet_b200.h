@@ -109,6 +109,10 @@ int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isol
 #define SPONET_BATCH_PADDED_ROWS 1
 #define SPONET_BATCH_RECORDS 2
 
+/* Device memory of destroyed batches is kept for the next batch (cudaMalloc / cudaFree of tens of gigabytes cost up to
+ * seconds; at most 64 GiB idle per process).  This returns it to the driver. */
+int sponet_graph_batch_trim(void);
+
 /* Graph `slot` of a batch as a host CSR (row_ptr [n+1]; col may be NULL to query row_ptr[n] first). */
 int sponet_graph_batch_get(const sponet_graph* g, int64_t slot, int32_t* row_ptr, int32_t* col, int64_t col_capacity);
 

@@ -156,6 +156,7 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     g->d_nbtab = nullptr;
     g->batch = 1;
     g->d_rec = nullptr;
+    g->pooled = false;
     g->nbtab_log2 = use_tab ? lg : 0;
     g->n_col4 = n4;
     g->n = n;
@@ -206,13 +207,21 @@ extern "C" int sponet_graph_destroy(sponet_graph* g) {
     int cur = 0;
     cudaGetDevice(&cur);
     if (cur != g->device) cudaSetDevice(g->device);
-    cudaFree(g->d_row_ptr);
-    cudaFree(g->d_row);
-    cudaFree(g->d_col);
-    cudaFree(g->d_row4);
-    cudaFree(g->d_col4);
-    cudaFree(g->d_nbtab);
-    cudaFree(g->d_rec);
+    if (g->pooled) {  // batch memory goes back to the pool it came from (graphgen.cu)
+        cudaDeviceSynchronize();
+        sp_pool_free(g->d_row);
+        sp_pool_free(g->d_col);
+        sp_pool_free(g->d_row4);
+        sp_pool_free(g->d_col4);
+        sp_pool_free(g->d_rec);
+    } else {
+        cudaFree(g->d_row_ptr);
+        cudaFree(g->d_row);
+        cudaFree(g->d_col);
+        cudaFree(g->d_row4);
+        cudaFree(g->d_col4);
+        cudaFree(g->d_nbtab);
+    }
     if (cur != g->device) cudaSetDevice(cur);
     delete g;
     return SPONET_OK;

@@ -65,7 +65,14 @@ struct sponet_graph {
     // the degree and the sampled neighbour of most agents share ONE DRAM burst (a batch never fits the L2); neighbours
     // 15.. are read from d_col.  nullptr when the batch was created without records (or a degree exceeds 255).
     uint32_t* d_rec;     // [batch * n * 16]
+    bool pooled;         // device memory from sp_pool_alloc (graphgen.cu)
 };
+
+// Device memory of graph batches (graphgen.cu): tens of gigabytes per ensemble call, allocated and released block after
+// block.  cudaMalloc / cudaFree of that size cost 0.1 - 2 s a time, so released blocks are kept (up to 64 GiB, per
+// process) and handed out again; sponet_graph_batch_trim() returns them to the driver.
+cudaError_t sp_pool_alloc(void** out, size_t bytes);
+void sp_pool_free(void* p);
 
 // ---------------------------------------------------------------------------------------------
 // staging: a caller pointer may live on the host or on the device

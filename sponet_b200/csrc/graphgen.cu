@@ -22,8 +22,90 @@
 //   Rows are sorted by neighbour id.
 #include <cub/cub.cuh>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "sponet_log1p.h"
+
+// ---- pool of large device blocks (see common.cuh) ----
+namespace {
+struct PoolBlock {
+    void* p;
+    size_t bytes;
+    int dev;
+};
+std::mutex pool_mu;
+std::vector<PoolBlock> pool_idle;                 // released, oldest first
+std::unordered_map<void*, PoolBlock> pool_live;   // handed out
+size_t pool_idle_bytes = 0;
+constexpr size_t POOL_KEEP = (size_t)64 << 30, POOL_MIN = (size_t)1 << 20;
+
+void pool_evict_locked(size_t keep) {
+    while (!pool_idle.empty() && (pool_idle_bytes > keep || pool_idle.size() > 32)) {
+        cudaFree(pool_idle.front().p);
+        pool_idle_bytes -= pool_idle.front().bytes;
+        pool_idle.erase(pool_idle.begin());
+    }
+}
+}  // namespace
+
+cudaError_t sp_pool_alloc(void** out, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (bytes >= POOL_MIN) {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)pool_idle.size(); ++i) {
+            const PoolBlock& b = pool_idle[i];
+            if (b.dev == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 && (best < 0 || b.bytes < pool_idle[best].bytes)) best = i;
+        }
+        if (best >= 0) {
+            const PoolBlock b = pool_idle[best];
+            pool_idle.erase(pool_idle.begin() + best);
+            pool_idle_bytes -= b.bytes;
+            pool_live[b.p] = b;
+            *out = b.p;
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the idle blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(pool_mu);
+            pool_evict_locked(0);
+        }
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess && bytes >= POOL_MIN) {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        pool_live[*out] = PoolBlock{*out, bytes, dev};
+    }
+    return e;
+}
+
+void sp_pool_free(void* p) {  // (the caller has synchronised the device)
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(pool_mu);
+    auto it = pool_live.find(p);
+    if (it == pool_live.end()) {
+        cudaFree(p);
+        return;
+    }
+    pool_idle.push_back(it->second);
+    pool_idle_bytes += it->second.bytes;
+    pool_live.erase(it);
+    pool_evict_locked(POOL_KEEP);
+}
+
+extern "C" int sponet_graph_batch_trim(void) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(pool_mu);
+    pool_evict_locked(0);
+    return SPONET_OK;
+}
 
 namespace {
 
@@ -221,10 +303,11 @@ __global__ void sum_u32_kernel(int64_t rows, const uint32_t* v, unsigned long lo
 struct Freer {
     std::vector<void*> p;
     ~Freer() {
-        for (void* q : p) cudaFree(q);
+        cudaDeviceSynchronize();
+        for (void* q : p) sp_pool_free(q);
     }
     cudaError_t alloc(void** out, size_t bytes) {
-        cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+        cudaError_t e = sp_pool_alloc(out, bytes ? bytes : 16);
         if (e == cudaSuccess) p.push_back(*out);
         return e;
     }
@@ -325,11 +408,12 @@ extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int fo
     sponet_graph* g = new sponet_graph();
     memset(g, 0, sizeof(*g));
     g->batch = B;
+    g->pooled = true;
     g->n = n;
     g->nnz = (int64_t)nnz;
     cudaError_t e = cudaGetDevice(&g->device);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row, rows * sizeof(int2));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col, std::max<uint64_t>(nnz, 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_row, rows * sizeof(int2));
+    if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_col, std::max<uint64_t>(nnz, 1) * sizeof(int32_t));
     if (e == cudaSuccess) {
         er_fill_kernel<<<grid, 256>>>(A, d_attempt, d_off, d_cursor, g->d_col);
         if (cap > 0)
@@ -347,7 +431,7 @@ extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int fo
     g->max_degree = (int32_t)mm[1];
     if (e == cudaSuccess && (layouts & SPONET_BATCH_RECORDS) && mm[1] <= 255u && (uint64_t)n * mm[1] < ((uint64_t)1 << 24) &&
         (uint64_t)rows * 16 < ((uint64_t)1 << 32)) {
-        e = cudaMalloc((void**)&g->d_rec, (size_t)rows * 64);
+        e = sp_pool_alloc((void**)&g->d_rec, (size_t)rows * 64);
         if (e == cudaSuccess) {
             er_record_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256>>>(rows, n, g->d_row, g->d_col, g->d_rec);
             e = cudaGetLastError();
@@ -373,8 +457,8 @@ extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int fo
             if (e == cudaSuccess) e = tmp.alloc(&d_ws2, ws2);
             if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_ws2, ws2, d_q, d_off4, rows);
         }
-        if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_row4, rows * sizeof(int2));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_col4, std::max<uint64_t>(n4, 1) * sizeof(int4));
+        if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_row4, rows * sizeof(int2));
+        if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_col4, std::max<uint64_t>(n4, 1) * sizeof(int4));
         if (e == cudaSuccess) {
             g->n_col4 = (int64_t)n4;
             er_pad_kernel<<<grid, 256>>>(rows, n, g->d_row, g->d_col, d_off4, g->d_row4, g->d_col4);

@@ -171,6 +171,24 @@ __global__ void pack_states_kernel(const uint8_t* x, int64_t num_states, int64_t
 // scheduler leaves 102 per thread), which lets a NINTH chain of workload H run with two warps like the other eight.
 // Per SM that is 2 % slower than 8 x 2, but 1 332 resident chains instead of 1 184 save a whole wave when the chain
 // count falls just above a multiple of 1 184 (1 250 chains per GPU when 8 GPUs share 1e4 realizations: +19 %).
+#ifndef SP_BATCH_LD64
+#define SP_BATCH_LD64 1
+#endif
+// gather out of a batch's agent records: a random 64-byte record out of gigabytes -- ask the L2 for no more than that
+__device__ __forceinline__ uint32_t sp_ldg_rec(const uint32_t* p) {
+#if SP_BATCH_LD64
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::64B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
+#ifndef SP_CSR_SETS
+#define SP_CSR_SETS 3
+#endif
+
 template <int BITS, bool SMEM, int GRAPH, bool ALIAS, bool RING, int MAXT = SP_RING_MAX_THREADS>
 __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) {
     using P = Pack<BITS>;
@@ -182,6 +200,8 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
     const bool PACKCNT = THR4 && packcnt_r != 0u;
     constexpr bool THR_SMEM = (BITS <= 4);  // M <= 16: threshold tables staged in shared memory
     constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int NS = (GRAPH == 1 && !ALIAS) ? SP_CSR_SETS : 3;  // stage register sets = own steps in flight
+    constexpr int ISS2 = NS > 3 ? 2 : 1;
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -360,8 +380,11 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         };
 
         // ---- stage registers, one set per in-flight own step (indices are compile-time after unrolling) ----
-        uint32_t q_a[3], q_r2[3], q_r3[3], q_meta[3], q_nbr[3];
-        int2 q_row[3];
+        // NS sets (own steps in flight): 3 -- the gather of an agent's entry is issued one step before it is used, the
+        // column gather of the CSR path inside the step that uses it.  A batch of per-run graphs does not fit the L2:
+        // with more sets the record header is gathered two steps ahead and the neighbour one step ahead (ISS2 = 2).
+        uint32_t q_a[NS], q_r2[NS], q_r3[NS], q_meta[NS], q_nbr[NS];
+        int2 q_row[NS];
 
         // Stage 1 of an own step: Philox, agent, gather of the agent's table entry (or CSR row).  With alias
         // tables (degree-weighted agent selection) the agent itself comes out of a gather, so the stage is
@@ -374,8 +397,10 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
             // every lane gathers (no divergence); noise lanes ignore the result
             if (GRAPH == 1) {
                 if (A.rec) {  // (word index of the agent's record, its header)
+                    // Only imitation events read the graph here: every record gathered is a random DRAM row, and the
+                    // rate of those -- not bytes, not latency -- is what bounds this path (profiles/r2_kernels.md 6).
                     const uint32_t base = (grow + a) << 4;
-                    q_row[s] = make_int2((int)base, (int)__ldg(A.rec + base));
+                    q_row[s] = make_int2((int)base, (q_meta[s] & 1u) ? 1 : (int)sp_ldg_rec(A.rec + base));
                 } else {
                     q_row[s] = __ldg(A.row + (grow + a));
                 }
@@ -421,7 +446,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
                     const uint32_t hdr = (uint32_t)q_row[s].y, k = __umulhi(q_r2[s], hdr & 0xFFu);
                     const bool in_rec = k < 15u;
                     const uint32_t* src = in_rec ? A.rec : (const uint32_t*)A.col;
-                    nbr = __ldg(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> 8)) + k));
+                    nbr = (q_meta[s] & 1u) ? 0u : sp_ldg_rec(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> 8)) + k));
                 } else {
                     nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
                 }
@@ -660,28 +685,37 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
                 } else {
                     issue1(0, e_pre);
                     e_pre += e_stride;
-                    issue2(0);
+                    if (NS == 3) issue2(0);
                     issue1(1, e_pre);
                     e_pre += e_stride;
+                    if (NS > 3) {
+#pragma unroll
+                        for (int q = 2; q < NS - 1; ++q) {
+                            issue1(q, e_pre);
+                            e_pre += e_stride;
+                        }
+                        issue2(0);
+                        issue2(1);
+                    }
                 }
                 int rem = n_super;  // super-steps left in this chunk
-                Dec dec[3];  // decisions of the step being committed and of the next one (rotating with the stage sets)
+                Dec dec[NS];  // decisions of the step being committed and of the next one (rotating with the stage sets)
                 evaluate(0, rem != 1 || in_last, dec[0]);
                 if (RING) coop_sync();  // all reads before anybody writes
                 while (rem > 0) {
-                    // blocks of at most 120 own steps (a multiple of the 3 register sets): the packed count
+                    // blocks of at most 120 own steps (a multiple of the 3, 4 or 5 register sets): the packed count
                     // deltas of a lane move by at most 1 per step and are folded after each block
                     const int stop = rem > 120 ? rem - 120 : 0;
                     while (rem > stop) {
 #pragma unroll
-                        for (int u = 0; u < 3; ++u) {
+                        for (int u = 0; u < NS; ++u) {
                             if (rem == stop) break;
-                            issue2((u + 1) % 3);  // the next own step's neighbour, out of the entry gathered a step ago
+                            issue2((u + ISS2) % NS);  // the neighbour of the next own step (ISS2 = 2: of the one after), out of the entry gathered earlier
                             const bool active = rem != 1 || in_last;
                             const bool active_next = rem > 2 || (rem == 2 && in_last);
                             // write phase of this step, read phase: verify it, evaluate the next one
                             Dec& cur = dec[u];
-                            Dec& nxt = dec[(u + 1) % 3];
+                            Dec& nxt = dec[(u + 1) % NS];
                             const bool lost = write(cur);
                             settle_writes(lost);
                             // The draws of the step after the next one sit in the read phase on purpose: its block
@@ -691,16 +725,16 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
                                 resolve((u + 2) % 3);  // two own steps ahead: agent + entry gather
                                 draw(e_pre);           // three own steps ahead: Philox + alias gather
                             } else {
-                                issue1((u + 2) % 3, e_pre);  // two own steps ahead: Philox + gather
+                                issue1((u + NS - 1) % NS, e_pre);  // NS - 1 own steps ahead: Philox + gather
                             }
                             e_pre += e_stride;
                             const bool bad = changed(u, active, cur, lost);
-                            evaluate((u + 1) % 3, active_next, nxt);
+                            evaluate((u + 1) % NS, active_next, nxt);
                             if (!coop_any(bad)) {
                                 if (cur.acc) book(u, cur);
                             } else {
                                 hazard_rounds(u, active, cur, bad, lost);
-                                evaluate((u + 1) % 3, active_next, nxt);  // the state has moved on
+                                evaluate((u + 1) % NS, active_next, nxt);  // the state has moved on
                                 if (RING) coop_sync();
                             }
                             --rem;
@@ -1269,6 +1303,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
     const size_t per_slot_min = cnt_bytes + 16 + thr_bytes;      // + the reduction words of a COOP chain
     const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
+    const bool batch_graph = g != nullptr && g->batch > 1;
     // Launches the local chains [c0, c1) with the geometry that suits their number; returns the chains one wave
     // of that geometry holds (resident chain slots on the whole device).
     auto launch_range = [&](int64_t c0, int64_t c1, bool wide, bool launch, int64_t* wave, int* wpc_out) -> int {
@@ -1297,11 +1332,15 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
                 // with about sqrt(0.7 N) events in flight (measured: N = 1e4 -> 2 warps, 1e5 -> 8, 1e6 -> 16+).
                 int w_cap = 1;
                 while (w_cap < 16 && (double)(64 * w_cap) * (double)(64 * w_cap) <= 0.7 * (double)n) w_cap *= 2;
+                // A batch of per-run graphs lives in HBM and the rate of random DRAM rows bounds the kernel: fewer
+                // graphs in flight, each read by more warps, find more open rows (N = 1e5, events/s with 1 / 2 / 4 / 8 /
+                // 16 warps per chain: 2.9e10 / 3.4e10 / 4.8e10 / 3.9e10 / 2.2e10) -- half the cap, fewer chains on a tie.
+                if (batch_graph) w_cap = std::max(1, w_cap / 2);
                 int best = 0;
                 for (int sl = fit; sl >= 1; --sl) {
                     int w = std::min(max_warps / sl, w_cap);
                     if (w > 1 && sl > 15) w = 1;  // named barriers 1..15 identify the chains of a CTA
-                    if (sl * w > best) {
+                    if (sl * w > best || (batch_graph && sl * w == best)) {
                         best = sl * w;
                         slots = sl;
                         wpc = w;
@@ -1370,7 +1409,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     double cost = 0.0, cost_wide = 1e300;
     SP_TRY(plan(false, &tail_begin, &cost));
     bool wide = false;
-    if (o->warps_per_chain == 0 && !o->force_global_state && graph_kind != 0) {
+    if (o->warps_per_chain == 0 && !o->force_global_state && graph_kind != 0 && !batch_graph) {
         int64_t wave_n = 0, wave_w = 0;
         SP_TRY(launch_range(0, num_chains, false, false, &wave_n, nullptr));
         SP_TRY(launch_range(0, num_chains, true, false, &wave_w, nullptr));

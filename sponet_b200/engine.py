@@ -121,6 +121,11 @@ class GraphBatch:
     __del__ = close
 
 
+def trim_graph_batch_memory() -> None:
+    """Returns the device memory kept from destroyed graph batches (sponet_graph_batch_trim) to the driver."""
+    _lib.check(_lib.lib().sponet_graph_batch_trim())
+
+
 class GraphCache:
     """One GraphHandle per (network identity, device); rebuilt when the adjacency object changes."""
 

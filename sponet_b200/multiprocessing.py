@@ -368,7 +368,12 @@ def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng
 
 _NETWORK_STREAMS = 8
 _FORCE_HOST_NETWORKS = False  # tests: take the host-generated pipeline although the generator has device_batch
-_BATCH_BYTES = 24 << 30       # device memory one batch of generated graphs may take
+_BATCH_BYTES = None           # device memory one batch of generated graphs may take (None: from the device, see below)
+_POOLED = [0]                 # bytes of the last batch: kept by the library's pool, so "free" understates what is available
+
+
+def _pooled_bytes_hint() -> int:
+    return _POOLED[0]
 
 
 def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar):
@@ -392,7 +397,13 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
     # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
     mean_entries = N * (getattr(gen, "p", 0.0) * (N - 1) + 2.0)
     per_graph = 84.0 * N + 4.0 * mean_entries + (T * N if cv is None else 0)
-    max_graphs = int(min(_BATCH_BYTES // per_graph, (2**32 - 1) // (16 * N), (2**32 - 1) // (1.2 * mean_entries)))
+    budget = _BATCH_BYTES
+    if budget is None:  # a third of the device (60 GB of a B200's 180), never more than is free right now
+        import torch
+
+        free, total = torch.cuda.mem_get_info()
+        budget = min(total // 3, int(0.6 * free) + _pooled_bytes_hint())
+    max_graphs = int(min(budget // per_graph, (2**32 - 1) // (16 * N), (2**32 - 1) // (1.2 * mean_entries)))
     max_graphs = max(1, max_graphs)
     s_blk = min(S, max_graphs)
     r_blk = max(1, max_graphs // s_blk)
@@ -412,6 +423,7 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
                                                   chain_offset=s0 * num_runs)
             finally:
                 batch.close()
+            _POOLED[0] = int(per_graph * (s1 - s0) * (hi - lo))
             local[s0:s1, lo - rb : hi - rb] = out_x if cv is None else out_cv
             _tick(pbar, (s1 - s0) * (hi - lo))
     del keep

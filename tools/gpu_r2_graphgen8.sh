@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+export PYTHONPATH=$PWD
+timeout 900 python -m pytest tests/test_gpu_graphgen.py tests/test_gpu_native.py tests/test_gpu_api.py -x -q 2>&1 | tail -1
+for g in 2368 1667 700 100; do timeout 300 python tools/probe_batch_kernel.py $g 4 1 0 2>&1 | tail -1; done
+timeout 900 python tools/probe_networks.py 10000 100 2>&1 | grep "device batches"
+timeout 900 python tools/probe_networks.py 2368 10 2>&1 | grep "device batches"
