@@ -36,6 +36,16 @@ def main():
     sw_dist = sample_moments_sweep(plist, x0, 1.0, 4, 21, cv, rng=np.random.default_rng(8), hist_bins=12)
     ss_dist = estimate_steady_state(plist[0], cv, tol_abs=0.02, rng=np.random.default_rng(9), verbose=False, num_chains=16)
 
+    # per-run networks generated on the device: runs sharded, graph c a function of (generator seed, c) only
+    from sponet_b200.network_generator import ErdosRenyiGenerator
+
+    def net_params():
+        gen = ErdosRenyiGenerator(800, 0.01, rng=np.random.default_rng(21), force_no_isolates=True)
+        return CNVMParameters(num_opinions=3, network_generator=gen, r=workloads.R3, r_tilde=workloads.RT3)
+
+    xn = np.random.default_rng(1).integers(0, 3, (2, 800))
+    _, n_dist_cv = sample_many_runs(net_params(), xn, 1.5, 4, 11, collective_variable=OpinionShares(3), rng=np.random.default_rng(22))
+
     # the same calls on ONE GPU (sharding switched off locally)
     real = smp._dist
     smp._dist = lambda: (0, 1)
@@ -48,8 +58,10 @@ def main():
                                             rng=np.random.default_rng(7))
     sw_one = sample_moments_sweep(plist, x0, 1.0, 4, 21, cv, rng=np.random.default_rng(8), hist_bins=12)
     ss_one = estimate_steady_state(plist[0], cv, tol_abs=0.02, rng=np.random.default_rng(9), verbose=False, num_chains=16)
+    _, n_one_cv = sample_many_runs(net_params(), xn, 1.5, 4, 11, collective_variable=OpinionShares(3), rng=np.random.default_rng(22))
     smp._dist = real
     sm._dist = real
+    assert n_dist_cv.shape == (2, 11, 4, 3) and np.array_equal(n_dist_cv, n_one_cv), "sharded per-run-network ensemble differs"
     for a, b in zip(sw_dist, sw_one):
         assert np.array_equal(a, b), "sharded sweep differs from the single-GPU sweep"
     assert np.array_equal(ss_dist, ss_one), "sharded steady-state estimate differs"

@@ -10,7 +10,6 @@ prof() {  # name, kernel regex, title, command...
   python tools/ncu_summary.py /tmp/prof/$name.ncu-rep gpurun_out/${name}_summary.md "$title" > /dev/null 2>&1
   rm -f /tmp/prof/$name.ncu-rep
 }
-prof r2_cnvm_batch cnvm_native "round 2: cnvm_native_kernel<2,smem,csr,noalias,coop> on a batch of 1184 per-run ER graphs (N=1e5, 64-byte agent records), t_max=2" python tools/probe_batch_kernel.py 1184 2 1
-prof r2_cnvm_batch_norec cnvm_native "same without agent records (row gather, then column gather)" python tools/probe_batch_kernel.py 1184 2 0
-cat gpurun_out/plain_r2_cnvm_batch.log gpurun_out/plain_r2_cnvm_batch_norec.log
-ls -la gpurun_out | tail -8
+prof r2_cnvm_batch cnvm_native "round 2 (final): cnvm_native_kernel<2,smem,csr,noalias,coop> on a batch of 2368 per-run ER graphs (N=1e5, 64-byte agent records, 4 warps per chain), t_max=2" python tools/probe_batch_kernel.py 2368 2 1
+cat gpurun_out/plain_r2_cnvm_batch.log
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
