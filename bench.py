@@ -624,6 +624,144 @@ def run_sweep(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------------
+# --workload networks: H with a NEW Erdos-Renyi network for every realization
+# ---------------------------------------------------------------------------------------------
+# Mean degree 16 with rejection of samples that contain an isolated vertex (1 % of them): the closest workload to H that the
+# reference can run.  With H's mean degree 10 a sample has ~4.5 isolates: the reference then either gives up after
+# max_sample_time (RuntimeError, sponet/network_generator.py:75-78) or, with force_no_isolates=True, never returns --
+# `while (j := i) == i` in _unisolate_vertices (:451) is always true.  (tools/probe_networks.py measures this repo on H's own
+# degree with the repair rule: profiles/r2_kernels.md section 6.)
+NET_DEGREE = 16.0
+NET_P = NET_DEGREE / (N_AGENTS - 1)
+
+
+def run_networks_reference(args) -> None:
+    """The unmodified reference on the same workload: `sponet.sample_many_runs` with `sponet.ErdosRenyiGenerator` in the
+    parameters -- every worker draws a networkx graph before every run (sponet/cnvm/model.py:95-96)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    ok, why = numba_reference_available()
+    if not ok:
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+        return
+    os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join("/tmp", f"numba_cache_{os.getuid()}"))
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import sponet
+    from sponet_b200 import workloads
+
+    threads = host_threads()
+    gen = sponet.ErdosRenyiGenerator(N_AGENTS, NET_P, max_sample_time=120, rng=np.random.default_rng(1))
+    params = sponet.CNVMParameters(num_opinions=3, network_generator=gen, r=workloads.R3, r_tilde=workloads.RT3, alpha=1.0)
+    x0 = np.random.default_rng(0).integers(0, 3, N_AGENTS).astype(np.uint8)
+    cv = sponet.OpinionShares(3)
+    rate = params.r_imit * N_AGENTS + params.r_noise * N_AGENTS
+
+    def call(runs, t_max, seed):
+        t0 = time.perf_counter()
+        sponet.sample_many_runs(params, x0, t_max, NUM_T, runs, n_jobs=threads, collective_variable=cv, rng=np.random.default_rng(seed))
+        return time.perf_counter() - t0
+
+    call(threads, 0.05, 1)  # JIT compile + cache
+    tot_ev, tot_sec = 0.0, 0.0
+    for k in range(max(args.steps, 1)):
+        tot_sec += call(threads, T_MAX, 1000 + k)
+        tot_ev += threads * T_MAX * rate
+    value = tot_ev / tot_sec
+    line = {"impl": "reference", "metric": "agent-update events/sec (CNVM, a new ER N=1e5 network per realization)", "value": value,
+            "unit": "events/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 0, "ms_per_step": 1e3 * tot_sec / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": f"H's model with network_generator=ErdosRenyiGenerator({N_AGENTS}, {NET_DEGREE:g}/(N-1)): "
+                                   f"{threads} realizations per step, t_max=100, T=101",
+                       "reference_arm": "unmodified reference (baseline/_ref): sponet.sample_many_runs, whole call (process pool included)"},
+            "cpu_baseline": {"value": value, "unit": "events/s", "cores": threads, "kind": "reference",
+                             "sample": f"{threads} realizations per step, each on its own networkx graph"},
+            "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_networks(args) -> None:
+    """1e4 realizations per GPU of H's model, each on its own G(N, p) generated on the device, through the public API
+    (`sample_many_runs` with `sponet_b200.ErdosRenyiGenerator`): host buffers in and out, graph generation, pooled batch
+    memory and the all-gather of the result inside the timed region (wall clock, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from sponet_b200 import CNVMParameters, ErdosRenyiGenerator, OpinionShares, sample_many_runs, workloads
+    from sponet_b200 import multiprocessing as mp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    x0 = np.random.default_rng(0).integers(0, 3, N_AGENTS).astype(np.uint8)
+    cv = OpinionShares(3)
+    R = RUNS_PER_GPU * world
+
+    def params(seed):
+        gen = ErdosRenyiGenerator(N_AGENTS, NET_P, rng=np.random.default_rng(seed))
+        return CNVMParameters(num_opinions=3, network_generator=gen, r=workloads.R3, r_tilde=workloads.RT3, alpha=1.0)
+
+    # self-check: the result does not depend on how the realizations are cut into blocks of graphs
+    _, a = sample_many_runs(params(3), x0, 0.5, 4, 24 * world, collective_variable=cv, rng=np.random.default_rng(4))
+    mp._BATCH_BYTES = int(7 * 16e6)
+    _, b = sample_many_runs(params(3), x0, 0.5, 4, 24 * world, collective_variable=cv, rng=np.random.default_rng(4))
+    mp._BATCH_BYTES = None
+    blocks_ok = bool(np.array_equal(a, b))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for w in range(args.warmup):
+        sample_many_runs(params(10 + w), x0, T_MAX / 20, NUM_T, R, collective_variable=cv, rng=np.random.default_rng(w))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        _, c = sample_many_runs(params(100 + k), x0, T_MAX, NUM_T, R, collective_variable=cv, rng=np.random.default_rng(200 + k))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    tt = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec = float(tt.cpu()[0])
+        rate = (workloads.R3.max() + 3 * workloads.RT3.max()) * N_AGENTS
+        value = R * T_MAX * rate * args.steps / sec
+        base = None
+        if not args.no_cpu_baseline:
+            try:
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+                for key in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                    env.pop(key, None)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "networks",
+                                    "--steps", "1"], capture_output=True, text=True, timeout=900, env=env)
+                base = json.loads(r.stdout.strip().splitlines()[-1]).get("cpu_baseline")
+            except Exception as e:
+                base = {"unavailable": f"{type(e).__name__}: {e}"}
+        line = {"metric": "agent-update events/sec (CNVM, a new ER N=1e5 network per realization)", "value": value, "unit": "events/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8 (2-bit packed states), uint32 graph records", "data": "synthetic",
+                "config": {"workload": f"H's model with network_generator=ErdosRenyiGenerator({N_AGENTS}, {NET_DEGREE:g}/(N-1)): "
+                                       f"{RUNS_PER_GPU} realizations per GPU, each on its own graph generated on the device, "
+                                       "t_max=100, T=101, OpinionShares",
+                           "parallelism": f"realizations split over {world} GPU(s), blocks of graphs per launch"},
+                "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": int(x0.nbytes), "d2h_bytes_per_step": int(c.nbytes),
+                        "api": "sponet_b200.sample_many_runs(CNVMParameters(network_generator=ErdosRenyiGenerator(...)), x0, 100, 101, R, OpinionShares(3))"},
+                "block_size_independent": blocks_ok, "clocks": clocks, "cpu_baseline": base,
+                "sample_mean_final_shares": [float(v) for v in c[:, -1].mean(0) / N_AGENTS]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
 # --all-configs: every BASELINE.json configuration shape on one GPU next to the CPU arm
 # (writes gpurun_out/configs.json; summarised in profiles/r1_configs.md).  Not part of the default run.
 # ---------------------------------------------------------------------------------------------
@@ -768,7 +906,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the side measurements of configs 2-4")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 1e4 realizations per GPU; strong: 1e4 realizations in total (SURVEY.md 8(d))")
-    ap.add_argument("--workload", default="H", choices=["H", "sweep"], help="sweep: BASELINE config 5 (moments all-reduced)")
+    ap.add_argument("--workload", default="H", choices=["H", "sweep", "networks"],
+                    help="sweep: BASELINE config 5 (moments all-reduced); networks: H with a new network per realization")
     ap.add_argument("--sweep-runs", type=int, default=100_000, help="realizations per sweep point on 8 GPUs (scaled by N/8)")
     ap.add_argument("--all-configs", action="store_true", help="measure every BASELINE config shape (one GPU)")
     args = ap.parse_args()
@@ -776,7 +915,10 @@ def main():
         run_all_configs()
         return
     if args.impl == "reference":
-        run_reference_arm(args)
+        if args.workload == "networks":
+            run_networks_reference(args)
+        else:
+            run_reference_arm(args)
         return
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         port = str(29500 + os.getpid() % 2000)
@@ -785,6 +927,9 @@ def main():
                                    os.path.abspath(__file__), *sys.argv[1:]])
     if args.workload == "sweep":
         run_sweep(args)
+        return
+    if args.workload == "networks":
+        run_networks(args)
         return
     run_gpu_arm(args)
 

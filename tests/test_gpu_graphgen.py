@@ -237,3 +237,31 @@ def test_per_run_networks_agree_with_the_host_pipeline_statistically():
         z = (da.mean() - db.mean()) / np.sqrt(da.var() / R + db.var() / R)
         assert abs(z) < 5.0, (k, z)
         assert 0.6 < da.var() / db.var() < 1.6
+
+
+def test_h_sized_batch_beyond_2_31_entries(oracle):
+    """2 368 graphs of H's size in one batch: 2.37e9 adjacency entries, i.e. row offsets beyond 2^31 (they are unsigned 32-bit)
+    and 15 GB of records.  The last graphs equal the sequential generator, and chains on them the sequential chain oracle."""
+    from sponet_b200 import CNVM, CNVMParameters, engine
+
+    n, G, M = 100_000, 2368, 3
+    p = 10 / (n - 1)
+    kw = dict(num_opinions=M, r=[[0, 1, 2], [1, 0, 1], [2, 0, 0]], r_tilde=[[0, .2, .1], [0, 0, .1], [.1, .2, 0]])
+    batch = engine.GraphBatch(n, p, 31337, 1, G, 0, G, force_no_isolates=True)
+    assert batch.info()["nnz"] > 2**31
+    x0 = np.random.default_rng(0).integers(0, M, n).astype(np.uint8)
+    t_eval = np.linspace(0.0, 1.0, 3)
+    model = CNVM(CNVMParameters(num_agents=n, **kw))
+    struct, keep = model._struct()
+    x, _ = engine.run_native("cnvm", batch, n, struct, x0[None, :], t_eval, 5, G, 0, G, want_x=True, final_state_only=True)
+    assert x.shape[:2] == (1, G)
+    for slot in (0, 2200, G - 1):
+        rp, col = batch.csr(slot)
+        orp, ocol, _ = oracle.er_graph(n, p, 31337, slot, force_no_isolates=True)
+        np.testing.assert_array_equal(rp, orp)
+        np.testing.assert_array_equal(col, ocol)
+        ox, _ = _oracle_chain(oracle, kw, rp, col, x0, t_eval, 5, slot)
+        np.testing.assert_array_equal(x[0, slot].reshape(-1, n)[-1], ox[-1])
+    batch.close()
+    del keep
+    engine.trim_graph_batch_memory()
