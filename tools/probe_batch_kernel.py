@@ -10,7 +10,8 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 t_max = float(sys.argv[2]) if len(sys.argv) > 2 else 2.0
 records = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
 wpc = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-N, M = 100_000, 3
+import os
+N, M = int(os.environ.get("PROBE_N", "100000")), 3
 kw = dict(num_opinions=M, r=[[0, 1, 2], [1, 0, 1], [2, 0, 0]], r_tilde=[[0, .2, .1], [0, 0, .1], [.1, .2, 0]])
 model = CNVM(CNVMParameters(num_agents=N, **kw))
 struct, keep = model._struct()
@@ -27,4 +28,4 @@ for rep in range(4):
     engine.run_native("cnvm", b, N, struct, d_x0, t_eval, 77 + rep, G, 0, G, cv_spec=spec, want_cv=True, counters=counters, warps_per_chain=wpc)
     e1.record()
     torch.cuda.synchronize()
-    print(f"batch of {G} graphs records={records} wpc={wpc} t_max={t_max} extra rounds/step {counters[3].item() / max(counters[2].item(), 1):.3f}: {counters[0].item() / e0.elapsed_time(e1) * 1e3:.4g} events/s ({e0.elapsed_time(e1):.1f} ms)")
+    print(f"N={N} batch of {G} graphs records={records} wpc={wpc} t_max={t_max} extra rounds/step {counters[3].item() / max(counters[2].item(), 1):.3f}: {counters[0].item() / e0.elapsed_time(e1) * 1e3:.4g} events/s ({e0.elapsed_time(e1):.1f} ms)")
