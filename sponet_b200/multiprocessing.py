@@ -339,8 +339,7 @@ def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng
     if spec is not None and spec.edge:
         spec = None  # an edge CV carries its own (fixed) graph; evaluated from the returned states below
     gen = p.network_generator
-    if (kind == "cnvm" and hasattr(gen, "device_batch") and p.alpha == 1 and (cv is None or spec is not None)
-            and not _FORCE_HOST_NETWORKS):
+    if kind == "cnvm" and hasattr(gen, "device_batch") and p.alpha == 1 and not _FORCE_HOST_NETWORKS:
         # the generator makes its graphs on the GPU: the whole ensemble in a few launches, one graph per chain
         return _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar)
     bounds = np.concatenate(([0], np.cumsum(_split_runs(pairs, world))))
@@ -393,10 +392,11 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
     rb, re = int(bounds[rank]), int(bounds[rank + 1])
     D = N if cv is None else cv.dimension
     local = np.empty((S, re - rb, T, D), dtype=np.uint8 if cv is None else np.float64)
+    want_x = cv is None or spec is None  # a CV the kernels cannot evaluate: from the returned states, pair by pair
     # graphs per block: device memory (rows 8 B + record 64 B + 12 B of build scratch per vertex, 4 B per entry), the
     # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
     mean_entries = N * (getattr(gen, "p", 0.0) * (N - 1) + 2.0)
-    per_graph = 84.0 * N + 4.0 * mean_entries + (T * N if cv is None else 0)
+    per_graph = 84.0 * N + 4.0 * mean_entries + (T * N if want_x else 0)
     budget = _BATCH_BYTES
     if budget is None:  # a third of the device (60 GB of a B200's 180), never more than is free right now
         import torch
@@ -419,12 +419,19 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
             batch = gen.device_batch(gseed, s1 - s0, num_runs, s0 * num_runs + lo, s0 * num_runs + hi)
             try:
                 out_x, out_cv = engine.run_native("cnvm", batch, N, struct, st, t_out, seed, num_runs, lo, hi,
-                                                  cv_spec=spec, want_cv=cv is not None, want_x=cv is None,
+                                                  cv_spec=None if want_x else spec, want_cv=not want_x, want_x=want_x,
                                                   chain_offset=s0 * num_runs)
             finally:
                 batch.close()
             _POOLED[0] = int(per_graph * (s1 - s0) * (hi - lo))
-            local[s0:s1, lo - rb : hi - rb] = out_x if cv is None else out_cv
+            if cv is None:
+                local[s0:s1, lo - rb : hi - rb] = out_x
+            elif want_x:
+                for j in range(s1 - s0):
+                    for i in range(hi - lo):
+                        local[s0 + j, lo - rb + i] = np.asarray(cv(out_x[j, i]))
+            else:
+                local[s0:s1, lo - rb : hi - rb] = out_cv
             _tick(pbar, (s1 - s0) * (hi - lo))
     del keep
     _close(pbar)

@@ -205,6 +205,22 @@ def test_sample_many_runs_with_a_device_generator(oracle):
     _, mean, var, ns = sample_moments(params(8), states[0], 2.0, T, R, rel_tol=1e9, collective_variable=cv, rng=np.random.default_rng(1))
     assert ns == R
     np.testing.assert_allclose(mean, c[0].mean(0), atol=1e-12)
+    # a collective variable the kernels do not evaluate (its own fixed graph): from the returned states of the same chains
+    import networkx as nx
+
+    from sponet_b200 import Interfaces
+
+    kw2 = dict(num_opinions=2, r=[[0, 1.0], [1.2, 0]], r_tilde=[[0, 0.05], [0.02, 0]])
+    iface = Interfaces(nx.cycle_graph(n))
+
+    def params2(seed):
+        return CNVMParameters(network_generator=ErdosRenyiGenerator(n, p, rng=np.random.default_rng(seed), force_no_isolates=True), **kw2)
+
+    s2 = states % 2
+    _, ci = sample_many_runs(params2(8), s2, 2.0, T, 3, collective_variable=iface, rng=np.random.default_rng(1))
+    _, xi = sample_many_runs(params2(8), s2, 2.0, T, 3, rng=np.random.default_rng(1))
+    assert ci.shape == (S, 3, T, 1)
+    np.testing.assert_array_equal(ci[1, 2], iface(xi[1, 2]))
     # alpha != 1 (agent weights depend on the graph): the host pipeline, still a fresh network per run
     pa = CNVMParameters(network_generator=ErdosRenyiGenerator(n, p, rng=np.random.default_rng(8), force_no_isolates=True), alpha=0.5, **kw)
     _, ca = sample_many_runs(pa, states[0], 1.0, 3, 2, collective_variable=cv, rng=np.random.default_rng(1))
