@@ -1,7 +1,11 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=$PWD
-nvidia-smi --query-gpu=name --format=csv,noheader | wc -l
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -8
-timeout 600 python bench.py --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_2gpu_weak.json 2> gpurun_out/bench_2gpu_weak.err; echo "weak rc=$?"; tail -2 gpurun_out/bench_2gpu_weak.err; cat gpurun_out/bench_2gpu_weak.json
-timeout 600 python bench.py --gpus 2 --steps 2 --warmup 1 --scaling strong > gpurun_out/bench_2gpu_strong.json 2> gpurun_out/bench_2gpu_strong.err; echo "strong rc=$?"; tail -2 gpurun_out/bench_2gpu_strong.err; cat gpurun_out/bench_2gpu_strong.json
-timeout 600 python bench.py --gpus 2 --workload sweep --steps 1 --sweep-runs 8000 > gpurun_out/sweep_2gpu.json 2> gpurun_out/sweep_2gpu.err; echo "sweep rc=$?"; tail -2 gpurun_out/sweep_2gpu.err; cat gpurun_out/sweep_2gpu.json
+timeout 900 python bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/bench_2gpu_weak.json 2> /dev/null; echo "2 weak rc=$?"
+timeout 600 python bench.py --gpus 2 --steps 5 --warmup 3 --scaling strong --no-cpu-baseline --no-configs > gpurun_out/bench_2gpu_strong.json 2> /dev/null; echo "2 strong rc=$?"
+python - <<'PY'
+import json
+for f in ["bench_2gpu_weak","bench_2gpu_strong"]:
+    for l in open(f"gpurun_out/{f}.json"):
+        if l.startswith("{"):
+            d=json.loads(l); print(f, "%.4g"%d["value"], "%.4g"%d["e2e"]["value"], d.get("sharded_equals_single"))
+PY
