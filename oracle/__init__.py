@@ -480,3 +480,15 @@ def er_graph(n, p, seed, c, force_no_isolates=False, max_attempts=64):
     if nnz < 0:
         raise RuntimeError("oracle_er_graph: column buffer too small")
     return row_ptr, col[:nnz].copy(), used.value
+
+
+def ba_graph(n, m, seed, c):
+    """oracle_ba_graph: graph index c of the device-side Barabasi-Albert generator as (row_ptr, col)."""
+    f = lib().oracle_ba_graph
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, _i32, _i32]
+    row_ptr = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(2 * m * (n - m), dtype=np.int32)
+    nnz = f(n, m, seed, c, row_ptr, col)
+    assert nnz == col.size
+    return row_ptr, col

@@ -61,10 +61,12 @@ struct sponet_graph {
     // A BATCH of `batch` graphs over the same n agents (graphgen.cu: one graph per chain of a native call):
     // d_row is [batch * n] with ABSOLUTE 32-bit offsets into the shared d_col / d_col4; no d_row_ptr, no table.
     int64_t batch;       // 1 for an ordinary graph
-    // Batch, CNVM: one 64-byte record per agent = (degree | (row begin - graph's first entry) << 8, first 15 neighbours):
-    // the degree and the sampled neighbour of most agents share ONE DRAM burst (a batch never fits the L2); neighbours
-    // 15.. are read from d_col.  nullptr when the batch was created without records (or a degree exceeds 255).
+    // Batch, CNVM: one 64-byte record per agent = (degree | (row begin - graph's first entry) << rec_deg_bits, first 15
+    // neighbours): the degree and the sampled neighbour of most agents share ONE DRAM burst (a batch never fits the L2);
+    // neighbours 15.. are read from d_col.  rec_deg_bits = bits of the largest degree (>= 8).  nullptr when the batch was
+    // created without records or degree and offset do not fit 32 bits together.
     uint32_t* d_rec;     // [batch * n * 16]
+    int32_t rec_deg_bits;
     bool pooled;         // device memory from sp_pool_alloc (graphgen.cu)
 };
 

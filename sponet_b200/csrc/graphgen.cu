@@ -22,6 +22,7 @@
 //   Rows are sorted by neighbour id.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -233,23 +234,47 @@ __global__ void er_fill_patch_kernel(ErArgs A, const int2* patch, const uint32_t
     col[o[e.y] + atomicAdd(cur + e.y, 1u)] = e.x;
 }
 
-// sorts every row (the atomics above fill them in arbitrary order), writes the (begin, degree) descriptors
-__global__ void er_finish_kernel(ErArgs A, const uint32_t* off, const uint32_t* deg, int32_t* col, int2* row,
-                                 uint32_t* dmin, uint32_t* dmax) {
+// sorts every row (the atomics above fill them in arbitrary order), writes the (begin, degree) descriptors; degree range of
+// the batch and the largest number of adjacency entries of one graph
+__global__ void batch_finish_kernel(int64_t rows, int64_t n, const uint32_t* off, const uint32_t* deg, int32_t* col, int2* row,
+                                    uint32_t* dmin, uint32_t* dmax, uint32_t* gmax) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = tid < A.count * A.n;
+    const bool live = tid < rows;
     const uint32_t d = live ? deg[tid] : 0u;
     int32_t* r = col + (live ? off[tid] : 0u);
-    for (uint32_t a = 1; a < d; ++a) {  // insertion sort: rows are short (np for sparse graphs)
-        const int32_t key = r[a];
-        uint32_t q = a;
-        while (q > 0 && r[q - 1] > key) {
-            r[q] = r[q - 1];
-            --q;
+    if (d <= 48u) {  // insertion sort: rows are short ...
+        for (uint32_t a = 1; a < d; ++a) {
+            const int32_t key = r[a];
+            uint32_t q = a;
+            while (q > 0 && r[q - 1] > key) {
+                r[q] = r[q - 1];
+                --q;
+            }
+            r[q] = key;
         }
-        r[q] = key;
+    } else {  // ... except the hubs of a scale-free graph (thousands of neighbours): heap sort
+        auto sift = [&](uint32_t root, uint32_t end) {
+            const int32_t key = r[root];
+            for (;;) {
+                uint32_t child = 2 * root + 1;
+                if (child >= end) break;
+                if (child + 1 < end && r[child + 1] > r[child]) ++child;
+                if (r[child] <= key) break;
+                r[root] = r[child];
+                root = child;
+            }
+            r[root] = key;
+        };
+        for (uint32_t a = d / 2; a-- > 0;) sift(a, d);
+        for (uint32_t end = d - 1; end > 0; --end) {
+            const int32_t top = r[0];
+            r[0] = r[end];
+            r[end] = top;
+            sift(0, end);
+        }
     }
     if (live) row[tid] = make_int2((int)off[tid], (int)d);
+    if (live && tid % n == n - 1) atomicMax(gmax, off[tid] + d - off[tid - (n - 1)]);
     const uint32_t lo = __reduce_min_sync(0xffffffffu, live ? d : 0xFFFFFFFFu), hi = __reduce_max_sync(0xffffffffu, d);
     if ((threadIdx.x & 31) == 0) {
         atomicMin(dmin, lo);
@@ -272,7 +297,7 @@ __global__ void er_pad_kernel(int64_t rows, int64_t n, const int2* row, const in
 }
 
 // 64-byte agent records of the CNVM kernel (common.cuh, sponet_graph::d_rec)
-__global__ void er_record_kernel(int64_t rows, int64_t n, const int2* row, const int32_t* col, uint32_t* rec) {
+__global__ void batch_record_kernel(int64_t rows, int64_t n, const int2* row, const int32_t* col, uint32_t* rec, int deg_bits) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per record word
     const int64_t a = t >> 4;
     const int w = (int)(t & 15);
@@ -281,7 +306,7 @@ __global__ void er_record_kernel(int64_t rows, int64_t n, const int2* row, const
     uint32_t v;
     if (w == 0) {
         const uint32_t first = (uint32_t)row[a - a % n].x;  // the graph's first adjacency entry
-        v = (uint32_t)r.y | (((uint32_t)r.x - first) << 8);
+        v = (uint32_t)r.y | (((uint32_t)r.x - first) << deg_bits);
     } else {
         v = (w - 1 < r.y) ? (uint32_t)col[(uint32_t)r.x + (uint32_t)(w - 1)] : 0u;
     }
@@ -313,6 +338,187 @@ struct Freer {
     }
 };
 
+// ---- Barabasi-Albert (networkx.barabasi_albert_graph, as sponet/network_generator.py:118-144 calls it) ----
+// Star on the vertices 0 .. m; every later vertex t attaches to m DISTINCT targets drawn uniformly from the endpoint list of
+// the edges so far (= proportional to degree), duplicates drawn again.  Edge e < m is (0, e + 1), edge e >= m is the
+// (e % m)-th edge of vertex e / m + m; position 2 e of the endpoint list is the edge's source, 2 e + 1 its target.
+// Candidate k of vertex t: position mulhi(word 0 of Philox(counter (k, t, c_lo, c_hi[16] | 5 << 24), key seed), 2 m (t - m)).
+// A vertex depends on earlier vertices only, so the batch is resolved in rounds (Sanders & Schulz, "Scalable generation of
+// scale-free graphs", 2016): a vertex whose candidates point at unresolved vertices waits for the next round.
+struct BaArgs {
+    int64_t n, count, nrun, R_total, run_begin;
+    int32_t m;
+    uint64_t seed;
+};
+constexpr int BA_MAX_M = 64;
+
+__device__ __forceinline__ uint64_t ba_graph_index(const BaArgs& A, int64_t b) {
+    const int64_t j = b / A.nrun, i = b - j * A.nrun;
+    return (uint64_t)(j * A.R_total + A.run_begin + i);
+}
+
+__global__ void ba_resolve_kernel(BaArgs A, int32_t* targets, volatile uint8_t* done, unsigned long long* remaining) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    const int64_t b = tid / A.n, t = tid - b * A.n;
+    const int m = A.m;
+    if (t <= m || done[tid]) return;
+    const uint64_t c = ba_graph_index(A, b);
+    const uint32_t range = (uint32_t)(2 * (int64_t)m * (t - m));
+    int32_t tg[BA_MAX_M];
+    int cnt = 0;
+    for (uint32_t k = 0; cnt < m; ++k) {
+        const uint4 r4 = sp_philox4x32_10(k, (uint32_t)t, (uint32_t)c, ((uint32_t)(c >> 32) & 0xFFFFu) | (5u << 24), (uint32_t)A.seed,
+                                          (uint32_t)(A.seed >> 32));
+        const uint32_t r = __umulhi(r4.x, range);
+        const uint32_t e = r >> 1;
+        int32_t v;
+        if (!(r & 1u)) {
+            v = e < (uint32_t)m ? 0 : (int32_t)(e / (uint32_t)m) + m;
+        } else if (e < (uint32_t)m) {
+            v = (int32_t)e + 1;
+        } else {
+            const int64_t owner = b * A.n + (int64_t)(e / (uint32_t)m) + m;
+            if (!done[owner]) return;  // next round
+            v = __ldcg(targets + owner * m + (int64_t)(e % (uint32_t)m));  // (written by another thread of this launch: not through L1)
+        }
+        bool dup = false;
+        for (int q = 0; q < cnt; ++q) dup |= (tg[q] == v);
+        if (!dup) tg[cnt++] = v;
+    }
+    for (int q = 0; q < m; ++q) targets[tid * m + q] = tg[q];
+    __threadfence();
+    done[tid] = 1;
+    atomicAdd(remaining, (unsigned long long)-1ll);
+}
+
+// the edges of vertex t (the star's for t <= m): calls f(u, v) once per edge
+template <typename F>
+__device__ __forceinline__ void ba_edges(const BaArgs& A, const int32_t* targets, int64_t tid, int64_t t, F&& f) {
+    if (t == 0) return;
+    if (t <= A.m) {
+        f(0, (int32_t)t);
+        return;
+    }
+    for (int q = 0; q < A.m; ++q) f((int32_t)t, targets[tid * A.m + q]);
+}
+
+__global__ void ba_degree_kernel(BaArgs A, const int32_t* targets, uint32_t* deg) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    const int64_t b = tid / A.n, t = tid - b * A.n;
+    uint32_t* d = deg + b * A.n;
+    ba_edges(A, targets, tid, t, [&](int32_t u, int32_t v) {
+        atomicAdd(d + u, 1u);
+        atomicAdd(d + v, 1u);
+    });
+}
+
+__global__ void ba_fill_kernel(BaArgs A, const int32_t* targets, const uint32_t* off, uint32_t* cursor, int32_t* col) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.count * A.n) return;
+    const int64_t b = tid / A.n, t = tid - b * A.n;
+    const uint32_t* o = off + b * A.n;
+    uint32_t* cur = cursor + b * A.n;
+    ba_edges(A, targets, tid, t, [&](int32_t u, int32_t v) {
+        col[o[u] + atomicAdd(cur + u, 1u)] = v;
+        col[o[v] + atomicAdd(cur + v, 1u)] = u;
+    });
+}
+
+// Common tail of the batch generators: degrees -> absolute row offsets, graph handle and adjacency array; after the
+// generator's fill kernels: rows sorted, (begin, degree) descriptors, degree range, and the layouts of the simulation kernels.
+struct BatchBuilder {
+    Freer& tmp;
+    int64_t n, B, rows;
+    const char* who;
+    uint32_t *d_off = nullptr, *d_cursor = nullptr;
+    uint64_t* d_total = nullptr;
+    sponet_graph* g = nullptr;
+    BatchBuilder(Freer& t, int64_t n_, int64_t B_, const char* w) : tmp(t), n(n_), B(B_), rows(n_ * B_), who(w) {}
+    ~BatchBuilder() {
+        if (g) sponet_graph_destroy(g);
+    }
+    sponet_graph* release() {
+        sponet_graph* r = g;
+        g = nullptr;
+        return r;
+    }
+    int scan(const uint32_t* d_deg) {
+        SP_CUDA(tmp.alloc((void**)&d_total, 8));
+        SP_CUDA(cudaMemset(d_total, 0, 8));
+        sum_u32_kernel<<<1184, 256>>>(rows, d_deg, (unsigned long long*)d_total);
+        SP_CUDA(cudaGetLastError());
+        uint64_t nnz = 0;
+        SP_CUDA(cudaMemcpy(&nnz, d_total, 8, cudaMemcpyDeviceToHost));
+        SP_REQUIRE(nnz < ((uint64_t)1 << 32), "%s: %llu adjacency entries exceed 2^32; use smaller batches", who, (unsigned long long)nnz);
+        SP_CUDA(tmp.alloc((void**)&d_off, rows * 4));
+        SP_CUDA(tmp.alloc((void**)&d_cursor, rows * 4));
+        SP_CUDA(cudaMemset(d_cursor, 0, rows * 4));
+        void* d_ws = nullptr;
+        size_t ws = 0;
+        SP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, ws, d_deg, d_off, rows));
+        SP_CUDA(tmp.alloc(&d_ws, ws));
+        SP_CUDA(cub::DeviceScan::ExclusiveSum(d_ws, ws, d_deg, d_off, rows));
+        g = new sponet_graph();
+        memset(g, 0, sizeof(*g));
+        g->batch = B;
+        g->pooled = true;
+        g->n = n;
+        g->nnz = (int64_t)nnz;
+        SP_CUDA(cudaGetDevice(&g->device));
+        SP_CUDA(sp_pool_alloc((void**)&g->d_row, rows * sizeof(int2)));
+        SP_CUDA(sp_pool_alloc((void**)&g->d_col, std::max<uint64_t>(nnz, 1) * sizeof(int32_t)));
+        return SPONET_OK;
+    }
+    int finish(const uint32_t* d_deg, int layouts) {
+        const unsigned grid = (unsigned)((rows + 255) / 256);
+        SP_CUDA(cudaGetLastError());  // (the generator's fill kernels)
+        uint32_t* d_mm;
+        SP_CUDA(tmp.alloc((void**)&d_mm, 16));
+        uint32_t mm[3] = {0xFFFFFFFFu, 0u, 0u};
+        SP_CUDA(cudaMemcpy(d_mm, mm, 12, cudaMemcpyHostToDevice));
+        batch_finish_kernel<<<grid, 256>>>(rows, n, d_off, d_deg, g->d_col, g->d_row, d_mm, d_mm + 1, d_mm + 2);
+        SP_CUDA(cudaGetLastError());
+        SP_CUDA(cudaMemcpy(mm, d_mm, 12, cudaMemcpyDeviceToHost));
+        g->min_degree = (int32_t)mm[0];
+        g->max_degree = (int32_t)mm[1];
+        // record header: the degree in the low bits, the row's offset within its graph above
+        int deg_bits = 8;
+        while (deg_bits < 31 && ((uint32_t)1 << deg_bits) <= mm[1]) ++deg_bits;
+        if ((layouts & SPONET_BATCH_RECORDS) && deg_bits <= 16 && (uint64_t)mm[2] < ((uint64_t)1 << (32 - deg_bits)) &&
+            (uint64_t)rows * 16 < ((uint64_t)1 << 32)) {
+            g->rec_deg_bits = deg_bits;
+            SP_CUDA(sp_pool_alloc((void**)&g->d_rec, (size_t)rows * 64));
+            batch_record_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256>>>(rows, n, g->d_row, g->d_col, g->d_rec, deg_bits);
+            SP_CUDA(cudaGetLastError());
+        }
+        if (layouts & SPONET_BATCH_PADDED_ROWS) {  // the CNTM kernels' layout
+            uint32_t *d_q, *d_off4;
+            uint64_t n4 = 0;
+            SP_CUDA(tmp.alloc((void**)&d_q, rows * 4));
+            SP_CUDA(tmp.alloc((void**)&d_off4, rows * 4));
+            quarter_kernel<<<grid, 256>>>(rows, d_deg, d_q);
+            SP_CUDA(cudaMemset(d_total, 0, 8));
+            sum_u32_kernel<<<1184, 256>>>(rows, d_q, (unsigned long long*)d_total);
+            SP_CUDA(cudaMemcpy(&n4, d_total, 8, cudaMemcpyDeviceToHost));
+            SP_REQUIRE(n4 < ((uint64_t)1 << 31), "%s: padded rows exceed 2^31 entries; use smaller batches", who);
+            void* d_ws2 = nullptr;
+            size_t ws2 = 0;
+            SP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, ws2, d_q, d_off4, rows));
+            SP_CUDA(tmp.alloc(&d_ws2, ws2));
+            SP_CUDA(cub::DeviceScan::ExclusiveSum(d_ws2, ws2, d_q, d_off4, rows));
+            SP_CUDA(sp_pool_alloc((void**)&g->d_row4, rows * sizeof(int2)));
+            SP_CUDA(sp_pool_alloc((void**)&g->d_col4, std::max<uint64_t>(n4, 1) * sizeof(int4)));
+            g->n_col4 = (int64_t)n4;
+            er_pad_kernel<<<grid, 256>>>(rows, n, g->d_row, g->d_col, d_off4, g->d_row4, g->d_col4);
+            SP_CUDA(cudaGetLastError());
+        }
+        SP_CUDA(cudaDeviceSynchronize());
+        return SPONET_OK;
+    }
+};
+
 }  // namespace
 
 extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isolates, uint64_t seed,
@@ -340,13 +546,12 @@ extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int fo
     const unsigned grid = (unsigned)((rows + 255) / 256);
 
     Freer tmp;
-    uint32_t *d_deg, *d_attempt, *d_iso, *d_off, *d_cursor, *d_mm;
+    uint32_t *d_deg, *d_attempt, *d_iso;
     uint8_t* d_dirty;
     SP_CUDA(tmp.alloc((void**)&d_deg, rows * 4));
     SP_CUDA(tmp.alloc((void**)&d_attempt, B * 4));
     SP_CUDA(tmp.alloc((void**)&d_iso, B * 4));
     SP_CUDA(tmp.alloc((void**)&d_dirty, B));
-    SP_CUDA(tmp.alloc((void**)&d_mm, 8));
     SP_CUDA(cudaMemset(d_deg, 0, rows * 4));
     SP_CUDA(cudaMemset(d_attempt, 0, B * 4));
     std::vector<uint8_t> dirty((size_t)B, 1);
@@ -386,92 +591,67 @@ extern "C" int sponet_graph_batch_create_er(int64_t num_agents, double p, int fo
         er_patch_kernel<<<(unsigned)((B * 32 + 255) / 256), 256>>>(A, d_deg, d_patch, d_npatch, cap);
         SP_CUDA(cudaGetLastError());
     }
-    // row offsets of the whole batch (absolute, 32-bit)
-    uint64_t* d_total;
-    SP_CUDA(tmp.alloc((void**)&d_total, 8));
-    SP_CUDA(cudaMemset(d_total, 0, 8));
-    sum_u32_kernel<<<1184, 256>>>(rows, d_deg, (unsigned long long*)d_total);
+    BatchBuilder bb(tmp, n, B, "graph_batch_create_er");
+    SP_TRY(bb.scan(d_deg));
+    er_fill_kernel<<<grid, 256>>>(A, d_attempt, bb.d_off, bb.d_cursor, bb.g->d_col);
+    if (cap > 0)
+        er_fill_patch_kernel<<<(unsigned)((B * cap + 255) / 256), 256>>>(A, d_patch, d_npatch, cap, bb.d_off, bb.d_cursor, bb.g->d_col);
+    SP_TRY(bb.finish(d_deg, layouts));
+    *out = bb.release();
+    return SPONET_OK;
+}
+
+extern "C" int sponet_graph_batch_create_ba(int64_t num_agents, int32_t m, uint64_t seed, int64_t num_states,
+                                            int64_t num_runs_total, int64_t run_begin, int64_t run_end, int layouts,
+                                            sponet_graph** out) {
+    SP_REQUIRE(out, "graph_batch_create_ba: out is NULL");
+    *out = nullptr;
+    const int64_t n = num_agents, nrun = run_end - run_begin, B = num_states * nrun;
+    SP_REQUIRE(n >= 2 && n < ((int64_t)1 << 31), "graph_batch_create_ba: num_agents out of range");
+    SP_REQUIRE(m >= 1 && m < n, "Barabasi-Albert network must have m >= 1 and m < n, m = %d, n = %lld", m, (long long)n);  // networkx's message
+    SP_REQUIRE(m <= BA_MAX_M, "graph_batch_create_ba: m <= %d", BA_MAX_M);
+    SP_REQUIRE(num_states >= 1 && nrun >= 1 && run_begin >= 0 && num_runs_total >= 1, "graph_batch_create_ba: bad run range");
+    SP_REQUIRE(B * n < ((int64_t)1 << 32), "graph_batch_create_ba: %lld graphs of %lld agents exceed 2^32 rows; use smaller batches",
+               (long long)B, (long long)n);
+    SP_REQUIRE(2 * (int64_t)m * n < ((int64_t)1 << 32), "graph_batch_create_ba: too many edges per graph");
+    BaArgs A;
+    A.n = n;
+    A.count = B;
+    A.nrun = nrun;
+    A.R_total = num_runs_total;
+    A.run_begin = run_begin;
+    A.m = m;
+    A.seed = seed;
+    const int64_t rows = B * n;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    Freer tmp;
+    int32_t* d_targets;
+    uint8_t* d_done;
+    unsigned long long* d_remaining;
+    uint32_t* d_deg;
+    SP_CUDA(tmp.alloc((void**)&d_targets, (size_t)rows * m * sizeof(int32_t)));
+    SP_CUDA(tmp.alloc((void**)&d_done, rows));
+    SP_CUDA(tmp.alloc((void**)&d_remaining, 8));
+    SP_CUDA(tmp.alloc((void**)&d_deg, rows * 4));
+    SP_CUDA(cudaMemset(d_done, 0, rows));
+    SP_CUDA(cudaMemset(d_deg, 0, rows * 4));
+    unsigned long long remaining = (unsigned long long)B * (unsigned long long)(n - 1 - m);
+    SP_CUDA(cudaMemcpy(d_remaining, &remaining, 8, cudaMemcpyHostToDevice));
+    int rounds_done = 0;
+    for (int round = 0; remaining > 0; ++round, ++rounds_done) {
+        SP_REQUIRE(round < 4096, "graph_batch_create_ba: the dependency rounds do not end");
+        ba_resolve_kernel<<<grid, 256>>>(A, d_targets, d_done, d_remaining);
+        SP_CUDA(cudaGetLastError());
+        SP_CUDA(cudaMemcpy(&remaining, d_remaining, 8, cudaMemcpyDeviceToHost));
+    }
+    if (getenv("SPONET_DEBUG")) fprintf(stderr, "graph_batch_create_ba: %d dependency rounds\n", rounds_done);
+    ba_degree_kernel<<<grid, 256>>>(A, d_targets, d_deg);
     SP_CUDA(cudaGetLastError());
-    uint64_t nnz = 0;
-    SP_CUDA(cudaMemcpy(&nnz, d_total, 8, cudaMemcpyDeviceToHost));
-    SP_REQUIRE(nnz < ((uint64_t)1 << 32), "graph_batch_create_er: %llu adjacency entries exceed 2^32; use smaller batches", (unsigned long long)nnz);
-    SP_CUDA(tmp.alloc((void**)&d_off, rows * 4));
-    SP_CUDA(tmp.alloc((void**)&d_cursor, rows * 4));
-    SP_CUDA(cudaMemset(d_cursor, 0, rows * 4));
-    {
-        void* d_ws = nullptr;
-        size_t ws = 0;
-        SP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, ws, d_deg, d_off, rows));
-        SP_CUDA(tmp.alloc(&d_ws, ws));
-        SP_CUDA(cub::DeviceScan::ExclusiveSum(d_ws, ws, d_deg, d_off, rows));
-    }
-    sponet_graph* g = new sponet_graph();
-    memset(g, 0, sizeof(*g));
-    g->batch = B;
-    g->pooled = true;
-    g->n = n;
-    g->nnz = (int64_t)nnz;
-    cudaError_t e = cudaGetDevice(&g->device);
-    if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_row, rows * sizeof(int2));
-    if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_col, std::max<uint64_t>(nnz, 1) * sizeof(int32_t));
-    if (e == cudaSuccess) {
-        er_fill_kernel<<<grid, 256>>>(A, d_attempt, d_off, d_cursor, g->d_col);
-        if (cap > 0)
-            er_fill_patch_kernel<<<(unsigned)((B * cap + 255) / 256), 256>>>(A, d_patch, d_npatch, cap, d_off, d_cursor, g->d_col);
-        const uint32_t mm[2] = {0xFFFFFFFFu, 0u};
-        e = cudaMemcpy(d_mm, mm, 8, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) {
-            er_finish_kernel<<<grid, 256>>>(A, d_off, d_deg, g->d_col, g->d_row, d_mm, d_mm + 1);
-            e = cudaGetLastError();
-        }
-    }
-    uint32_t mm[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpy(mm, d_mm, 8, cudaMemcpyDeviceToHost);
-    g->min_degree = (int32_t)mm[0];
-    g->max_degree = (int32_t)mm[1];
-    if (e == cudaSuccess && (layouts & SPONET_BATCH_RECORDS) && mm[1] <= 255u && (uint64_t)n * mm[1] < ((uint64_t)1 << 24) &&
-        (uint64_t)rows * 16 < ((uint64_t)1 << 32)) {
-        e = sp_pool_alloc((void**)&g->d_rec, (size_t)rows * 64);
-        if (e == cudaSuccess) {
-            er_record_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256>>>(rows, n, g->d_row, g->d_col, g->d_rec);
-            e = cudaGetLastError();
-        }
-    }
-    if (e == cudaSuccess && (layouts & SPONET_BATCH_PADDED_ROWS)) {  // the CNTM kernels' layout
-        uint32_t *d_q, *d_off4;
-        uint64_t n4 = 0;
-        e = tmp.alloc((void**)&d_q, rows * 4);
-        if (e == cudaSuccess) e = tmp.alloc((void**)&d_off4, rows * 4);
-        if (e == cudaSuccess) {
-            quarter_kernel<<<grid, 256>>>(rows, d_deg, d_q);
-            e = cudaMemset(d_total, 0, 8);
-            sum_u32_kernel<<<1184, 256>>>(rows, d_q, (unsigned long long*)d_total);
-            if (e == cudaSuccess) e = cudaMemcpy(&n4, d_total, 8, cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess && n4 >= ((uint64_t)1 << 31)) {
-                sponet_graph_destroy(g);
-                return sponet_fail(SPONET_ERR_INVALID, "graph_batch_create_er: padded rows exceed 2^31 entries; use smaller batches");
-            }
-            void* d_ws2 = nullptr;
-            size_t ws2 = 0;
-            if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, ws2, d_q, d_off4, rows);
-            if (e == cudaSuccess) e = tmp.alloc(&d_ws2, ws2);
-            if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_ws2, ws2, d_q, d_off4, rows);
-        }
-        if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_row4, rows * sizeof(int2));
-        if (e == cudaSuccess) e = sp_pool_alloc((void**)&g->d_col4, std::max<uint64_t>(n4, 1) * sizeof(int4));
-        if (e == cudaSuccess) {
-            g->n_col4 = (int64_t)n4;
-            er_pad_kernel<<<grid, 256>>>(rows, n, g->d_row, g->d_col, d_off4, g->d_row4, g->d_col4);
-            e = cudaGetLastError();
-        }
-    }
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) {
-        sponet_graph_destroy(g);
-        cudaGetLastError();
-        return sponet_fail(SPONET_ERR_CUDA, "graph_batch_create_er: %s", cudaGetErrorString(e));
-    }
-    *out = g;
+    BatchBuilder bb(tmp, n, B, "graph_batch_create_ba");
+    SP_TRY(bb.scan(d_deg));
+    ba_fill_kernel<<<grid, 256>>>(A, d_targets, bb.d_off, bb.d_cursor, bb.g->d_col);
+    SP_TRY(bb.finish(d_deg, layouts));
+    *out = bb.release();
     return SPONET_OK;
 }
 

@@ -29,6 +29,7 @@ struct NativeCnvmArgs {
     const int32_t* col;
     uint32_t graph_stride;  // n for a BATCH of graphs (chain cl of the call runs on graph cl: rows [cl n, (cl+1) n)), else 0
     const uint32_t* rec;    // batch: 64-byte agent records (sponet_graph::d_rec) or nullptr
+    uint32_t rec_deg_bits, rec_deg_mask;  // header = degree | row offset << rec_deg_bits
     const uint2* nbtab;  // neighbour sampler table (GRAPH == 2): [n << nbtab_log2]
     int32_t nbtab_log2;
     const uint32_t* noise_thr;  // [P] noise-branch threshold of the chain's parameter set
@@ -443,10 +444,10 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
             uint32_t nbr;
             if (GRAPH == 1) {
                 if (A.rec) {  // neighbour k < 15 out of the record (same DRAM burst as the header), else out of the row
-                    const uint32_t hdr = (uint32_t)q_row[s].y, k = __umulhi(q_r2[s], hdr & 0xFFu);
+                    const uint32_t hdr = (uint32_t)q_row[s].y, k = __umulhi(q_r2[s], hdr & A.rec_deg_mask);
                     const bool in_rec = k < 15u;
                     const uint32_t* src = in_rec ? A.rec : (const uint32_t*)A.col;
-                    nbr = (q_meta[s] & 1u) ? 0u : sp_ldg_rec(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> 8)) + k));
+                    nbr = (q_meta[s] & 1u) ? 0u : sp_ldg_rec(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> A.rec_deg_bits)) + k));
                 } else {
                     nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
                 }
@@ -1206,6 +1207,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
         A.col = g->d_col;
         A.graph_stride = g->batch > 1 ? (uint32_t)n : 0u;
         A.rec = g->batch > 1 ? g->d_rec : nullptr;
+        A.rec_deg_bits = (uint32_t)g->rec_deg_bits;
+        A.rec_deg_mask = (1u << g->rec_deg_bits) - 1u;
         A.nbtab = g->d_nbtab;
         A.nbtab_log2 = g->nbtab_log2;
     }

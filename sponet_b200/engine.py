@@ -87,10 +87,25 @@ class GraphBatch:
         if rc == _lib.ERR_INVALID and _lib.last_error().startswith("Timeout"):
             raise RuntimeError(_lib.last_error())  # network_generator.py:75-78
         _lib.check(rc)
+        self._adopt(h, num_agents, num_states, run_begin, run_end)
+
+    def _adopt(self, h, num_agents, num_states, run_begin, run_end):
         self._h = h
         self.num_agents = int(num_agents)
         self.count = int(num_states) * (int(run_end) - int(run_begin))
         self.device = current_device()
+
+    @classmethod
+    def barabasi_albert(cls, num_agents, m, seed, num_states, num_runs_total, run_begin, run_end, padded_rows=False, records=True):
+        """Barabasi-Albert graphs (sponet_graph_batch_create_ba; networkx.barabasi_albert_graph's process)."""
+        _lib.require_device()
+        h = C.c_void_p()
+        _lib.check(_lib.lib().sponet_graph_batch_create_ba(int(num_agents), int(m), int(seed), int(num_states), int(num_runs_total),
+                                                           int(run_begin), int(run_end),
+                                                           int(bool(padded_rows)) | 2 * int(bool(records)), C.byref(h)))
+        self = cls.__new__(cls)
+        self._adopt(h, num_agents, num_states, run_begin, run_end)
+        return self
 
     @property
     def handle(self):

@@ -379,7 +379,7 @@ def _pooled_bytes_hint() -> int:
 
 
 def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar):
-    """Per-run networks from a generator with ``device_batch`` (network_generator.ErdosRenyiGenerator, alpha = 1): the
+    """Per-run networks from a generator with ``device_batch`` (network_generator.ErdosRenyi / BarabasiAlbert, alpha = 1): the
     graphs of a block of (initial state, run) pairs are generated on the GPU and the block's chains run in ONE launch,
     chain (j, i) on graph index j * num_runs + i.  Graph and Philox stream of a pair depend on the two seeds and on the
     pair's index only: the result is the same for every block size and number of ranks.  Runs are split over ranks
@@ -398,7 +398,7 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
     want_x = cv is None or spec is None  # a CV the kernels cannot evaluate: from the returned states, pair by pair
     # graphs per block: device memory (rows 8 B + record 64 B + 12 B of build scratch per vertex, 4 B per entry), the
     # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
-    mean_entries = N * (getattr(gen, "p", 0.0) * (N - 1) + 2.0)
+    mean_entries = N * (gen.expected_mean_degree() + 2.0)
     per_graph = 84.0 * N + 4.0 * mean_entries + (T * N if want_x else 0)
     budget = _BATCH_BYTES
     if budget is None:  # a third of the device (60 GB of a B200's 180), never more than is free right now

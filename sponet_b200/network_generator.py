@@ -7,9 +7,10 @@ reference's own generators included) works as well.
 
 What is new: a generator may also offer ``device_batch(...)``, which makes ALL the graphs of an ensemble call on the
 GPU (``engine.GraphBatch``), one per realization, so that ``sample_many_runs`` runs the whole ensemble in one launch
-instead of one host-generated graph and one launch per realization.  ``ErdosRenyiGenerator`` implements it
-(``csrc/graphgen.cu``).  The device graphs are G(n, p) like networkx's, but not the same graphs: they are keyed by
-(seed, realization index), the seed being drawn from the generator's ``rng``.
+instead of one host-generated graph and one launch per realization.  ``ErdosRenyiGenerator`` and
+``BarabasiAlbertGenerator`` implement it (``csrc/graphgen.cu``).  The device graphs follow the same random-graph process as
+networkx's, but they are not the same graphs: they are keyed by (seed, realization index), the seed being drawn from the
+generator's ``rng``.
 """
 from __future__ import annotations
 
@@ -84,6 +85,9 @@ class ErdosRenyiGenerator:
         """Advances ``rng`` once per ensemble call; every graph of the call derives from this seed and its index."""
         return int(self.rng.integers(0, 2**63, dtype=np.int64))
 
+    def expected_mean_degree(self) -> float:
+        return self.p * (self.num_agents - 1)
+
     def device_batch(self, seed: int, num_states: int, num_runs_total: int, run_begin: int, run_end: int,
                      padded_rows: bool = False, records: bool = True):
         """The graphs of realizations [run_begin, run_end) of every initial state, generated on the current GPU."""
@@ -128,6 +132,21 @@ class BarabasiAlbertGenerator:
 
     def __call__(self):
         return _nx().barabasi_albert_graph(self.num_agents, self.m, seed=self.rng)
+
+    def draw_batch_seed(self) -> int:
+        return int(self.rng.integers(0, 2**63, dtype=np.int64))
+
+    def expected_mean_degree(self) -> float:
+        return 2.0 * self.m
+
+    def device_batch(self, seed: int, num_states: int, num_runs_total: int, run_begin: int, run_end: int,
+                     padded_rows: bool = False, records: bool = True):
+        """The same process as networkx's (star on m + 1 vertices, m distinct degree-proportional targets per new vertex),
+        run on the current GPU for the realizations [run_begin, run_end) of every initial state."""
+        from . import engine
+
+        return engine.GraphBatch.barabasi_albert(self.num_agents, self.m, seed, num_states, num_runs_total, run_begin, run_end,
+                                                 padded_rows=padded_rows, records=records)
 
     def __repr__(self) -> str:
         return f"Barabasi-Albert random graph on {self.num_agents} nodes"

@@ -281,3 +281,70 @@ def test_h_sized_batch_beyond_2_31_entries(oracle):
     batch.close()
     del keep
     engine.trim_graph_batch_memory()
+
+
+@pytest.mark.parametrize("n,m,S,R,rb,re", [(500, 3, 2, 5, 1, 4), (4000, 5, 1, 3, 0, 3), (300, 1, 1, 2, 0, 2), (200, 64, 1, 2, 0, 2)])
+def test_ba_device_batch_equals_oracle(oracle, n, m, S, R, rb, re):
+    from sponet_b200 import engine
+
+    b = engine.GraphBatch.barabasi_albert(n, m, 4711, S, R, rb, re, padded_rows=True)
+    for slot in range(b.count):
+        j, i = divmod(slot, re - rb)
+        rp, col = b.csr(slot)
+        orp, ocol = oracle.ba_graph(n, m, 4711, j * R + rb + i)
+        np.testing.assert_array_equal(rp, orp)
+        np.testing.assert_array_equal(col, ocol)
+    info = b.info()
+    assert info["min_degree"] >= 1 and info["nnz"] == b.count * 2 * m * (n - m)
+    b.close()
+    with pytest.raises(ValueError, match="m >= 1 and m < n"):
+        engine.GraphBatch.barabasi_albert(10, 10, 1, 1, 1, 0, 1)
+
+
+@pytest.mark.parametrize("records", [True, False])
+def test_cnvm_chains_on_a_ba_batch(oracle, records):
+    """Scale-free per-run graphs: hubs of several hundred neighbours (record header with more than 8 degree bits, most of a
+    hub's neighbours outside its record)."""
+    from sponet_b200 import CNVM, CNVMParameters, OpinionShares, engine
+    from sponet_b200.multiprocessing import _kernel_cv_spec
+
+    n, m, M, S, R, T = 5000, 4, 3, 2, 4, 4
+    kw = dict(num_opinions=M, r=[[0, 1, 2], [1, 0, 1], [2, 0, 0]], r_tilde=[[0, .2, .1], [0, 0, .1], [.1, .2, 0]])
+    states = np.random.default_rng(2).integers(0, M, (S, n)).astype(np.uint8)
+    t_eval = np.linspace(0.0, 3.0, T)
+    batch = engine.GraphBatch.barabasi_albert(n, m, 5, S, R, 0, R, records=records)
+    assert batch.info()["max_degree"] > 255
+    model = CNVM(CNVMParameters(num_agents=n, **kw))
+    struct, keep = model._struct()
+    spec = _kernel_cv_spec(OpinionShares(M), n)
+    x, cv = engine.run_native("cnvm", batch, n, struct, states, t_eval, 77, R, 0, R, want_x=True, want_cv=True, cv_spec=spec)
+    for j in range(S):
+        for i in range(R):
+            rp, col = batch.csr(j * R + i)
+            ox, oc = _oracle_chain(oracle, kw, rp, col, states[j], t_eval, 77, j * R + i)
+            np.testing.assert_array_equal(x[j, i], ox)
+            np.testing.assert_array_equal(cv[j, i], oc.astype(float))
+    batch.close()
+    del keep
+
+
+def test_sample_many_runs_with_a_ba_generator(oracle):
+    from sponet_b200 import BarabasiAlbertGenerator, CNVMParameters, OpinionShares, engine, sample_many_runs
+
+    n, m, R, T, M = 800, 3, 5, 3, 2
+    kw = dict(num_opinions=M, r=[[0, 1.0], [1.2, 0]], r_tilde=[[0, 0.05], [0.02, 0]])
+    x0 = np.random.default_rng(0).integers(0, M, n)
+
+    def params():
+        return CNVMParameters(network_generator=BarabasiAlbertGenerator(n, m, rng=np.random.default_rng(6)), **kw)
+
+    t, c = sample_many_runs(params(), x0, 2.0, T, R, collective_variable=OpinionShares(M), rng=np.random.default_rng(1))
+    _, x = sample_many_runs(params(), x0, 2.0, T, R, rng=np.random.default_rng(1))
+    assert c.shape == (R, T, M) and x.shape == (R, T, n)
+    gseed = BarabasiAlbertGenerator(n, m, rng=np.random.default_rng(6)).draw_batch_seed()
+    seed = engine.draw_seed(np.random.default_rng(1))
+    for i in (0, R - 1):
+        rp, col = oracle.ba_graph(n, m, gseed, i)
+        ox, oc = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
+        np.testing.assert_array_equal(x[i], ox)
+        np.testing.assert_array_equal(c[i], oc.astype(float))

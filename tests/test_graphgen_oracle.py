@@ -92,3 +92,31 @@ def test_host_generators_follow_the_reference_protocol():
     s1 = ErdosRenyiGenerator(10, 0.5, rng=np.random.default_rng(5)).draw_batch_seed()
     s2 = ErdosRenyiGenerator(10, 0.5, rng=np.random.default_rng(5)).draw_batch_seed()
     assert s1 == s2 and 0 <= s1 < 2**63
+
+
+def test_ba_oracle_follows_the_networkx_process(oracle):
+    """The sequential statement of the device Barabasi-Albert generator: a simple graph with m (n - m) edges whose degree
+    distribution is that of networkx.barabasi_albert_graph (same process: star on m + 1 vertices, m distinct
+    degree-proportional targets per new vertex) -- compared on pooled samples, 5 sigma of the binomial count per degree."""
+    nx = pytest.importorskip("networkx")
+    n, m, G = 3000, 4, 12
+    ours, theirs = [], []
+    for c in range(G):
+        rp, col = oracle.ba_graph(n, m, seed=9, c=c)
+        deg = _check_simple_graph(rp, col, n)
+        assert rp[-1] == 2 * m * (n - m) and deg.min() >= min(m, 1) and deg[m + 1 :].min() >= m
+        ours.append(deg)
+        theirs.append(np.array([d for _, d in nx.barabasi_albert_graph(n, m, seed=100 + c).degree()]))
+    ours, theirs = np.concatenate(ours), np.concatenate(theirs)
+    assert ours.sum() == theirs.sum()
+    for k in (4, 5, 6, 8, 12, 20):
+        pa, pb = (ours == k).mean(), (theirs == k).mean()
+        assert abs(pa - pb) < 5 * np.sqrt((pa * (1 - pa) + pb * (1 - pb)) / ours.size) + 1e-4, (k, pa, pb)
+    # the hubs are the early vertices in both
+    assert ours.reshape(G, n)[:, : m + 1].mean() > 20 * m and theirs.reshape(G, n)[:, : m + 1].mean() > 20 * m
+    rp2, col2 = oracle.ba_graph(n, m, seed=9, c=0)
+    rp3, col3 = oracle.ba_graph(n, m, seed=9, c=1)
+    assert np.array_equal(rp2, oracle.ba_graph(n, m, seed=9, c=0)[0]) and not np.array_equal(col2[: col3.size], col3[: col2.size])
+    # m = 1: a tree
+    rp, col = oracle.ba_graph(500, 1, seed=1, c=0)
+    assert rp[-1] == 2 * 499
