@@ -113,7 +113,7 @@ int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isol
  * vertices 0 .. m, then every vertex t > m attaches to m DISTINCT targets drawn uniformly from the endpoints of the edges so
  * far (duplicates are drawn again).  Edge e < m is (0, e + 1), edge e >= m the (e % m)-th edge of vertex e / m + m; endpoint
  * position 2 e is the edge's source, 2 e + 1 its target; candidate k of vertex t is position mulhi(word 0 of
- * Philox4x32-10(counter (k, t, c_lo, c_hi[16] | 5 << 24), key seed), 2 m (t - m)).  Resolved on the device in dependency rounds;
+ * Philox4x32-10(counter (k, t, c_lo, c_hi[16] | 5 << 24), key seed), 2 m (t - m)).  One warp per graph resolves 32 vertices at a time;
  * restated sequentially by oracle_ba_graph (bit-identical).  m <= 64. */
 int sponet_graph_batch_create_ba(int64_t num_agents, int32_t m, uint64_t seed, int64_t num_states, int64_t num_runs_total,
                                  int64_t run_begin, int64_t run_end, int layouts, sponet_graph** out);

@@ -343,8 +343,8 @@ struct Freer {
 // the edges so far (= proportional to degree), duplicates drawn again.  Edge e < m is (0, e + 1), edge e >= m is the
 // (e % m)-th edge of vertex e / m + m; position 2 e of the endpoint list is the edge's source, 2 e + 1 its target.
 // Candidate k of vertex t: position mulhi(word 0 of Philox(counter (k, t, c_lo, c_hi[16] | 5 << 24), key seed), 2 m (t - m)).
-// A vertex depends on earlier vertices only, so the batch is resolved in rounds (Sanders & Schulz, "Scalable generation of
-// scale-free graphs", 2016): a vertex whose candidates point at unresolved vertices waits for the next round.
+// A vertex depends on earlier vertices only (the endpoint-list formulation of Sanders & Schulz, "Scalable generation of
+// scale-free graphs", 2016), which is what lets a warp resolve 32 vertices at a time.
 struct BaArgs {
     int64_t n, count, nrun, R_total, run_begin;
     int32_t m;
@@ -357,39 +357,58 @@ __device__ __forceinline__ uint64_t ba_graph_index(const BaArgs& A, int64_t b) {
     return (uint64_t)(j * A.R_total + A.run_begin + i);
 }
 
-__global__ void ba_resolve_kernel(BaArgs A, int32_t* targets, volatile uint8_t* done, unsigned long long* remaining) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= A.count * A.n) return;
-    const int64_t b = tid / A.n, t = tid - b * A.n;
+// One warp per graph walks the vertices in chunks of 32 (one per lane).  Everything before the chunk is resolved; a lane whose
+// candidate points at a vertex of its own chunk that is not resolved yet tries again after the others have written theirs (the
+// lowest unresolved lane of a chunk depends on resolved vertices only, so every pass resolves at least one lane).
+__global__ void ba_resolve_kernel(BaArgs A, int32_t* targets) {
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= A.count) return;
     const int m = A.m;
-    if (t <= m || done[tid]) return;
     const uint64_t c = ba_graph_index(A, b);
-    const uint32_t range = (uint32_t)(2 * (int64_t)m * (t - m));
-    int32_t tg[BA_MAX_M];
-    int cnt = 0;
-    for (uint32_t k = 0; cnt < m; ++k) {
-        const uint4 r4 = sp_philox4x32_10(k, (uint32_t)t, (uint32_t)c, ((uint32_t)(c >> 32) & 0xFFFFu) | (5u << 24), (uint32_t)A.seed,
-                                          (uint32_t)(A.seed >> 32));
-        const uint32_t r = __umulhi(r4.x, range);
-        const uint32_t e = r >> 1;
-        int32_t v;
-        if (!(r & 1u)) {
-            v = e < (uint32_t)m ? 0 : (int32_t)(e / (uint32_t)m) + m;
-        } else if (e < (uint32_t)m) {
-            v = (int32_t)e + 1;
-        } else {
-            const int64_t owner = b * A.n + (int64_t)(e / (uint32_t)m) + m;
-            if (!done[owner]) return;  // next round
-            v = __ldcg(targets + owner * m + (int64_t)(e % (uint32_t)m));  // (written by another thread of this launch: not through L1)
+    int32_t* T = targets + b * A.n * m;
+    for (int64_t t0 = (int64_t)m + 1; t0 < A.n; t0 += 32) {
+        const int64_t t = t0 + lane;
+        bool done = t >= A.n;
+        const uint32_t range = (uint32_t)(2 * (int64_t)m * (t - m));
+        for (;;) {
+            const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
+            if (done_mask == 0xffffffffu) break;
+            if (!done) {
+                int32_t tg[BA_MAX_M];
+                int cnt = 0;
+                bool wait = false;
+                for (uint32_t k = 0; cnt < m && !wait; ++k) {
+                    const uint4 r4 = sp_philox4x32_10(k, (uint32_t)t, (uint32_t)c, ((uint32_t)(c >> 32) & 0xFFFFu) | (5u << 24),
+                                                      (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                    const uint32_t r = __umulhi(r4.x, range);
+                    const uint32_t e = r >> 1;
+                    int32_t v;
+                    if (!(r & 1u)) {
+                        v = e < (uint32_t)m ? 0 : (int32_t)(e / (uint32_t)m) + m;
+                    } else if (e < (uint32_t)m) {
+                        v = (int32_t)e + 1;
+                    } else {
+                        const int64_t owner = (int64_t)(e / (uint32_t)m) + m;
+                        if (owner >= t0 && !((done_mask >> (owner - t0)) & 1u)) {
+                            wait = true;  // a vertex of this chunk that is not resolved yet
+                            break;
+                        }
+                        v = __ldcg(T + owner * m + (int64_t)(e % (uint32_t)m));  // (may have been written by another lane: not through L1)
+                    }
+                    bool dup = false;
+                    for (int q = 0; q < cnt; ++q) dup |= (tg[q] == v);
+                    if (!dup) tg[cnt++] = v;
+                }
+                if (!wait) {
+                    for (int q = 0; q < m; ++q) T[t * m + q] = tg[q];
+                    __threadfence();
+                    done = true;
+                }
+            }
+            __syncwarp();
         }
-        bool dup = false;
-        for (int q = 0; q < cnt; ++q) dup |= (tg[q] == v);
-        if (!dup) tg[cnt++] = v;
     }
-    for (int q = 0; q < m; ++q) targets[tid * m + q] = tg[q];
-    __threadfence();
-    done[tid] = 1;
-    atomicAdd(remaining, (unsigned long long)-1ll);
 }
 
 // the edges of vertex t (the star's for t <= m): calls f(u, v) once per edge
@@ -626,25 +645,12 @@ extern "C" int sponet_graph_batch_create_ba(int64_t num_agents, int32_t m, uint6
     const unsigned grid = (unsigned)((rows + 255) / 256);
     Freer tmp;
     int32_t* d_targets;
-    uint8_t* d_done;
-    unsigned long long* d_remaining;
     uint32_t* d_deg;
     SP_CUDA(tmp.alloc((void**)&d_targets, (size_t)rows * m * sizeof(int32_t)));
-    SP_CUDA(tmp.alloc((void**)&d_done, rows));
-    SP_CUDA(tmp.alloc((void**)&d_remaining, 8));
     SP_CUDA(tmp.alloc((void**)&d_deg, rows * 4));
-    SP_CUDA(cudaMemset(d_done, 0, rows));
     SP_CUDA(cudaMemset(d_deg, 0, rows * 4));
-    unsigned long long remaining = (unsigned long long)B * (unsigned long long)(n - 1 - m);
-    SP_CUDA(cudaMemcpy(d_remaining, &remaining, 8, cudaMemcpyHostToDevice));
-    int rounds_done = 0;
-    for (int round = 0; remaining > 0; ++round, ++rounds_done) {
-        SP_REQUIRE(round < 4096, "graph_batch_create_ba: the dependency rounds do not end");
-        ba_resolve_kernel<<<grid, 256>>>(A, d_targets, d_done, d_remaining);
-        SP_CUDA(cudaGetLastError());
-        SP_CUDA(cudaMemcpy(&remaining, d_remaining, 8, cudaMemcpyDeviceToHost));
-    }
-    if (getenv("SPONET_DEBUG")) fprintf(stderr, "graph_batch_create_ba: %d dependency rounds\n", rounds_done);
+    ba_resolve_kernel<<<(unsigned)((B * 32 + 127) / 128), 128>>>(A, d_targets);
+    SP_CUDA(cudaGetLastError());
     ba_degree_kernel<<<grid, 256>>>(A, d_targets, d_deg);
     SP_CUDA(cudaGetLastError());
     BatchBuilder bb(tmp, n, B, "graph_batch_create_ba");
