@@ -254,8 +254,9 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         const uint64_t chain = (uint64_t)(j * A.R_total + A.run_begin + i);
         const uint32_t ctr2 = (uint32_t)chain, ctr3 = (uint32_t)(chain >> 32) & 0x00FFFFFFu;  // tag 0
         const int64_t* kcounts = A.counts + cl * (int64_t)(T - 1);
-        const uint32_t grow = GRAPH == 1 ? (uint32_t)cl * A.graph_stride : 0u;  // first row of the chain's own graph (batch)
-        const uint32_t gcol = (GRAPH == 1 && A.rec) ? (uint32_t)__ldg(&A.row[grow].x) : 0u;  // ... and its first adjacency entry
+        // GRAPH: 0 complete graph, 1 CSR, 2 neighbour sampler table, 3 a batch of per-run graphs with agent records
+        const uint32_t grow = (GRAPH == 1 || GRAPH == 3) ? (uint32_t)cl * A.graph_stride : 0u;  // first row of the chain's own graph (batch)
+        const uint32_t gcol = GRAPH == 3 ? (uint32_t)__ldg(&A.row[grow].x) : 0u;                // ... and its first adjacency entry
         // the chain's parameter set: noise-branch threshold, acceptance tables (staged per chain slot)
         const int64_t pset = j * A.param_stride;
         const uint32_t noise_thr = __ldg(A.noise_thr + pset);
@@ -396,15 +397,12 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         uint2 z_at = make_uint2(0u, 0u);
         auto gather_entry = [&](int s, uint32_t a, uint32_t r2) {
             // every lane gathers (no divergence); noise lanes ignore the result
-            if (GRAPH == 1) {
-                if (A.rec) {  // (word index of the agent's record, its header)
-                    // Only imitation events read the graph here: every record gathered is a random DRAM row, and the
-                    // rate of those -- not bytes, not latency -- is what bounds this path (profiles/r2_kernels.md 6).
-                    const uint32_t base = (grow + a) << 4;
-                    q_row[s] = make_int2((int)base, (q_meta[s] & 1u) ? 1 : (int)sp_ldg_rec(A.rec + base));
-                } else {
-                    q_row[s] = __ldg(A.row + (grow + a));
-                }
+            if (GRAPH == 1) q_row[s] = __ldg(A.row + (grow + a));
+            if (GRAPH == 3) {  // (word index of the agent's record, its header)
+                // Only imitation events read the graph here: every record gathered is a random DRAM row, and the
+                // rate of those -- not bytes, not latency -- is what bounds this path (profiles/r2_kernels.md 6).
+                const uint32_t base = (grow + a) << 4;
+                q_row[s] = make_int2((int)base, (q_meta[s] & 1u) ? 1 : (int)sp_ldg_rec(A.rec + base));
             }
             if (GRAPH == 2) {
                 // slot index (a << lg) | (top lg bits of r2) in one funnel shift; the table has < 2^26 entries
@@ -443,14 +441,12 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         auto issue2 = [&](int s) {
             uint32_t nbr;
             if (GRAPH == 1) {
-                if (A.rec) {  // neighbour k < 15 out of the record (same DRAM burst as the header), else out of the row
-                    const uint32_t hdr = (uint32_t)q_row[s].y, k = __umulhi(q_r2[s], hdr & A.rec_deg_mask);
-                    const bool in_rec = k < 15u;
-                    const uint32_t* src = in_rec ? A.rec : (const uint32_t*)A.col;
-                    nbr = (q_meta[s] & 1u) ? 0u : sp_ldg_rec(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> A.rec_deg_bits)) + k));
-                } else {
-                    nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
-                }
+                nbr = (uint32_t)__ldg(A.col + ((uint32_t)q_row[s].x + __umulhi(q_r2[s], (uint32_t)q_row[s].y)));  // (32-bit unsigned offsets: a batch)
+            } else if (GRAPH == 3) {  // neighbour k < 15 out of the record (same DRAM burst as the header), else out of the row
+                const uint32_t hdr = (uint32_t)q_row[s].y, k = __umulhi(q_r2[s], hdr & A.rec_deg_mask);
+                const bool in_rec = k < 15u;
+                const uint32_t* src = in_rec ? A.rec : (const uint32_t*)A.col;
+                nbr = (q_meta[s] & 1u) ? 0u : sp_ldg_rec(src + ((in_rec ? (uint32_t)q_row[s].x + 1u : gcol + (hdr >> A.rec_deg_bits)) + k));
             } else if (GRAPH == 2) {
                 const uint32_t w0 = (uint32_t)q_row[s].x, w1 = (uint32_t)q_row[s].y;
                 const uint32_t thr = ((w0 >> 20) << 12) | (w1 >> 20);
@@ -1078,6 +1074,8 @@ cnvm_kernel_t pick_cnvm(bool alias, bool ring, bool wide) {
 
 template <int BITS, bool SMEM>
 cnvm_kernel_t pick_cnvm_g(int graph, bool alias, bool ring, bool wide) {
+    if (graph == 3)  // batches of per-run graphs: uniform agent weights only, 16 warps
+        return (SMEM && ring) ? cnvm_native_kernel<BITS, SMEM, 3, false, SMEM> : cnvm_native_kernel<BITS, SMEM, 3, false, false>;
     if (graph == 2) return pick_cnvm<BITS, SMEM, 2>(alias, ring, wide);
     if (graph == 1) return pick_cnvm<BITS, SMEM, 1>(alias, ring, wide);
     return pick_cnvm<BITS, SMEM, 0>(alias, ring, false);
@@ -1305,7 +1303,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     const size_t thr_bytes = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);  // per chain slot
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
     const size_t per_slot_min = cnt_bytes + 16 + thr_bytes;      // + the reduction words of a COOP chain
-    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : 1);
+    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : (g->batch > 1 && g->d_rec) ? 3 : 1);
     const bool batch_graph = g != nullptr && g->batch > 1;
     // Launches the local chains [c0, c1) with the geometry that suits their number; returns the chains one wave
     // of that geometry holds (resident chain slots on the whole device).
