@@ -196,9 +196,12 @@ def test_sample_many_runs_with_a_device_generator(oracle):
     try:
         mp._BATCH_BYTES = int(2.5 * (84.0 * n + 4.0 * n * (p * (n - 1) + 2.0)))
         _, c2 = sample_many_runs(params(8), states, 2.0, T, R, collective_variable=cv, rng=np.random.default_rng(1))
+        mp._BATCH_BYTES = int(1.5 * (84.0 * n + 4.0 * n * (p * (n - 1) + 2.0)))  # one graph per launch: blocks of states too
+        _, c3 = sample_many_runs(params(8), states, 2.0, T, R, collective_variable=cv, rng=np.random.default_rng(1))
     finally:
         mp._BATCH_BYTES = old
     np.testing.assert_array_equal(c, c2)
+    np.testing.assert_array_equal(c, c3)
     # a 1-D initial state is squeezed; sample_moments rides on the same path
     _, c1 = sample_many_runs(params(8), states[0], 2.0, T, R, collective_variable=cv, rng=np.random.default_rng(1))
     np.testing.assert_array_equal(c1, c[0])
