@@ -31,7 +31,8 @@ R3 = np.array([[0, 1, 2], [1, 0, 1], [2, 0, 0]], dtype=float)
 RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
 RUNS = 12_000
 SEEDS = {"cnvm_er500": 101, "cnvm_ba400_alpha0": 102, "cnvm_complete300": 103, "cntm_er400": 104,
-         "cnvm_er1e4": 201, "cnvm_er1e5": 202, "cntm_ba1e4": 203, "cntm_ba1e5": 204}
+         "cnvm_er1e4": 201, "cnvm_er1e5": 202, "cntm_ba1e4": 203, "cntm_ba1e5": 204,
+         "cnvm_pernet_er1000": 301, "cnvm_pernet_ba1000": 302}
 ONLY = set(sys.argv[1:])
 
 
@@ -117,3 +118,17 @@ for name, n, t_max, T in (("cntm_ba1e4", 10_000, 10.0, 6), ("cntm_ba1e5", 100_00
     run(name, CNTMParameters(network=g, r=1.0, r_tilde=0.2, threshold_01=0.5, threshold_10=0.5), 2, x0, t_max, T,
         dict(model="cntm", workload="ba_cntm", num_agents=n, csr_crc=crc(rp, col), r=1.0, r_tilde=0.2, threshold_01=0.5,
              threshold_10=0.5), runs=10_000)
+
+
+# ---- a NEW network for every realization (params.network_generator; sponet/cnvm/model.py:95-96) ----
+# The reference's own generators (networkx); the device-side generators of this repo must give the same distribution of
+# the collective variable -- the graph-to-graph variation is part of it at N = 1000.
+import sponet.network_generator as ng  # noqa: E402
+
+x0 = np.random.default_rng(4).integers(0, 3, 1000)
+run("cnvm_pernet_er1000",
+    CNVMParameters(num_opinions=3, network_generator=ng.ErdosRenyiGenerator(1000, 0.02, rng=np.random.default_rng(11)), r=R3, r_tilde=RT3),
+    3, x0, 4.0, 5, dict(model="cnvm_pernet", generator="er", num_agents=1000, p=0.02, r=R3, r_tilde=RT3, alpha=1.0))
+run("cnvm_pernet_ba1000",
+    CNVMParameters(num_opinions=3, network_generator=ng.BarabasiAlbertGenerator(1000, 3, rng=np.random.default_rng(12)), r=R3, r_tilde=RT3),
+    3, x0, 4.0, 5, dict(model="cnvm_pernet", generator="ba", num_agents=1000, m=3, r=R3, r_tilde=RT3, alpha=1.0))

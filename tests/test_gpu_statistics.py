@@ -59,7 +59,14 @@ def _native_counts(g, runs, seed, scale_noise=1.0):
     from sponet_b200 import CNTMParameters, CNVMParameters, OpinionShares, sample_many_runs
 
     model, M = str(g["model"]), int(g["num_opinions"])
-    if "workload" in g:
+    if model == "cnvm_pernet":  # a new network per realization, generated on the device
+        from sponet_b200 import BarabasiAlbertGenerator, ErdosRenyiGenerator
+
+        n = int(g["num_agents"])
+        gen = (ErdosRenyiGenerator(n, float(g["p"]), rng=np.random.default_rng(seed + 1)) if str(g["generator"]) == "er"
+               else BarabasiAlbertGenerator(n, int(g["m"]), rng=np.random.default_rng(seed + 1)))
+        params = CNVMParameters(num_opinions=M, network_generator=gen, r=g["r"], r_tilde=g["r_tilde"] * scale_noise)
+    elif "workload" in g:
         params = _workload_params(g, scale_noise)
     elif model == "cntm":
         nl = csr_to_neighbor_list(g["row_ptr"], g["col"])
@@ -107,6 +114,24 @@ def test_native_mode_matches_reference_distribution(name):
     assert nat.shape == (NATIVE_RUNS,) + ref.shape[1:]
     np.testing.assert_array_equal(nat[:, 0], np.broadcast_to(ref[0, 0], nat[:, 0].shape))  # t = 0: the initial state
     assert (nat.sum(-1) == g["x_init"].size).all()
+    zm, zv, pmin, n_cmp = _compare(ref, nat)
+    print(f"{name}: worst z(mean)={zm:.2f} z(var)={zv:.2f} min KS p={pmin:.3g} over {n_cmp} comparisons")
+    assert zm <= Z, f"means differ: z = {zm:.2f}"
+    assert zv <= Z, f"variances differ: z = {zv:.2f}"
+    assert pmin >= ALPHA / n_cmp, f"KS rejects: p = {pmin:.3g}"
+
+
+@pytest.mark.parametrize("name", ["cnvm_pernet_er1000", "cnvm_pernet_ba1000"])
+def test_per_run_networks_match_the_reference_distribution(name):
+    """`params.network_generator`: the reference draws a networkx graph per realization (its ErdosRenyiGenerator /
+    BarabasiAlbertGenerator, 1.2e4 realizations through its own `sample_many_runs`); here the graphs of all realizations are
+    generated on the device.  At N = 1000 the variation from graph to graph is a visible part of the CV's distribution, so
+    means, variances and KS test the generated ensemble of graphs as well as the chains on them."""
+    g = load_golden("stats_" + name)
+    ref = g["counts"].astype(np.int64)
+    nat = _native_counts(g, NATIVE_RUNS, seed=777)
+    assert nat.shape == (NATIVE_RUNS,) + ref.shape[1:]
+    np.testing.assert_array_equal(nat[:, 0], np.broadcast_to(ref[0, 0], nat[:, 0].shape))
     zm, zv, pmin, n_cmp = _compare(ref, nat)
     print(f"{name}: worst z(mean)={zm:.2f} z(var)={zv:.2f} min KS p={pmin:.3g} over {n_cmp} comparisons")
     assert zm <= Z, f"means differ: z = {zm:.2f}"
