@@ -118,6 +118,16 @@ int sponet_graph_batch_create_er(int64_t num_agents, double p, int force_no_isol
 int sponet_graph_batch_create_ba(int64_t num_agents, int32_t m, uint64_t seed, int64_t num_states, int64_t num_runs_total,
                                  int64_t run_begin, int64_t run_end, int layouts, sponet_graph** out);
 
+/* The same for Watts-Strogatz graphs (sponet/network_generator.py:147-183 = networkx.connected_watts_strogatz_graph(n, k, p,
+ * tries)): ring lattice with k / 2 neighbours on each side; positions (j, u), j = 1 .. k / 2 outer, u inner: with probability p
+ * the edge (u, u + j) is replaced by (u, w), w uniform and drawn again while w == u or {u, w} is an edge of the CURRENT graph; the
+ * graph is drawn again (attempt + 1) until it is connected, SPONET_ERR_INVALID "Maximum number of tries exceeded" after `tries`.
+ * Position q = (j - 1) n + u uses Philox4x32-10(counter (d, q, c_lo, c_hi[16] | attempt << 16 | 6 << 24), key seed): word 0 of
+ * draw 0 against floor(p 2^32), w = mulhi(word 0 of draw d >= 1, n).  One warp per graph (the rewiring is sequential by
+ * definition); restated by oracle_ws_graph (bit-identical).  A vertex may hold at most k + 32 neighbours. */
+int sponet_graph_batch_create_ws(int64_t num_agents, int32_t k, double p, uint64_t seed, int64_t num_states, int64_t num_runs_total,
+                                 int64_t run_begin, int64_t run_end, int32_t tries, int layouts, sponet_graph** out);
+
 /* Device memory of destroyed batches is kept for the next batch (cudaMalloc / cudaFree of tens of gigabytes cost up to
  * seconds; at most 64 GiB idle per process).  This returns it to the driver. */
 int sponet_graph_batch_trim(void);

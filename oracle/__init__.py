@@ -492,3 +492,25 @@ def ba_graph(n, m, seed, c):
     nnz = f(n, m, seed, c, row_ptr, col)
     assert nnz == col.size
     return row_ptr, col
+
+
+def ws_row_capacity(k: int) -> int:
+    """Adjacency slots per vertex of the Watts-Strogatz generators (device and oracle): k lattice neighbours + rewired-in edges."""
+    return int(k) + 32
+
+
+def ws_graph(n, k, p, seed, c, tries=100):
+    """oracle_ws_graph: graph index c of the device-side Watts-Strogatz generator as (row_ptr, col, attempts)."""
+    f = lib().oracle_ws_graph
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, _i32, _i32, C.POINTER(C.c_int32)]
+    row_ptr = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(n * (k // 2) * 2, dtype=np.int32)
+    used = C.c_int32(0)
+    nnz = f(n, k, int(prob_to_thr(np.array([p]))[0]), seed, c, tries, ws_row_capacity(k), row_ptr, col, C.byref(used))
+    if nnz == -1:
+        raise RuntimeError("Maximum number of tries exceeded")
+    if nnz < 0:
+        raise RuntimeError("oracle_ws_graph: a vertex exceeds the row capacity")
+    assert nnz == col.size
+    return row_ptr, col, used.value

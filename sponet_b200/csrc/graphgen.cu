@@ -445,6 +445,150 @@ __global__ void ba_fill_kernel(BaArgs A, const int32_t* targets, const uint32_t*
     });
 }
 
+// ---- Watts-Strogatz (networkx.connected_watts_strogatz_graph, as sponet/network_generator.py:147-183 calls it) ----
+// Ring lattice with k / 2 neighbours on each side, then the positions (j, u) in networkx's order (j = 1 .. k / 2 outer, u inner):
+// with probability p the edge (u, u + j) is replaced by (u, w), w uniform, drawn again while w == u or {u, w} is an edge; the
+// graph is drawn again until it is connected.  The rewiring is sequential by definition (a candidate is tested against the
+// CURRENT edges), so one warp owns a graph: the lanes draw the decisions of 32 positions at a time and scan adjacency rows
+// together, the rewirings are applied in position order.  Random numbers: see oracle_ws_graph (oracle/oracle_native.inc).
+struct WsArgs {
+    int64_t n, count, nrun, R_total, run_begin;
+    int32_t k, tries, cap;
+    uint32_t p_thr;
+    uint64_t seed;
+};
+
+__global__ void __launch_bounds__(128) ws_build_kernel(WsArgs A, int32_t* adj_all, uint32_t* deg_all, int32_t* queue_all,
+                                                       uint32_t* seen_all, int32_t* status) {
+    __shared__ uint32_t tails[4];
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (b >= A.count) return;
+    const int64_t n = A.n, cap = A.cap;
+    const int half = A.k / 2;
+    volatile int32_t* adj = adj_all + b * n * cap;
+    volatile uint32_t* deg = deg_all + b * n;
+    int32_t* queue = queue_all + b * n;
+    uint32_t* seen = seen_all + b * ((n + 31) / 32);
+    const int64_t jb = b / A.nrun, ib = b - jb * A.nrun;
+    const uint64_t c = (uint64_t)(jb * A.R_total + A.run_begin + ib);
+    int32_t result = -1;
+    for (int attempt = 0; attempt < A.tries && result == -1; ++attempt) {
+        const uint32_t c3 = ((uint32_t)(c >> 32) & 0xFFFFu) | (((uint32_t)attempt & 0xFFu) << 16) | (6u << 24);
+        for (int64_t u = lane; u < n; u += 32) {  // the lattice
+            for (int j = 1; j <= half; ++j) {
+                adj[u * cap + 2 * (j - 1)] = (int32_t)((u + j) % n);
+                adj[u * cap + 2 * (j - 1) + 1] = (int32_t)((u - j + n) % n);
+            }
+            deg[u] = (uint32_t)(2 * half);
+        }
+        __syncwarp();
+        bool overflow = false;
+        const int64_t positions = (int64_t)half * n;
+        for (int64_t q0 = 0; q0 < positions && !overflow; q0 += 32) {
+            const int64_t q = q0 + lane;
+            bool flip = false;
+            if (q < positions) {
+                const uint4 r = sp_philox4x32_10(0u, (uint32_t)q, (uint32_t)c, c3, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                flip = sp_thr_accept(r.x, A.p_thr);
+            }
+            uint32_t todo = __ballot_sync(0xffffffffu, flip);
+            while (todo) {  // in position order; all lanes work on the same rewiring
+                const int64_t qq = q0 + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int j = (int)(qq / n) + 1;
+                const int64_t u = qq - (int64_t)(j - 1) * n, v = (u + j) % n;
+                uint32_t du = deg[u];
+                int64_t w = 0;
+                bool skip = false;
+                for (uint32_t d = 1;; ++d) {
+                    const uint4 r = sp_philox4x32_10(d, (uint32_t)qq, (uint32_t)c, c3, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                    w = (int64_t)__umulhi(r.x, (uint32_t)n);
+                    if (d > 1 && (int64_t)du >= n - 1) {
+                        skip = true;
+                        break;
+                    }
+                    bool bad = false;
+                    for (uint32_t e = lane; e < du; e += 32) bad |= adj[u * cap + e] == (int32_t)w;
+                    if (!__any_sync(0xffffffffu, bad) && w != u) break;
+                }
+                if (skip) continue;
+                // remove {u, v}: the entry moves to the end of its row
+                for (int side = 0; side < 2; ++side) {
+                    const int64_t a = side ? v : u;
+                    const int32_t other = (int32_t)(side ? u : v);
+                    const uint32_t da = deg[a];
+                    uint32_t where = 0xFFFFFFFFu;
+                    for (uint32_t e0 = 0; e0 < da && where == 0xFFFFFFFFu; e0 += 32) {
+                        const uint32_t e = e0 + lane;
+                        const uint32_t hit = __ballot_sync(0xffffffffu, e < da && adj[a * cap + e] == other);
+                        if (hit) where = e0 + __ffs(hit) - 1;
+                    }
+                    if (lane == 0 && where != 0xFFFFFFFFu) {
+                        adj[a * cap + where] = adj[a * cap + da - 1];
+                        deg[a] = da - 1;
+                    }
+                    __syncwarp();
+                }
+                du = deg[u];
+                const uint32_t dw = deg[w];
+                if ((int64_t)du >= cap || (int64_t)dw >= cap) {
+                    overflow = true;
+                    break;
+                }
+                if (lane == 0) {
+                    adj[u * cap + du] = (int32_t)w;
+                    adj[w * cap + dw] = (int32_t)u;
+                    deg[u] = du + 1;
+                    deg[w] = dw + 1;
+                }
+                __syncwarp();
+            }
+        }
+        if (overflow) {
+            result = -3;
+            break;
+        }
+        // connected?  breadth-first from vertex 0, 32 frontier vertices at a time
+        for (int64_t i = lane; i < (n + 31) / 32; i += 32) seen[i] = 0u;
+        __syncwarp();
+        if (lane == 0) {
+            seen[0] = 1u;
+            queue[0] = 0;
+            tails[wib] = 1u;
+        }
+        __syncwarp();
+        uint32_t head = 0;
+        for (;;) {
+            const uint32_t tail = *(volatile uint32_t*)&tails[wib];
+            if (head >= tail) break;
+            const uint32_t idx = head + lane;
+            if (idx < tail) {
+                const int64_t a = __ldcg(queue + idx);
+                const uint32_t da = deg[a];
+                for (uint32_t e = 0; e < da; ++e) {
+                    const int32_t nb = adj[a * cap + e];
+                    const uint32_t bit = 1u << (nb & 31);
+                    if (!(atomicOr(seen + (nb >> 5), bit) & bit)) queue[atomicAdd(&tails[wib], 1u)] = nb;
+                }
+            }
+            head = min(head + 32u, tail);
+            __threadfence_block();
+            __syncwarp();
+        }
+        if ((int64_t)tails[wib] == n) result = attempt + 1;
+        __syncwarp();
+    }
+    if (lane == 0) status[b] = result;
+}
+
+__global__ void ws_fill_kernel(int64_t rows, int64_t cap, const int32_t* adj, const uint32_t* deg, const uint32_t* off, int32_t* col) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= rows) return;
+    const uint32_t d = deg[tid];
+    for (uint32_t e = 0; e < d; ++e) col[off[tid] + e] = adj[tid * cap + e];
+}
+
 // Common tail of the batch generators: degrees -> absolute row offsets, graph handle and adjacency array; after the
 // generator's fill kernels: rows sorted, (begin, degree) descriptors, degree range, and the layouts of the simulation kernels.
 struct BatchBuilder {
@@ -656,6 +800,57 @@ extern "C" int sponet_graph_batch_create_ba(int64_t num_agents, int32_t m, uint6
     BatchBuilder bb(tmp, n, B, "graph_batch_create_ba");
     SP_TRY(bb.scan(d_deg));
     ba_fill_kernel<<<grid, 256>>>(A, d_targets, bb.d_off, bb.d_cursor, bb.g->d_col);
+    SP_TRY(bb.finish(d_deg, layouts));
+    *out = bb.release();
+    return SPONET_OK;
+}
+
+extern "C" int sponet_graph_batch_create_ws(int64_t num_agents, int32_t k, double p, uint64_t seed, int64_t num_states,
+                                            int64_t num_runs_total, int64_t run_begin, int64_t run_end, int32_t tries, int layouts,
+                                            sponet_graph** out) {
+    SP_REQUIRE(out, "graph_batch_create_ws: out is NULL");
+    *out = nullptr;
+    const int64_t n = num_agents, nrun = run_end - run_begin, B = num_states * nrun;
+    SP_REQUIRE(n >= 3 && n < ((int64_t)1 << 31), "graph_batch_create_ws: num_agents out of range");
+    SP_REQUIRE(k >= 2 && k < n, "graph_batch_create_ws: 2 <= k < n required (k = %d, n = %lld)", k, (long long)n);
+    SP_REQUIRE(p >= 0.0 && p <= 1.0, "graph_batch_create_ws: p must be in [0, 1]");
+    SP_REQUIRE(tries >= 1 && tries <= 256, "graph_batch_create_ws: tries must be in [1, 256]");
+    SP_REQUIRE(num_states >= 1 && nrun >= 1 && run_begin >= 0 && num_runs_total >= 1, "graph_batch_create_ws: bad run range");
+    SP_REQUIRE(B * n < ((int64_t)1 << 32), "graph_batch_create_ws: %lld graphs of %lld agents exceed 2^32 rows; use smaller batches",
+               (long long)B, (long long)n);
+    SP_REQUIRE((int64_t)(k / 2) * n < ((int64_t)1 << 32), "graph_batch_create_ws: too many lattice edges per graph");
+    WsArgs A;
+    A.n = n;
+    A.count = B;
+    A.nrun = nrun;
+    A.R_total = num_runs_total;
+    A.run_begin = run_begin;
+    A.k = k;
+    A.tries = tries;
+    A.cap = k + 32;  // k lattice neighbours + rewired-in edges (oracle.ws_row_capacity)
+    A.p_thr = sp_prob_to_thr(p);
+    A.seed = seed;
+    const int64_t rows = B * n;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    Freer tmp;
+    int32_t *d_adj, *d_queue, *d_status;
+    uint32_t *d_deg, *d_seen;
+    SP_CUDA(tmp.alloc((void**)&d_adj, (size_t)rows * A.cap * sizeof(int32_t)));
+    SP_CUDA(tmp.alloc((void**)&d_deg, rows * 4));
+    SP_CUDA(tmp.alloc((void**)&d_queue, rows * 4));
+    SP_CUDA(tmp.alloc((void**)&d_seen, (size_t)B * ((n + 31) / 32) * 4));
+    SP_CUDA(tmp.alloc((void**)&d_status, B * 4));
+    ws_build_kernel<<<(unsigned)((B * 32 + 127) / 128), 128>>>(A, d_adj, d_deg, d_queue, d_seen, d_status);
+    SP_CUDA(cudaGetLastError());
+    std::vector<int32_t> status((size_t)B);
+    SP_CUDA(cudaMemcpy(status.data(), d_status, B * 4, cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < B; ++b) {
+        if (status[b] == -1) return sponet_fail(SPONET_ERR_INVALID, "Maximum number of tries exceeded");  // networkx's message
+        SP_REQUIRE(status[b] > 0, "graph_batch_create_ws: a vertex has more than %d neighbours", A.cap);
+    }
+    BatchBuilder bb(tmp, n, B, "graph_batch_create_ws");
+    SP_TRY(bb.scan(d_deg));
+    ws_fill_kernel<<<grid, 256>>>(rows, A.cap, d_adj, d_deg, bb.d_off, bb.g->d_col);
     SP_TRY(bb.finish(d_deg, layouts));
     *out = bb.release();
     return SPONET_OK;

@@ -111,6 +111,22 @@ class GraphBatch:
     def handle(self):
         return self._h
 
+    @classmethod
+    def watts_strogatz(cls, num_agents, k, p, seed, num_states, num_runs_total, run_begin, run_end, tries=100, padded_rows=False,
+                       records=True):
+        """Connected Watts-Strogatz graphs (sponet_graph_batch_create_ws; networkx.connected_watts_strogatz_graph's process)."""
+        _lib.require_device()
+        h = C.c_void_p()
+        rc = _lib.lib().sponet_graph_batch_create_ws(int(num_agents), int(k), float(p), int(seed), int(num_states),
+                                                     int(num_runs_total), int(run_begin), int(run_end), int(tries),
+                                                     int(bool(padded_rows)) | 2 * int(bool(records)), C.byref(h))
+        if rc == _lib.ERR_INVALID and _lib.last_error().startswith("Maximum number of tries"):
+            raise RuntimeError(_lib.last_error())  # networkx raises NetworkXError here
+        _lib.check(rc)
+        self = cls.__new__(cls)
+        self._adopt(h, num_agents, num_states, run_begin, run_end)
+        return self
+
     def csr(self, slot: int):
         """Graph `slot` of the batch as host (row_ptr, col)."""
         row_ptr = np.empty(self.num_agents + 1, dtype=np.int32)

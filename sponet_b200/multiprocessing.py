@@ -399,7 +399,7 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
     # graphs per block: device memory (rows 8 B + record 64 B + 12 B of build scratch per vertex, 4 B per entry), the
     # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
     mean_entries = N * (gen.expected_mean_degree() + 2.0)
-    per_graph = 84.0 * N + 4.0 * mean_entries + (T * N if want_x else 0)
+    per_graph = (84.0 + getattr(gen, "build_bytes_per_vertex", 0.0)) * N + 4.0 * mean_entries + (T * N if want_x else 0)
     budget = _BATCH_BYTES
     if budget is None:  # a third of the device (60 GB of a B200's 180), never more than is free right now
         import torch

@@ -351,3 +351,45 @@ def test_sample_many_runs_with_a_ba_generator(oracle):
         ox, oc = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
         np.testing.assert_array_equal(x[i], ox)
         np.testing.assert_array_equal(c[i], oc.astype(float))
+
+
+@pytest.mark.parametrize("n,k,p,S,R,rb,re", [(500, 6, 0.2, 2, 5, 1, 4), (3000, 10, 0.1, 1, 3, 0, 3), (200, 4, 1.0, 1, 3, 0, 3),
+                                             (64, 2, 0.0, 1, 2, 0, 2), (400, 2, 0.5, 1, 3, 0, 3), (100, 40, 0.5, 1, 2, 0, 2)])
+def test_ws_device_batch_equals_oracle(oracle, n, k, p, S, R, rb, re):
+    """(400, 2, 0.5): sparse rings fall apart and are drawn again -- the attempt counter; (100, 40, .5): rows of 2 x 32+ lanes.)"""
+    from sponet_b200 import engine
+
+    b = engine.GraphBatch.watts_strogatz(n, k, p, 815, S, R, rb, re, padded_rows=True)
+    for slot in range(b.count):
+        j, i = divmod(slot, re - rb)
+        rp, col = b.csr(slot)
+        orp, ocol, _ = oracle.ws_graph(n, k, p, 815, j * R + rb + i)
+        np.testing.assert_array_equal(rp, orp)
+        np.testing.assert_array_equal(col, ocol)
+    assert b.info()["nnz"] == b.count * n * (k // 2) * 2
+    b.close()
+    with pytest.raises(RuntimeError, match="Maximum number of tries"):
+        engine.GraphBatch.watts_strogatz(2000, 2, 0.9, 3, 1, 2, 0, 2, tries=3)
+    with pytest.raises(ValueError):
+        engine.GraphBatch.watts_strogatz(10, 10, 0.1, 3, 1, 1, 0, 1)
+
+
+def test_sample_many_runs_with_a_ws_generator(oracle):
+    from sponet_b200 import CNVMParameters, OpinionShares, WattsStrogatzGenerator, engine, sample_many_runs
+
+    n, k, p, R, T, M = 1000, 8, 0.15, 5, 3, 2
+    kw = dict(num_opinions=M, r=[[0, 1.0], [1.2, 0]], r_tilde=[[0, 0.05], [0.02, 0]])
+    x0 = np.random.default_rng(0).integers(0, M, n)
+
+    def params():
+        return CNVMParameters(network_generator=WattsStrogatzGenerator(n, k, p, rng=np.random.default_rng(6)), **kw)
+
+    t, c = sample_many_runs(params(), x0, 2.0, T, R, collective_variable=OpinionShares(M), rng=np.random.default_rng(1))
+    _, x = sample_many_runs(params(), x0, 2.0, T, R, rng=np.random.default_rng(1))
+    gseed = WattsStrogatzGenerator(n, k, p, rng=np.random.default_rng(6)).draw_batch_seed()
+    seed = engine.draw_seed(np.random.default_rng(1))
+    for i in (0, R - 1):
+        rp, col, _ = oracle.ws_graph(n, k, p, gseed, i)
+        ox, oc = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
+        np.testing.assert_array_equal(x[i], ox)
+        np.testing.assert_array_equal(c[i], oc.astype(float))

@@ -120,3 +120,31 @@ def test_ba_oracle_follows_the_networkx_process(oracle):
     # m = 1: a tree
     rp, col = oracle.ba_graph(500, 1, seed=1, c=0)
     assert rp[-1] == 2 * 499
+
+
+def test_ws_oracle_follows_the_networkx_process(oracle):
+    """Sequential statement of the device Watts-Strogatz generator against networkx.watts_strogatz_graph: n k / 2 edges, every
+    vertex keeps its k / 2 own edges, the share of surviving lattice edges is 1 - p, the degree distribution agrees."""
+    nx = pytest.importorskip("networkx")
+    n, k, p, G = 2000, 6, 0.2, 10
+    ours, theirs, lattice = [], [], []
+    for c in range(G):
+        rp, col, attempts = oracle.ws_graph(n, k, p, seed=5, c=c)
+        deg = _check_simple_graph(rp, col, n)
+        assert rp[-1] == n * k and deg.min() >= k // 2 and attempts == 1
+        src = np.repeat(np.arange(n), deg)
+        lattice.append((np.minimum((src - col) % n, (col - src) % n) <= k // 2).mean())
+        ours.append(deg)
+        theirs.append(np.array([d for _, d in nx.watts_strogatz_graph(n, k, p, seed=50 + c).degree()]))
+    ours, theirs = np.concatenate(ours), np.concatenate(theirs)
+    # (a rewired edge lands inside the lattice band by chance with probability ~ k / n)
+    assert abs(np.mean(lattice) - (1 - p)) < 5 * np.sqrt(p * (1 - p) / (n * k / 2 * G)) + 2 * k / n
+    for d in range(k - 2, k + 4):
+        pa, pb = (ours == d).mean(), (theirs == d).mean()
+        assert abs(pa - pb) < 5 * np.sqrt((pa * (1 - pa) + pb * (1 - pb)) / ours.size) + 1e-4, (d, pa, pb)
+    # p = 0: the lattice itself; a sparse ring that falls apart is drawn again or given up
+    rp, col, _ = oracle.ws_graph(50, 4, 0.0, seed=1, c=0)
+    assert np.array_equal(col[rp[7] : rp[8]], [5, 6, 8, 9])
+    assert any(oracle.ws_graph(400, 2, 0.5, seed=2, c=c)[2] > 1 for c in range(3))
+    with pytest.raises(RuntimeError, match="Maximum number of tries"):
+        oracle.ws_graph(2000, 2, 0.9, seed=3, c=0, tries=3)
