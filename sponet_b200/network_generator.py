@@ -129,6 +129,7 @@ class BarabasiAlbertGenerator:
         self.num_agents = num_agents
         self.m = m
         self.rng = rng
+        self.build_bytes_per_vertex = 4.0 * m  # the targets of every vertex while a device batch is built
 
     def __call__(self):
         return _nx().barabasi_albert_graph(self.num_agents, self.m, seed=self.rng)
