@@ -128,6 +128,16 @@ int sponet_graph_batch_create_ba(int64_t num_agents, int32_t m, uint64_t seed, i
 int sponet_graph_batch_create_ws(int64_t num_agents, int32_t k, double p, uint64_t seed, int64_t num_states, int64_t num_runs_total,
                                  int64_t run_begin, int64_t run_end, int32_t tries, int layouts, sponet_graph** out);
 
+/* The same for random d-regular graphs (sponet/network_generator.py:87-115 = networkx.random_regular_graph(d, n)): the pairing
+ * process with restarts.  Attempt a: n d stubs (position mod n); pass s: Fisher-Yates shuffle of the remaining stubs (i = L - 1
+ * .. 1: swap with j = mulhi(word 0 of Philox4x32-10(counter (i, s | a << 16, c_lo, c_hi[16] | 7 << 24), key seed), i + 1)),
+ * consecutive stubs paired in order, a loop or an existing edge leaves one potential at each of its vertices; no potential left:
+ * done; every two distinct vertices with potentials already adjacent: the attempt failed, the next one starts; else the
+ * potentials (in vertex order) are the stubs of the next pass.  One warp per graph; restated by oracle_regular_graph
+ * (bit-identical). */
+int sponet_graph_batch_create_regular(int64_t num_agents, int32_t d, uint64_t seed, int64_t num_states, int64_t num_runs_total,
+                                      int64_t run_begin, int64_t run_end, int32_t tries, int layouts, sponet_graph** out);
+
 /* Device memory of destroyed batches is kept for the next batch (cudaMalloc / cudaFree of tens of gigabytes cost up to
  * seconds; at most 64 GiB idle per process).  This returns it to the driver. */
 int sponet_graph_batch_trim(void);

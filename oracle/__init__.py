@@ -514,3 +514,17 @@ def ws_graph(n, k, p, seed, c, tries=100):
         raise RuntimeError("oracle_ws_graph: a vertex exceeds the row capacity")
     assert nnz == col.size
     return row_ptr, col, used.value
+
+
+def regular_graph(n, d, seed, c, tries=64):
+    """oracle_regular_graph: graph index c of the device-side random regular generator as (row_ptr, col, attempts)."""
+    f = lib().oracle_regular_graph
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, _i32, _i32, C.POINTER(C.c_int32)]
+    row_ptr = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(n * d, dtype=np.int32)
+    used = C.c_int32(0)
+    nnz = f(n, d, seed, c, tries, row_ptr, col, C.byref(used))
+    if nnz < 0:
+        raise RuntimeError("oracle_regular_graph: no attempt produced a regular graph")
+    return row_ptr, col, used.value

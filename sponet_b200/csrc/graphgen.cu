@@ -445,6 +445,26 @@ __global__ void ba_fill_kernel(BaArgs A, const int32_t* targets, const uint32_t*
     });
 }
 
+// Arrays a single warp reads and writes through the L2 (ld.cg / st.cg): what one lane wrote is what another lane reads after
+// __syncwarp(), without the cost of volatile (system-scope) accesses.
+template <typename T>
+struct CgArray {
+    T* p;
+    struct Ref {
+        T* q;
+        __device__ __forceinline__ operator T() const { return __ldcg(q); }
+        __device__ __forceinline__ const Ref& operator=(T v) const {
+            __stcg(q, v);
+            return *this;
+        }
+        __device__ __forceinline__ const Ref& operator=(const Ref& o) const {
+            __stcg(q, (T)o);
+            return *this;
+        }
+    };
+    __device__ __forceinline__ Ref operator[](int64_t i) const { return Ref{p + i}; }
+};
+
 // ---- Watts-Strogatz (networkx.connected_watts_strogatz_graph, as sponet/network_generator.py:147-183 calls it) ----
 // Ring lattice with k / 2 neighbours on each side, then the positions (j, u) in networkx's order (j = 1 .. k / 2 outer, u inner):
 // with probability p the edge (u, u + j) is replaced by (u, w), w uniform, drawn again while w == u or {u, w} is an edge; the
@@ -466,8 +486,8 @@ __global__ void __launch_bounds__(128) ws_build_kernel(WsArgs A, int32_t* adj_al
     if (b >= A.count) return;
     const int64_t n = A.n, cap = A.cap;
     const int half = A.k / 2;
-    volatile int32_t* adj = adj_all + b * n * cap;
-    volatile uint32_t* deg = deg_all + b * n;
+    const CgArray<int32_t> adj{adj_all + b * n * cap};
+    const CgArray<uint32_t> deg{deg_all + b * n};
     int32_t* queue = queue_all + b * n;
     uint32_t* seen = seen_all + b * ((n + 31) / 32);
     const int64_t jb = b / A.nrun, ib = b - jb * A.nrun;
@@ -587,6 +607,175 @@ __global__ void ws_fill_kernel(int64_t rows, int64_t cap, const int32_t* adj, co
     if (tid >= rows) return;
     const uint32_t d = deg[tid];
     for (uint32_t e = 0; e < d; ++e) col[off[tid] + e] = adj[tid * cap + e];
+}
+
+// ---- random regular graphs (networkx.random_regular_graph, as sponet/network_generator.py:87-115 calls it) ----
+// The pairing process with restarts: see oracle_regular_graph (oracle/oracle_native.inc) for the definition.  Shuffle and
+// pairing are sequential by definition; one warp owns a graph, its lanes draw the random numbers of 32 shuffle steps at a
+// time and scan adjacency rows together.
+struct RrArgs {
+    int64_t n, count, nrun, R_total, run_begin;
+    int32_t d, tries;
+    uint64_t seed;
+};
+
+__global__ void __launch_bounds__(128) rr_build_kernel(RrArgs A, int32_t* stubs_all, int32_t* adj_all, uint32_t* deg_all,
+                                                       uint32_t* pot_all, int32_t* status) {
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= A.count) return;
+    const int64_t n = A.n;
+    const int d = A.d;
+    const CgArray<int32_t> stubs{stubs_all + b * n * d}, adj{adj_all + b * n * d};
+    const CgArray<uint32_t> deg{deg_all + b * n}, pot{pot_all + b * n};
+    const int64_t jb = b / A.nrun, ib = b - jb * A.nrun;
+    const uint64_t c = (uint64_t)(jb * A.R_total + A.run_begin + ib);
+    const uint32_t c3 = ((uint32_t)(c >> 32) & 0xFFFFu) | (7u << 24);
+    int32_t result = -1;
+    for (int attempt = 0; attempt < A.tries && result == -1; ++attempt) {
+        int64_t L = n * d;
+        for (int64_t q = lane; q < L; q += 32) stubs[q] = (int32_t)(q % n);
+        for (int64_t u = lane; u < n; u += 32) deg[u] = 0u;
+        __syncwarp();
+        bool failed = false;
+        for (uint32_t pass = 0; L > 0 && !failed; ++pass) {
+            const uint32_t c1 = (pass & 0xFFFFu) | ((uint32_t)attempt << 16);
+            // Fisher-Yates, i = L - 1 .. 1, 32 steps at a time: the lanes draw their targets; steps that touch 64 different
+            // positions commute and are done by all lanes at once, otherwise in order by lane 0
+            for (int64_t i0 = L - 1; i0 >= 1; i0 -= 32) {
+                const int64_t i = i0 - lane;
+                const bool live = i >= 1;
+                uint32_t j = 0;
+                if (live) {
+                    const uint4 r = sp_philox4x32_10((uint32_t)i, c1, (uint32_t)c, c3, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                    j = __umulhi(r.x, (uint32_t)(i + 1));
+                }
+                // lane's step touches i and j (j <= i); another lane's i' lies in (i0 - 32, i0]
+                bool clash = live && (int64_t)j != i && (int64_t)j > i0 - 32 && (int64_t)j >= 1;
+                const uint32_t same = __match_any_sync(0xffffffffu, live ? j : 0xFFFFFFFFu - (uint32_t)lane);
+                clash |= live && (same & ~(1u << lane)) != 0u;
+                if (!__any_sync(0xffffffffu, clash)) {
+                    if (live && (int64_t)j != i) {
+                        const int32_t x = stubs[i], y = stubs[j];
+                        stubs[i] = y;
+                        stubs[j] = x;
+                    }
+                } else {
+                    const int steps = (int)(i0 < 32 ? i0 : 32);
+                    for (int t = 0; t < steps; ++t) {
+                        const uint32_t jt = __shfl_sync(0xffffffffu, j, t);
+                        if (lane == 0) {
+                            const int64_t it = i0 - t;
+                            const int32_t x = stubs[it];
+                            stubs[it] = stubs[jt];
+                            stubs[jt] = x;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            for (int64_t u = lane; u < n; u += 32) pot[u] = 0u;
+            __syncwarp();
+            uint32_t npot = 0;
+            // the pairs in order, 32 at a time: pairs over 64 different vertices commute (one lane each), otherwise the
+            // chunk is done pair by pair with all lanes scanning the row
+            for (int64_t q0 = 0; q0 + 1 < L; q0 += 64) {
+                const int64_t q = q0 + 2 * lane;
+                const bool live = q + 1 < L;
+                const int32_t m1 = live ? stubs[q] : -1 - 2 * lane, m2 = live ? stubs[q + 1] : -2 - 2 * lane;
+                bool clash = false;
+                for (int t = 0; t < 32; ++t) {
+                    const int32_t a1 = __shfl_sync(0xffffffffu, m1, t), a2 = __shfl_sync(0xffffffffu, m2, t);
+                    clash |= t != lane && (a1 == m1 || a1 == m2 || a2 == m1 || a2 == m2);
+                }
+                if (!__any_sync(0xffffffffu, clash)) {
+                    bool bad = false;
+                    if (live) {
+                        const uint32_t d1 = deg[m1];
+                        bad = m1 == m2;
+                        for (uint32_t e = 0; e < d1; ++e) bad |= adj[(int64_t)m1 * d + e] == m2;
+                        if (!bad) {
+                            const uint32_t d2 = deg[m2];
+                            adj[(int64_t)m1 * d + d1] = m2;
+                            adj[(int64_t)m2 * d + d2] = m1;
+                            deg[m1] = d1 + 1;
+                            deg[m2] = d2 + 1;
+                        } else if (m1 == m2) {
+                            pot[m1] = pot[m1] + 2u;
+                        } else {
+                            pot[m1] = pot[m1] + 1u;
+                            pot[m2] = pot[m2] + 1u;
+                        }
+                    }
+                    npot += 2u * (uint32_t)__popc(__ballot_sync(0xffffffffu, bad));
+                } else {
+                    const int pairs = (int)(((L - q0) / 2) < 32 ? ((L - q0) / 2) : 32);
+                    for (int t = 0; t < pairs; ++t) {
+                        const int32_t s1 = __shfl_sync(0xffffffffu, m1, t), s2 = __shfl_sync(0xffffffffu, m2, t);
+                        const uint32_t d1 = deg[s1];
+                        bool hit = false;
+                        for (uint32_t e = lane; e < d1; e += 32) hit |= adj[(int64_t)s1 * d + e] == s2;
+                        const bool bad = __any_sync(0xffffffffu, hit) || s1 == s2;
+                        if (lane == 0) {
+                            if (!bad) {
+                                const uint32_t d2 = deg[s2];
+                                adj[(int64_t)s1 * d + d1] = s2;
+                                adj[(int64_t)s2 * d + d2] = s1;
+                                deg[s1] = d1 + 1;
+                                deg[s2] = d2 + 1;
+                            } else {
+                                pot[s1] = pot[s1] + 1u;
+                                pot[s2] = pot[s2] + 1u;
+                            }
+                        }
+                        if (bad) npot += 2;
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+            }
+            if (npot == 0) {
+                L = 0;
+                break;
+            }
+            // the vertices with potentials, in vertex order, back into stubs[0 .. npot) -- and networkx's _suitable on them
+            int64_t L2 = 0;
+            for (int64_t u0 = 0; u0 < n; u0 += 32) {
+                const int64_t u = u0 + lane;
+                const uint32_t pu = u < n ? pot[u] : 0u;
+                uint32_t have = __ballot_sync(0xffffffffu, pu != 0u);
+                while (have) {  // (few vertices: sequential)
+                    const int src = __ffs(have) - 1;
+                    have &= have - 1;
+                    const uint32_t cnt = __shfl_sync(0xffffffffu, pu, src);
+                    if (lane == 0)
+                        for (uint32_t t = 0; t < cnt; ++t) stubs[L2 + t] = (int32_t)(u0 + src);
+                    L2 += cnt;
+                }
+            }
+            __syncwarp();
+            bool suitable = false;
+            for (int64_t x = 0; x < L2 && !suitable; ++x) {
+                const int32_t u = stubs[x];
+                if (x > 0 && stubs[x - 1] == u) continue;
+                const uint32_t du = deg[u];
+                for (int64_t y = x + 1; y < L2 && !suitable; ++y) {
+                    const int32_t v = stubs[y];
+                    if (v == u) continue;
+                    bool hit = false;
+                    for (uint32_t e = lane; e < du; e += 32) hit |= adj[(int64_t)u * d + e] == v;
+                    suitable = !__any_sync(0xffffffffu, hit);
+                }
+            }
+            if (!suitable) {
+                failed = true;
+                break;
+            }
+            L = L2;
+        }
+        if (!failed) result = attempt + 1;
+    }
+    if (lane == 0) status[b] = result;
 }
 
 // Common tail of the batch generators: degrees -> absolute row offsets, graph handle and adjacency array; after the
@@ -851,6 +1040,53 @@ extern "C" int sponet_graph_batch_create_ws(int64_t num_agents, int32_t k, doubl
     BatchBuilder bb(tmp, n, B, "graph_batch_create_ws");
     SP_TRY(bb.scan(d_deg));
     ws_fill_kernel<<<grid, 256>>>(rows, A.cap, d_adj, d_deg, bb.d_off, bb.g->d_col);
+    SP_TRY(bb.finish(d_deg, layouts));
+    *out = bb.release();
+    return SPONET_OK;
+}
+
+extern "C" int sponet_graph_batch_create_regular(int64_t num_agents, int32_t d, uint64_t seed, int64_t num_states,
+                                                 int64_t num_runs_total, int64_t run_begin, int64_t run_end, int32_t tries,
+                                                 int layouts, sponet_graph** out) {
+    SP_REQUIRE(out, "graph_batch_create_regular: out is NULL");
+    *out = nullptr;
+    const int64_t n = num_agents, nrun = run_end - run_begin, B = num_states * nrun;
+    SP_REQUIRE(n >= 2 && n < ((int64_t)1 << 31), "graph_batch_create_regular: num_agents out of range");
+    SP_REQUIRE((n * d) % 2 == 0, "n * d must be even");                                  // networkx's messages
+    SP_REQUIRE(d >= 1 && d < n, "the 0 <= d < n inequality must be satisfied (and d >= 1: no isolated vertices)");
+    SP_REQUIRE(tries >= 1 && tries <= 32767, "graph_batch_create_regular: tries must be in [1, 32767]");
+    SP_REQUIRE(num_states >= 1 && nrun >= 1 && run_begin >= 0 && num_runs_total >= 1, "graph_batch_create_regular: bad run range");
+    SP_REQUIRE(B * n < ((int64_t)1 << 32), "graph_batch_create_regular: %lld graphs of %lld agents exceed 2^32 rows; use smaller batches",
+               (long long)B, (long long)n);
+    SP_REQUIRE(n * d < ((int64_t)1 << 32) - 64, "graph_batch_create_regular: too many stubs per graph");
+    RrArgs A;
+    A.n = n;
+    A.count = B;
+    A.nrun = nrun;
+    A.R_total = num_runs_total;
+    A.run_begin = run_begin;
+    A.d = d;
+    A.tries = tries;
+    A.seed = seed;
+    const int64_t rows = B * n;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    Freer tmp;
+    int32_t *d_stubs, *d_adj, *d_status;
+    uint32_t *d_deg, *d_pot;
+    SP_CUDA(tmp.alloc((void**)&d_stubs, (size_t)rows * d * sizeof(int32_t)));
+    SP_CUDA(tmp.alloc((void**)&d_adj, (size_t)rows * d * sizeof(int32_t)));
+    SP_CUDA(tmp.alloc((void**)&d_deg, rows * 4));
+    SP_CUDA(tmp.alloc((void**)&d_pot, rows * 4));
+    SP_CUDA(tmp.alloc((void**)&d_status, B * 4));
+    rr_build_kernel<<<(unsigned)((B * 32 + 127) / 128), 128>>>(A, d_stubs, d_adj, d_deg, d_pot, d_status);
+    SP_CUDA(cudaGetLastError());
+    std::vector<int32_t> status((size_t)B);
+    SP_CUDA(cudaMemcpy(status.data(), d_status, B * 4, cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < B; ++b)
+        SP_REQUIRE(status[b] > 0, "graph_batch_create_regular: no regular graph after %d attempts", tries);
+    BatchBuilder bb(tmp, n, B, "graph_batch_create_regular");
+    SP_TRY(bb.scan(d_deg));
+    ws_fill_kernel<<<grid, 256>>>(rows, d, d_adj, d_deg, bb.d_off, bb.g->d_col);
     SP_TRY(bb.finish(d_deg, layouts));
     *out = bb.release();
     return SPONET_OK;

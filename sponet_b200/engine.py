@@ -127,6 +127,19 @@ class GraphBatch:
         self._adopt(h, num_agents, num_states, run_begin, run_end)
         return self
 
+    @classmethod
+    def random_regular(cls, num_agents, d, seed, num_states, num_runs_total, run_begin, run_end, tries=1000, padded_rows=False,
+                       records=True):
+        """Random d-regular graphs (sponet_graph_batch_create_regular; networkx.random_regular_graph's pairing process)."""
+        _lib.require_device()
+        h = C.c_void_p()
+        _lib.check(_lib.lib().sponet_graph_batch_create_regular(int(num_agents), int(d), int(seed), int(num_states),
+                                                                int(num_runs_total), int(run_begin), int(run_end), int(tries),
+                                                                int(bool(padded_rows)) | 2 * int(bool(records)), C.byref(h)))
+        self = cls.__new__(cls)
+        self._adopt(h, num_agents, num_states, run_begin, run_end)
+        return self
+
     def csr(self, slot: int):
         """Graph `slot` of the batch as host (row_ptr, col)."""
         row_ptr = np.empty(self.num_agents + 1, dtype=np.int32)

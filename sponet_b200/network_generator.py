@@ -7,8 +7,8 @@ reference's own generators included) works as well.
 
 What is new: a generator may also offer ``device_batch(...)``, which makes ALL the graphs of an ensemble call on the
 GPU (``engine.GraphBatch``), one per realization, so that ``sample_many_runs`` runs the whole ensemble in one launch
-instead of one host-generated graph and one launch per realization.  ``ErdosRenyiGenerator``,
-``BarabasiAlbertGenerator`` and ``WattsStrogatzGenerator`` implement it (``csrc/graphgen.cu``).  The device graphs follow the same random-graph process as
+instead of one host-generated graph and one launch per realization.  All four generators
+of this module implement it (``csrc/graphgen.cu``).  The device graphs follow the same random-graph process as
 networkx's, but they are not the same graphs: they are keyed by (seed, realization index), the seed being drawn from the
 generator's ``rng``.
 """
@@ -111,9 +111,25 @@ class RandomRegularGenerator:
         self.num_agents = num_agents
         self.d = d
         self.rng = rng
+        self.build_bytes_per_vertex = 8.0 * d + 4.0  # stubs and adjacency rows while a device batch is built
 
     def __call__(self):
         return _nx().random_regular_graph(self.d, self.num_agents, seed=self.rng)
+
+    def draw_batch_seed(self) -> int:
+        return int(self.rng.integers(0, 2**63, dtype=np.int64))
+
+    def expected_mean_degree(self) -> float:
+        return float(self.d)
+
+    def device_batch(self, seed: int, num_states: int, num_runs_total: int, run_begin: int, run_end: int,
+                     padded_rows: bool = False, records: bool = True):
+        """networkx's pairing process with restarts, run on the current GPU (one warp per graph) for the realizations
+        [run_begin, run_end) of every initial state."""
+        from . import engine
+
+        return engine.GraphBatch.random_regular(self.num_agents, self.d, seed, num_states, num_runs_total, run_begin, run_end,
+                                                padded_rows=padded_rows, records=records)
 
     def __repr__(self) -> str:
         return f"Uniform random regular graph with d={self.d} on {self.num_agents} nodes"

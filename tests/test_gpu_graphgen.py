@@ -393,3 +393,44 @@ def test_sample_many_runs_with_a_ws_generator(oracle):
         ox, oc = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
         np.testing.assert_array_equal(x[i], ox)
         np.testing.assert_array_equal(c[i], oc.astype(float))
+
+
+@pytest.mark.parametrize("n,d,S,R,rb,re", [(500, 4, 2, 5, 1, 4), (3000, 10, 1, 3, 0, 3), (12, 5, 1, 8, 0, 8), (64, 63, 1, 2, 0, 2),
+                                           (50, 1, 1, 2, 0, 2), (100, 40, 1, 2, 0, 2)])
+def test_regular_device_batch_equals_oracle(oracle, n, d, S, R, rb, re):
+    """((12, 5): most attempts fail and restart; (100, 40): rows longer than a warp.)"""
+    from sponet_b200 import engine
+
+    b = engine.GraphBatch.random_regular(n, d, 99, S, R, rb, re, padded_rows=True)
+    for slot in range(b.count):
+        j, i = divmod(slot, re - rb)
+        rp, col = b.csr(slot)
+        orp, ocol, _ = oracle.regular_graph(n, d, 99, j * R + rb + i)
+        np.testing.assert_array_equal(rp, orp)
+        np.testing.assert_array_equal(col, ocol)
+    info = b.info()
+    assert info["min_degree"] == info["max_degree"] == d
+    b.close()
+    with pytest.raises(ValueError, match="n \\* d must be even"):
+        engine.GraphBatch.random_regular(11, 3, 1, 1, 1, 0, 1)
+
+
+def test_sample_many_runs_with_a_regular_generator(oracle):
+    from sponet_b200 import CNVMParameters, OpinionShares, RandomRegularGenerator, engine, sample_many_runs
+
+    n, d, R, T, M = 1000, 6, 4, 3, 2
+    kw = dict(num_opinions=M, r=[[0, 1.0], [1.2, 0]], r_tilde=[[0, 0.05], [0.02, 0]])
+    x0 = np.random.default_rng(0).integers(0, M, n)
+
+    def params():
+        return CNVMParameters(network_generator=RandomRegularGenerator(n, d, rng=np.random.default_rng(6)), **kw)
+
+    t, c = sample_many_runs(params(), x0, 2.0, T, R, collective_variable=OpinionShares(M), rng=np.random.default_rng(1))
+    _, x = sample_many_runs(params(), x0, 2.0, T, R, rng=np.random.default_rng(1))
+    gseed = RandomRegularGenerator(n, d, rng=np.random.default_rng(6)).draw_batch_seed()
+    seed = engine.draw_seed(np.random.default_rng(1))
+    for i in (0, R - 1):
+        rp, col, _ = oracle.regular_graph(n, d, gseed, i)
+        ox, oc = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
+        np.testing.assert_array_equal(x[i], ox)
+        np.testing.assert_array_equal(c[i], oc.astype(float))

@@ -63,12 +63,13 @@ def _native_counts(g, runs, seed, scale_noise=1.0):
         from sponet_b200 import BarabasiAlbertGenerator, ErdosRenyiGenerator
 
         n = int(g["num_agents"])
-        from sponet_b200 import WattsStrogatzGenerator
+        from sponet_b200 import RandomRegularGenerator, WattsStrogatzGenerator
 
         kind, grng = str(g["generator"]), np.random.default_rng(seed + 1)
         gen = (ErdosRenyiGenerator(n, float(g["p"]), rng=grng) if kind == "er"
                else BarabasiAlbertGenerator(n, int(g["m"]), rng=grng) if kind == "ba"
-               else WattsStrogatzGenerator(n, int(g["k"]), float(g["p"]), rng=grng))
+               else WattsStrogatzGenerator(n, int(g["k"]), float(g["p"]), rng=grng) if kind == "ws"
+               else RandomRegularGenerator(n, int(g["d"]), rng=grng))
         params = CNVMParameters(num_opinions=M, network_generator=gen, r=g["r"], r_tilde=g["r_tilde"] * scale_noise)
     elif "workload" in g:
         params = _workload_params(g, scale_noise)
@@ -125,10 +126,10 @@ def test_native_mode_matches_reference_distribution(name):
     assert pmin >= ALPHA / n_cmp, f"KS rejects: p = {pmin:.3g}"
 
 
-@pytest.mark.parametrize("name", ["cnvm_pernet_er1000", "cnvm_pernet_ba1000", "cnvm_pernet_ws1000"])
+@pytest.mark.parametrize("name", ["cnvm_pernet_er1000", "cnvm_pernet_ba1000", "cnvm_pernet_ws1000", "cnvm_pernet_reg1000"])
 def test_per_run_networks_match_the_reference_distribution(name):
     """`params.network_generator`: the reference draws a networkx graph per realization (its ErdosRenyiGenerator /
-    BarabasiAlbertGenerator / WattsStrogatzGenerator, 1.2e4 realizations through its own `sample_many_runs`); here the graphs of all realizations are
+    BarabasiAlbertGenerator / WattsStrogatzGenerator / RandomRegularGenerator, 1.2e4 realizations through its own `sample_many_runs`); here the graphs of all realizations are
     generated on the device.  At N = 1000 the variation from graph to graph is a visible part of the CV's distribution, so
     means, variances and KS test the generated ensemble of graphs as well as the chains on them."""
     g = load_golden("stats_" + name)

@@ -148,3 +148,30 @@ def test_ws_oracle_follows_the_networkx_process(oracle):
     assert any(oracle.ws_graph(400, 2, 0.5, seed=2, c=c)[2] > 1 for c in range(3))
     with pytest.raises(RuntimeError, match="Maximum number of tries"):
         oracle.ws_graph(2000, 2, 0.9, seed=3, c=0, tries=3)
+
+
+def test_regular_oracle_follows_the_networkx_process(oracle):
+    """Sequential statement of the device random-regular generator: simple d-regular graphs; on 6 vertices and d = 3 the 70
+    labelled graphs appear with the frequencies networkx.random_regular_graph gives them (the pairing process with restarts is
+    not exactly uniform: K_3,3 is over-represented by both) -- chi-square of the two samples, 5 sigma of its distribution."""
+    nx = pytest.importorskip("networkx")
+    from collections import Counter
+
+    for n, d in ((2000, 4), (501, 6), (64, 63), (50, 1)):
+        rp, col, _ = oracle.regular_graph(n, d, seed=3, c=1)
+        deg = _check_simple_graph(rp, col, n)
+        assert (deg == d).all()
+    R = 7000
+    ours, theirs = Counter(), Counter()
+    rng = np.random.default_rng(1)
+    for c in range(R):
+        ours[tuple(oracle.regular_graph(6, 3, 99, c)[1])] += 1
+        g = nx.random_regular_graph(3, 6, seed=rng)
+        theirs[tuple(v for i in range(6) for v in sorted(g[i]))] += 1
+    keys = sorted(set(ours) | set(theirs))
+    assert len(keys) == 70
+    x, y = np.array([ours[k] for k in keys], float), np.array([theirs[k] for k in keys], float)
+    chi2 = ((x - y) ** 2 / (x + y)).sum()
+    assert chi2 < 69 + 5 * np.sqrt(2 * 69), chi2
+    # restarts happen and are counted (dense small graphs fail often)
+    assert max(oracle.regular_graph(12, 5, 1, c)[2] for c in range(8)) > 1
