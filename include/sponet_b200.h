@@ -98,8 +98,8 @@ int sponet_graph_neighbor_table(const sponet_graph* g, int32_t* log2_slots, uint
  * batch do not fit the L2, and with the record the degree and the sampled neighbour of most agents come out of one
  * DRAM burst instead of two (skipped silently when a degree exceeds 255).  The neighbour rule is the same with and
  * without records: entry mulhi(r2, degree) of the sorted row.
- * The handle is accepted by sponet_cnvm_run / sponet_cntm_run in native mode (uniform degree_alpha, i.e. alpha = 1; no
- * degree-weighted and no edge collective variables) when it holds num_states * (run_end - run_begin) graphs, and is
+ * The handle is accepted by sponet_cnvm_run / sponet_cntm_run in native mode (uniform degree_alpha, i.e. alpha = 1, or after
+ * sponet_graph_batch_set_weights; no edge collective variables) when it holds num_states * (run_end - run_begin) graphs, and is
  * released with sponet_graph_destroy.  num_states * (run_end - run_begin) * num_agents must stay below 2^32.  A caller
  * that covers the states in blocks adds first_state * num_runs_total to run_begin / run_end (as it adds it to
  * sponet_native_opts.chain_offset of the run call). */
@@ -137,6 +137,13 @@ int sponet_graph_batch_create_ws(int64_t num_agents, int32_t k, double p, uint64
  * (bit-identical). */
 int sponet_graph_batch_create_regular(int64_t num_agents, int32_t d, uint64_t seed, int64_t num_states, int64_t num_runs_total,
                                       int64_t run_begin, int64_t run_end, int32_t tries, int layouts, sponet_graph** out);
+
+/* Degree-weighted agent selection on a batch (alpha != 1): weight_of_degree[d] = d^(1 - alpha) for d = 0 .. max_degree, computed
+ * by the caller with the arithmetic of sponet/cnvm/model.py:38 (`degrees ** (1 - alpha)`).  Builds, per graph, the alias table
+ * of sponet/sampling.py:54-96 over its agents' weights (same statements as sponet_build_alias_table) and the sequential sum of
+ * the weights; sponet_cnvm_run then takes agent weights, event rate and noise probability of every chain from its own graph
+ * (sponet/cnvm/model.py:257-258) and ignores params->degree_alpha. */
+int sponet_graph_batch_set_weights(sponet_graph* g, const double* weight_of_degree, int64_t num_weights);
 
 /* Device memory of destroyed batches is kept for the next batch (cudaMalloc / cudaFree of tens of gigabytes cost up to
  * seconds; at most 64 GiB idle per process).  This returns it to the driver. */

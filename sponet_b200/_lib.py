@@ -107,6 +107,7 @@ _SIGNATURES = {
     "sponet_graph_batch_create_ba": (C.c_int, [_i64, _i32, _u64, _i64, _i64, _i64, _i64, C.c_int, C.POINTER(_vp)]),
     "sponet_graph_batch_create_ws": (C.c_int, [_i64, _i32, _f64, _u64, _i64, _i64, _i64, _i64, _i32, C.c_int, C.POINTER(_vp)]),
     "sponet_graph_batch_create_regular": (C.c_int, [_i64, _i32, _u64, _i64, _i64, _i64, _i64, _i32, C.c_int, C.POINTER(_vp)]),
+    "sponet_graph_batch_set_weights": (C.c_int, [_vp, _vp, _i64]),
     "sponet_graph_batch_get": (C.c_int, [_vp, _i64, _vp, _vp, _i64]),
     "sponet_graph_batch_trim": (C.c_int, []),
     "sponet_cnvm_replay": (C.c_int, [_vp, _i64, C.POINTER(sponet_cnvm_params), _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -157,6 +157,8 @@ extern "C" int sponet_graph_create(int64_t n, const int32_t* row_ptr, const int3
     g->batch = 1;
     g->d_rec = nullptr;
     g->pooled = false;
+    g->d_alias = nullptr;
+    g->h_weight_sum = nullptr;
     g->nbtab_log2 = use_tab ? lg : 0;
     g->n_col4 = n4;
     g->n = n;
@@ -214,6 +216,8 @@ extern "C" int sponet_graph_destroy(sponet_graph* g) {
         sp_pool_free(g->d_row4);
         sp_pool_free(g->d_col4);
         sp_pool_free(g->d_rec);
+        sp_pool_free(g->d_alias);
+        delete[] g->h_weight_sum;
     } else {
         cudaFree(g->d_row_ptr);
         cudaFree(g->d_row);

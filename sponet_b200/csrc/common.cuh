@@ -68,6 +68,10 @@ struct sponet_graph {
     uint32_t* d_rec;     // [batch * n * 16]
     int32_t rec_deg_bits;
     bool pooled;         // device memory from sp_pool_alloc (graphgen.cu)
+    // Batch with degree-weighted agent selection (alpha != 1, sponet_graph_batch_set_weights): per graph the alias table of
+    // the weights w(degree) (sponet/sampling.py:54-96 on every graph) and the sum of the weights (event rates).
+    uint2* d_alias;      // [batch * n] (threshold, alias) or nullptr
+    double* h_weight_sum;  // [batch] (host) or nullptr
 };
 
 // Device memory of graph batches (graphgen.cu): tens of gigabytes per ensemble call, allocated and released block after
@@ -244,6 +248,9 @@ __device__ __forceinline__ double sp_u53(uint32_t a, uint32_t b) {
 #endif  // __CUDACC__
 
 // p -> floor(p * 2^32) saturated to 0xFFFFFFFF
+#ifdef __CUDACC__
+__host__ __device__
+#endif
 inline uint32_t sp_prob_to_thr(double p) {
     if (!(p > 0.0)) return 0u;
     if (p >= 1.0) return 0xFFFFFFFFu;

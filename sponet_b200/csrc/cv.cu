@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(CV_THREADS) propensities_kernel(const uint8_t*
 extern "C" int sponet_interfaces(const sponet_graph* g, const uint8_t* x, int64_t S, double* out,
                                  void* cuda_stream) {
     SP_REQUIRE(g && x && out && S >= 0, "interfaces: bad arguments");
-    SP_REQUIRE(g->batch == 1, "interfaces: a single graph is required, not a graph batch");
+    SP_REQUIRE(!g->pooled, "interfaces: a single graph is required, not a graph batch");
     if (S == 0) return SPONET_OK;
     SP_REQUIRE(S < ((int64_t)1 << 31), "interfaces: too many snapshots for one launch");
     SpScratch sc((cudaStream_t)cuda_stream);
@@ -175,7 +175,7 @@ extern "C" int sponet_propensities(const sponet_graph* g, int64_t num_agents, co
                                    const double* r, const double* r_tilde, double* out, void* cuda_stream) {
     SP_REQUIRE(x && out && r && r_tilde && S >= 0 && num_agents >= 1, "propensities: bad arguments");
     SP_REQUIRE(!g || (g->n == num_agents && degree_alpha), "propensities: graph / degree_alpha mismatch");
-    SP_REQUIRE(!g || g->batch == 1, "propensities: a single graph is required, not a graph batch");
+    SP_REQUIRE(!g || !g->pooled, "propensities: a single graph is required, not a graph batch");
     if (S == 0) return SPONET_OK;
     SP_REQUIRE(S < ((int64_t)1 << 31), "propensities: too many snapshots for one launch");
     SpScratch sc((cudaStream_t)cuda_stream);

@@ -778,6 +778,42 @@ __global__ void __launch_bounds__(128) rr_build_kernel(RrArgs A, int32_t* stubs_
     if (lane == 0) status[b] = result;
 }
 
+// ---- degree-weighted agent selection on a batch (alpha != 1) ----
+// One thread per graph: the sum of the weights in agent order (the reference's np.sum inside njit is a sequential loop,
+// cnvm/model.py:257) and the stack-based alias construction of sponet/sampling.py:54-96 -- the same statements as
+// sponet_build_alias_table (api.cu), whose tables the oracle and the single-graph path use.
+__global__ void batch_alias_kernel(int64_t B, int64_t n, const int2* row, const double* weight_of_degree, double* prob_all,
+                                   int32_t* small_all, int32_t* large_all, uint2* alias_all, double* weight_sum) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int2* r = row + b * n;
+    double* prob = prob_all + b * n;
+    int32_t *small_ids = small_all + b * n, *large_ids = large_all + b * n;
+    uint2* out = alias_all + b * n;
+    double total = 0.0;
+    for (int64_t i = 0; i < n; ++i) total = __dadd_rn(total, weight_of_degree[r[i].y]);
+    weight_sum[b] = total;
+    int64_t ns = 0, nl = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double pi = __dmul_rn(__ddiv_rn(weight_of_degree[r[i].y], total), (double)n);
+        prob[i] = pi;
+        out[i].y = 0u;
+        if (pi < 1) small_ids[ns++] = (int32_t)i;
+        else large_ids[nl++] = (int32_t)i;
+    }
+    while (ns > 0 && nl > 0) {
+        const int32_t sm = small_ids[--ns], lg = large_ids[--nl];
+        out[sm].y = (uint32_t)lg;
+        const double pl = __dsub_rn(__dadd_rn(prob[lg], prob[sm]), 1.0);
+        prob[lg] = pl;
+        if (pl < 1) small_ids[ns++] = lg;
+        else large_ids[nl++] = lg;
+    }
+    for (int64_t q = 0; q < nl; ++q) prob[large_ids[q]] = 1.0;
+    for (int64_t q = 0; q < ns; ++q) prob[small_ids[q]] = 1.0;
+    for (int64_t i = 0; i < n; ++i) out[i].x = sp_prob_to_thr(prob[i]);
+}
+
 // Common tail of the batch generators: degrees -> absolute row offsets, graph handle and adjacency array; after the
 // generator's fill kernels: rows sorted, (begin, degree) descriptors, degree range, and the layouts of the simulation kernels.
 struct BatchBuilder {
@@ -1089,6 +1125,31 @@ extern "C" int sponet_graph_batch_create_regular(int64_t num_agents, int32_t d, 
     ws_fill_kernel<<<grid, 256>>>(rows, d, d_adj, d_deg, bb.d_off, bb.g->d_col);
     SP_TRY(bb.finish(d_deg, layouts));
     *out = bb.release();
+    return SPONET_OK;
+}
+
+extern "C" int sponet_graph_batch_set_weights(sponet_graph* g, const double* weight_of_degree, int64_t num_weights) {
+    SP_REQUIRE(g && weight_of_degree, "graph_batch_set_weights: bad arguments");
+    SP_REQUIRE(g->pooled && g->batch >= 1, "graph_batch_set_weights: not a graph batch");
+    SP_REQUIRE(num_weights > g->max_degree, "graph_batch_set_weights: need a weight for every degree 0 .. %d", g->max_degree);
+    int cur = 0;
+    SP_CUDA(cudaGetDevice(&cur));
+    SP_REQUIRE(cur == g->device, "graph batch lives on device %d, current device is %d", g->device, cur);
+    const int64_t B = g->batch, n = g->n, rows = B * n;
+    Freer tmp;
+    double *d_w, *d_prob, *d_sum;
+    int32_t *d_small, *d_large;
+    SP_CUDA(tmp.alloc((void**)&d_w, (size_t)num_weights * sizeof(double)));
+    SP_CUDA(tmp.alloc((void**)&d_prob, (size_t)rows * sizeof(double)));
+    SP_CUDA(tmp.alloc((void**)&d_small, (size_t)rows * sizeof(int32_t)));
+    SP_CUDA(tmp.alloc((void**)&d_large, (size_t)rows * sizeof(int32_t)));
+    SP_CUDA(tmp.alloc((void**)&d_sum, (size_t)B * sizeof(double)));
+    SP_CUDA(cudaMemcpy(d_w, weight_of_degree, (size_t)num_weights * sizeof(double), cudaMemcpyHostToDevice));
+    if (!g->d_alias) SP_CUDA(sp_pool_alloc((void**)&g->d_alias, (size_t)rows * sizeof(uint2)));
+    batch_alias_kernel<<<(unsigned)((B + 31) / 32), 32>>>(B, n, g->d_row, d_w, d_prob, d_small, d_large, g->d_alias, d_sum);
+    SP_CUDA(cudaGetLastError());
+    if (!g->h_weight_sum) g->h_weight_sum = new double[(size_t)B];
+    SP_CUDA(cudaMemcpy(g->h_weight_sum, d_sum, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost));
     return SPONET_OK;
 }
 

@@ -20,7 +20,7 @@
 
 int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, int64_t num_chains,
                            int64_t nrun, int64_t R_total, int64_t run_begin, const double* d_t_eval,
-                           int T, double next_event_rate, int64_t* d_counts, const double* d_state_rates);
+                           int T, double next_event_rate, int64_t* d_counts, const double* d_state_rates, int rates_per_chain);
 int sp_validate_native_common(const double* t_eval, int64_t T, const sponet_native_opts* o, int64_t S);
 int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, int64_t n);
 int sp_validate_states(const uint8_t* x, int64_t count, int M);
@@ -461,10 +461,10 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.n = (int32_t)n;
     A.row4 = g->d_row4;
     A.col4 = g->d_col4;
-    SP_REQUIRE(g->batch == 1 || g->batch == num_chains, "graph batch holds %lld graphs, the call has %lld chains",
+    SP_REQUIRE(!g->pooled || g->batch == num_chains, "graph batch holds %lld graphs, the call has %lld chains",
                (long long)g->batch, (long long)num_chains);
     SP_REQUIRE(g->d_row4 && g->d_col4, "cntm_run: the graph batch was created without padded rows");
-    A.graph_stride = g->batch > 1 ? (uint32_t)n : 0u;
+    A.graph_stride = g->pooled ? (uint32_t)n : 0u;
     A.noise_thr = sp_prob_to_thr(p->noise_prob);
     {
         std::vector<int32_t> need((size_t)2 * (g->max_degree + 1));
@@ -491,7 +491,7 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
     A.hist_lo = o->hist_lo;
     A.hist_width = o->hist_width;
     A.ecv = cvd.ecv;
-    if (g->batch > 1 && cvd.ecv.kind != 0)
+    if (g->pooled && cvd.ecv.kind != 0)
         return sponet_fail(SPONET_ERR_UNSUPPORTED, "edge collective variables are not evaluated on a graph batch");
     A.D = cvd.D;
     A.cv_idx = cvd.d_idx;
@@ -515,7 +515,7 @@ extern "C" int sponet_cntm_run(const sponet_graph* g, const sponet_cntm_params* 
             int64_t* d_c;
             SP_CUDA(sc.alloc((void**)&d_c, (size_t)num_chains * (T - 1) * sizeof(int64_t)));
             SP_TRY(sp_launch_event_counts(sc.stream, o->seed, 0, num_chains, nrun, o->num_runs_total,
-                                          o->run_begin + o->chain_offset, d_t, (int)T, p->next_event_rate, d_c, nullptr));
+                                          o->run_begin + o->chain_offset, d_t, (int)T, p->next_event_rate, d_c, nullptr, 0));
             A.counts = d_c;
         }
     }

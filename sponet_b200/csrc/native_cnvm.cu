@@ -33,6 +33,7 @@ struct NativeCnvmArgs {
     const uint2* nbtab;  // neighbour sampler table (GRAPH == 2): [n << nbtab_log2]
     int32_t nbtab_log2;
     const uint32_t* noise_thr;  // [P] noise-branch threshold of the chain's parameter set
+    const uint32_t* chain_noise_thr;  // [S * nrun] per chain (a batch with weighted agents: the rate depends on the graph), or nullptr
     const uint2* alias_tab;  // (threshold, alias) per agent; nullptr = uniform agent weights
     const uint32_t* thr;  // [P][2*M*M]: imitation thresholds, then noise thresholds
     int32_t param_stride;  // 0: one parameter set for all initial states; 1: parameter set j for state slot j (sweep)
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
         const uint32_t gcol = GRAPH == 3 ? (uint32_t)__ldg(&A.row[grow].x) : 0u;                // ... and its first adjacency entry
         // the chain's parameter set: noise-branch threshold, acceptance tables (staged per chain slot)
         const int64_t pset = j * A.param_stride;
-        const uint32_t noise_thr = __ldg(A.noise_thr + pset);
+        const uint32_t noise_thr = A.chain_noise_thr ? __ldg(A.chain_noise_thr + cl) : __ldg(A.noise_thr + pset);
         {
             const uint32_t* tab = A.thr + pset * (2 * MM);
             if (THR4) {
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(MAXT, 1) cnvm_native_kernel(NativeCnvmArgs A) 
             z_r2 = r.z;
             z_r3 = r.w;
             z_meta = (uint32_t)(r.x < noise_thr) | (__umulhi(r.z, (uint32_t)M) << 8);
-            z_at = __ldg(A.alias_tab + z_idx);
+            z_at = __ldg(A.alias_tab + (grow + z_idx));  // (grow: the chain's own table in a batch)
         };
         auto resolve = [&](int s) {  // ALIAS only: sampling.py:117-122 with integer thresholds; noise events pick uniformly
             const uint32_t a = ((z_meta & 1u) | (uint32_t)sp_thr_accept(z_frac, z_at.x)) ? z_idx : z_at.y;
@@ -913,7 +914,7 @@ __device__ int64_t native_poisson(uint64_t seed, uint64_t chain, uint64_t interv
 // chain id of local chain cl: (cl / nrun) * R_total + run_begin + cl % nrun; nrun == 0 -> chain_begin + cl
 __global__ void event_counts_kernel(uint64_t seed, int64_t chain_begin, int64_t num_chains, int64_t nrun,
                                     int64_t R_total, int64_t run_begin, const double* t_eval, int T,
-                                    double next_event_rate, int64_t* counts, const double* state_rates) {
+                                    double next_event_rate, int64_t* counts, const double* state_rates, int rates_per_chain) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = T - 1;
     if (tid >= num_chains * per) return;
@@ -923,7 +924,7 @@ __global__ void event_counts_kernel(uint64_t seed, int64_t chain_begin, int64_t 
     if (nrun > 0) {
         const int64_t j = cl / nrun, i = cl - j * nrun;
         chain = (uint64_t)(j * R_total + run_begin + i);
-        if (state_rates) next_event_rate = state_rates[j];  // sweep: one rate per state slot
+        if (state_rates) next_event_rate = state_rates[rates_per_chain ? cl : j];  // sweep: one rate per state slot; weighted batch: per chain
     } else {
         chain = (uint64_t)(chain_begin + cl);
     }
@@ -936,7 +937,7 @@ __global__ void event_counts_kernel(uint64_t seed, int64_t chain_begin, int64_t 
 // Shared with native_cntm.cu.
 int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, int64_t num_chains,
                            int64_t nrun, int64_t R_total, int64_t run_begin, const double* d_t_eval,
-                           int T, double next_event_rate, int64_t* d_counts, const double* d_state_rates) {
+                           int T, double next_event_rate, int64_t* d_counts, const double* d_state_rates, int rates_per_chain) {
     const int64_t total = num_chains * (int64_t)(T - 1);
     if (total <= 0) return SPONET_OK;
     const int block = 128;
@@ -944,7 +945,7 @@ int sp_launch_event_counts(cudaStream_t st, uint64_t seed, int64_t chain_begin, 
     SP_REQUIRE(grid < ((int64_t)1 << 31), "too many (chain, interval) pairs for one launch");
     event_counts_kernel<<<(unsigned)grid, block, 0, st>>>(seed, chain_begin, num_chains, nrun, R_total,
                                                           run_begin, d_t_eval, T, next_event_rate,
-                                                          d_counts, d_state_rates);
+                                                          d_counts, d_state_rates, rates_per_chain);
     SP_CUDA(cudaGetLastError());
     return SPONET_OK;
 }
@@ -989,7 +990,7 @@ int sp_stage_cv(SpScratch& sc, const sponet_shares_cv* cv, int M, SpCvDev* out, 
         if (n <= 0)
             return sponet_fail(SPONET_ERR_UNSUPPORTED, "cv: edge collective variables need the agent states (not the count-only kernel)");
         SP_REQUIRE(M == 2, "cv: Interfaces / Propensities are defined for 2 opinions (model has %d)", M);
-        SP_REQUIRE(cv->graph && cv->graph->n == n && cv->graph->batch == 1, "cv: edge collective variable needs a graph over the model's %lld agents", (long long)n);
+        SP_REQUIRE(cv->graph && cv->graph->n == n && !cv->graph->pooled, "cv: edge collective variable needs a graph over the model's %lld agents", (long long)n);
         SP_REQUIRE(cv->dimension == (cv->kind == SPONET_CV_INTERFACES ? 1 : 2), "cv: dimension %d does not match the kind", cv->dimension);
         SP_REQUIRE(cv->divisor != 0.0, "cv: divisor must be non-zero");
         out->ecv.kind = cv->kind;
@@ -1133,7 +1134,7 @@ extern "C" int sponet_native_event_counts(uint64_t seed, int64_t chain_begin, in
     SP_CUDA(sc.in(t_eval, (size_t)T, &d_t));
     SP_CUDA(sc.out(counts, (size_t)(num_chains * (T - 1)), &d_c));
     SP_TRY(sp_launch_event_counts(sc.stream, seed, chain_begin, num_chains, 0, 0, 0, d_t, (int)T,
-                                  next_event_rate, d_c, nullptr));
+                                  next_event_rate, d_c, nullptr, 0));
     SP_CUDA(sc.finish());
     return SPONET_OK;
 }
@@ -1164,7 +1165,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     if (g) {
         SP_REQUIRE(g->n == n, "graph has %lld agents, expected %lld", (long long)g->n, (long long)n);
         SP_REQUIRE(g->min_degree >= 1, "Isolated vertices in the network are not allowed.");
-        SP_REQUIRE(g->batch == 1 || g->batch == S * nrun, "graph batch holds %lld graphs, the call has %lld chains",
+        SP_REQUIRE(!g->pooled || g->batch == S * nrun, "graph batch holds %lld graphs, the call has %lld chains",
                    (long long)g->batch, (long long)(S * nrun));
     }
     int dev = 0;
@@ -1185,10 +1186,30 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
         SP_TRY(sponet_cnvm_event_rates(g ? p->degree_alpha : nullptr, n, g ? 0.0 : p->degree_alpha[0], p[q].r_imit,
                                        p[q].r_noise, &rates[q], &noise_prob[q]));
     bool uniform = true;
+    std::vector<double> chain_rates;  // per chain: a graph batch with agent weights
     if (g) {
         for (int64_t i = 1; i < n && uniform; ++i) uniform = (p->degree_alpha[i] == p->degree_alpha[0]);
-        if (!uniform && g->batch > 1)
-            return sponet_fail(SPONET_ERR_UNSUPPORTED, "a graph batch needs uniform degree_alpha (alpha = 1): agent weights depend on the graph");
+        const bool weighted_batch = g->pooled && g->d_alias != nullptr;
+        if (weighted_batch) {  // agent weights, event rate and noise probability of every chain from its own graph
+            SP_REQUIRE(!sweep, "a graph batch with agent weights takes one parameter set");
+            uniform = true;  // (no table from params->degree_alpha)
+            A.alias_tab = g->d_alias;
+            chain_rates.resize((size_t)g->batch);
+            std::vector<uint32_t> cthr((size_t)g->batch);
+            for (int64_t b = 0; b < g->batch; ++b) {
+                const double denom = p->r_imit * g->h_weight_sum[b] + p->r_noise * (double)n;  // sponet_cnvm_event_rates
+                if (denom == 0.0) return sponet_fail(SPONET_ERR_ZERO_RATE, "division by zero: all rates are zero");
+                chain_rates[b] = 1.0 / denom;
+                cthr[b] = sp_prob_to_thr(p->r_noise * (double)n * chain_rates[b]);
+            }
+            uint32_t* d_cthr;
+            SP_CUDA(sc.alloc((void**)&d_cthr, cthr.size() * sizeof(uint32_t)));
+            SP_CUDA(cudaMemcpyAsync(d_cthr, cthr.data(), cthr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, sc.stream));
+            SP_CUDA(cudaStreamSynchronize(sc.stream));
+            A.chain_noise_thr = d_cthr;
+        } else if (!uniform && g->pooled) {
+            return sponet_fail(SPONET_ERR_UNSUPPORTED, "a graph batch needs uniform degree_alpha (alpha = 1) or sponet_graph_batch_set_weights");
+        }
         if (!uniform) {
             std::vector<double> prob(n);
             std::vector<int32_t> alias(n);
@@ -1203,8 +1224,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
         }
         A.row = g->d_row;
         A.col = g->d_col;
-        A.graph_stride = g->batch > 1 ? (uint32_t)n : 0u;
-        A.rec = g->batch > 1 ? g->d_rec : nullptr;
+        A.graph_stride = g->pooled ? (uint32_t)n : 0u;
+        A.rec = g->pooled ? g->d_rec : nullptr;
         A.rec_deg_bits = (uint32_t)g->rec_deg_bits;
         A.rec_deg_mask = (1u << g->rec_deg_bits) - 1u;
         A.nbtab = g->d_nbtab;
@@ -1221,7 +1242,7 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     A.cv_divs = cvd.d_divisors;
     A.cw = cvd.d_cw;
     A.ecv = cvd.ecv;
-    if (g && g->batch > 1 && cvd.ecv.kind != 0)
+    if (g && g->pooled && cvd.ecv.kind != 0)
         return sponet_fail(SPONET_ERR_UNSUPPORTED, "edge collective variables are not evaluated on a graph batch");
     SP_REQUIRE(cvd.ecv.kind != SPONET_CV_PROPENSITIES || (!out_sum && !out_sumsq && !o->out_hist),
                "cnvm_run: integer moment sums / histograms are not defined for Propensities");
@@ -1253,7 +1274,13 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
             int64_t* d_c;
             SP_CUDA(sc.alloc((void**)&d_c, (size_t)num_chains * (T - 1) * sizeof(int64_t)));
             const double* d_rates = nullptr;
-            if (sweep) {  // one event rate per state slot
+            if (!chain_rates.empty()) {
+                double* d_r;
+                SP_CUDA(sc.alloc((void**)&d_r, chain_rates.size() * sizeof(double)));
+                SP_CUDA(cudaMemcpyAsync(d_r, chain_rates.data(), chain_rates.size() * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
+                SP_CUDA(cudaStreamSynchronize(sc.stream));
+                d_rates = d_r;
+            } else if (sweep) {  // one event rate per state slot
                 double* d_r;
                 SP_CUDA(sc.alloc((void**)&d_r, (size_t)P * sizeof(double)));
                 SP_CUDA(cudaMemcpyAsync(d_r, rates.data(), (size_t)P * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
@@ -1261,7 +1288,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
                 d_rates = d_r;
             }
             SP_TRY(sp_launch_event_counts(sc.stream, o->seed, 0, num_chains, nrun, o->num_runs_total,
-                                          o->run_begin + o->chain_offset, d_t, (int)T, rates[0], d_c, d_rates));
+                                          o->run_begin + o->chain_offset, d_t, (int)T, rates[0], d_c, d_rates,
+                                          chain_rates.empty() ? 0 : 1));
             A.counts = d_c;
         }
     }
@@ -1303,8 +1331,8 @@ static int cnvm_run_impl(const sponet_graph* g, int64_t num_agents, const sponet
     const size_t thr_bytes = bits <= 2 ? 256 : (bits <= 4 ? (size_t)((2 * M * M + 1) & ~1) * 4 : 0);  // per chain slot
     const size_t cnt_bytes = (size_t)A.cnt_stride * 4;           // opinion (x class) counters per chain
     const size_t per_slot_min = cnt_bytes + 16 + thr_bytes;      // + the reduction words of a COOP chain
-    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : (g->batch > 1 && g->d_rec) ? 3 : 1);
-    const bool batch_graph = g != nullptr && g->batch > 1;
+    const int graph_kind = g == nullptr ? 0 : (g->d_nbtab ? 2 : (g->pooled && g->d_rec && !g->d_alias) ? 3 : 1);
+    const bool batch_graph = g != nullptr && g->pooled;
     // Launches the local chains [c0, c1) with the geometry that suits their number; returns the chains one wave
     // of that geometry holds (resident chain slots on the whole device).
     auto launch_range = [&](int64_t c0, int64_t c1, bool wide, bool launch, int64_t* wave, int* wpc_out) -> int {
@@ -1511,7 +1539,7 @@ extern "C" int sponet_cnvm_run_complete_counts(int64_t num_agents, const sponet_
             int64_t* d_c;
             SP_CUDA(sc.alloc((void**)&d_c, (size_t)num_chains * (T - 1) * sizeof(int64_t)));
             SP_TRY(sp_launch_event_counts(sc.stream, o->seed, 0, num_chains, nrun, o->num_runs_total,
-                                          o->run_begin + o->chain_offset, d_t, (int)T, next_event_rate, d_c, nullptr));
+                                          o->run_begin + o->chain_offset, d_t, (int)T, next_event_rate, d_c, nullptr, 0));
             A.counts = d_c;
         }
     }

@@ -335,7 +335,7 @@ int setup_cnvm(SpScratch& sc, const sponet_graph* g, int64_t n, const sponet_cnv
     A.M = M;
     if (g) {
         SP_REQUIRE(g->n == n, "graph has %lld agents, expected %lld", (long long)g->n, (long long)n);
-        SP_REQUIRE(g->batch == 1, "replay mode runs on a single graph, not on a graph batch");
+        SP_REQUIRE(!g->pooled, "replay mode runs on a single graph, not on a graph batch");
         SP_REQUIRE(g->min_degree >= 1, "Isolated vertices in the network are not allowed.");
         SP_TRY(sponet_cnvm_event_rates(p->degree_alpha, n, 0.0, p->r_imit, p->r_noise,
                                        &A.next_event_rate, &A.noise_probability));
@@ -434,7 +434,7 @@ extern "C" int sponet_cntm_replay(const sponet_graph* g, const sponet_cntm_param
                                   int64_t W, double* out_t, uint8_t* out_x, int64_t* stream_used,
                                   int64_t* events, void* cuda_stream) {
     SP_REQUIRE(g && params, "cntm replay: graph and params are required");
-    SP_REQUIRE(g->batch == 1, "replay mode runs on a single graph, not on a graph batch");
+    SP_REQUIRE(!g->pooled, "replay mode runs on a single graph, not on a graph batch");
     SpScratch sc((cudaStream_t)cuda_stream);
     ReplayArgs A{};
     A.n = g->n;
@@ -517,7 +517,7 @@ extern "C" int sponet_cntm_replay_all(const sponet_graph* g, const sponet_cntm_p
                                       int32_t* log_agent, int32_t* log_opinion, int64_t* num_changes,
                                       int64_t* stream_used, int64_t* events, void* cuda_stream) {
     SP_REQUIRE(g && params, "cntm replay: graph and params are required");
-    SP_REQUIRE(g->batch == 1, "replay mode runs on a single graph, not on a graph batch");
+    SP_REQUIRE(!g->pooled, "replay mode runs on a single graph, not on a graph batch");
     SpScratch sc((cudaStream_t)cuda_stream);
     ReplayAllArgs B{};
     ReplayArgs& A = B.base;

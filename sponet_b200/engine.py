@@ -140,6 +140,14 @@ class GraphBatch:
         self._adopt(h, num_agents, num_states, run_begin, run_end)
         return self
 
+    def set_weights(self, alpha: float) -> None:
+        """Degree-weighted agent selection (alpha != 1): per-graph alias tables and weight sums on the device
+        (sponet_graph_batch_set_weights); the weights are ``degree ** (1 - alpha)`` as cnvm/model.py:38 computes them."""
+        dmax = self.info()["max_degree"]
+        with np.errstate(divide="ignore"):
+            w = np.ascontiguousarray(np.arange(dmax + 1, dtype=np.int64) ** (1 - alpha), dtype=np.float64)
+        _lib.check(_lib.lib().sponet_graph_batch_set_weights(self._h, _lib.ptr(w), int(w.size)))
+
     def csr(self, slot: int):
         """Graph `slot` of the batch as host (row_ptr, col)."""
         row_ptr = np.empty(self.num_agents + 1, dtype=np.int32)

@@ -342,7 +342,7 @@ def _sample_native_per_run_network(model, kind, states, t_out, num_runs, cv, rng
     if spec is not None and spec.edge:
         spec = None  # an edge CV carries its own (fixed) graph; evaluated from the returned states below
     gen = p.network_generator
-    if kind == "cnvm" and hasattr(gen, "device_batch") and p.alpha == 1 and not _FORCE_HOST_NETWORKS:
+    if kind == "cnvm" and hasattr(gen, "device_batch") and not _FORCE_HOST_NETWORKS:
         # the generator makes its graphs on the GPU: the whole ensemble in a few launches, one graph per chain
         return _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar)
     bounds = np.concatenate(([0], np.cumsum(_split_runs(pairs, world))))
@@ -379,7 +379,7 @@ def _pooled_bytes_hint() -> int:
 
 
 def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, progress_bar):
-    """Per-run networks from a generator with ``device_batch`` (network_generator.ErdosRenyi / BarabasiAlbert, alpha = 1): the
+    """Per-run networks from a generator with ``device_batch`` (the generators of sponet_b200.network_generator): the
     graphs of a block of (initial state, run) pairs are generated on the GPU and the block's chains run in ONE launch,
     chain (j, i) on graph index j * num_runs + i.  Graph and Philox stream of a pair depend on the two seeds and on the
     pair's index only: the result is the same for every block size and number of ranks.  Runs are split over ranks
@@ -400,6 +400,8 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
     # 32-bit row / entry indices of a batch, and -- for full trajectories -- the output slab
     mean_entries = N * (gen.expected_mean_degree() + 2.0)
     per_graph = (84.0 + getattr(gen, "build_bytes_per_vertex", 0.0)) * N + 4.0 * mean_entries + (T * N if want_x else 0)
+    if p.alpha != 1:
+        per_graph += (8.0 + 16.0 - 64.0) * N  # alias table + its construction scratch instead of the records
     budget = _BATCH_BYTES
     if budget is None:  # a third of the device (60 GB of a B200's 180), never more than is free right now
         import torch
@@ -419,8 +421,10 @@ def _per_run_network_batched(model, states, t_out, seed, num_runs, cv, spec, pro
         for lo in range(rb, re, r_blk):
             hi = min(re, lo + r_blk)
             # (state block offset folded into the run offset: index = (s0 + j) * num_runs + i for the block's j)
-            batch = gen.device_batch(gseed, s1 - s0, num_runs, s0 * num_runs + lo, s0 * num_runs + hi)
+            batch = gen.device_batch(gseed, s1 - s0, num_runs, s0 * num_runs + lo, s0 * num_runs + hi, records=p.alpha == 1)
             try:
+                if p.alpha != 1:  # agent weights degree ** (1 - alpha), event rate and noise probability per graph
+                    batch.set_weights(p.alpha)
                 out_x, out_cv = engine.run_native("cnvm", batch, N, struct, st, t_out, seed, num_runs, lo, hi,
                                                   cv_spec=None if want_x else spec, want_cv=not want_x, want_x=want_x,
                                                   chain_offset=s0 * num_runs)

@@ -87,8 +87,13 @@ def _oracle_chain(oracle, kw, rp, col, x0, t_eval, seed, c):
     rate, noise_p = model.event_rates()
     counts = oracle.native_event_counts(seed, c, 1, t_eval, rate)[0]
     prm = model.params
+    da = np.asarray(model.degree_alpha, dtype=float)
+    alias_thr = alias = None
+    if not np.all(da == da[0]):  # alpha != 1: the graph's own alias table (sampling.py:54-96)
+        prob, alias = oracle.build_alias_table(da)
+        alias_thr = oracle.prob_to_thr(prob)
     ox, oc, _, _ = oracle.cnvm_native(np.ascontiguousarray(x0, dtype=np.uint8), prm.num_opinions, rp, col, int(oracle.prob_to_thr(noise_p)),
-                                      oracle.prob_to_thr(prm.prob_imit), oracle.prob_to_thr(prm.prob_noise), None, None, counts,
+                                      oracle.prob_to_thr(prm.prob_imit), oracle.prob_to_thr(prm.prob_noise), alias_thr, alias, counts,
                                       seed, c)
     return ox, oc
 
@@ -224,10 +229,20 @@ def test_sample_many_runs_with_a_device_generator(oracle):
     _, xi = sample_many_runs(params2(8), s2, 2.0, T, 3, rng=np.random.default_rng(1))
     assert ci.shape == (S, 3, T, 1)
     np.testing.assert_array_equal(ci[1, 2], iface(xi[1, 2]))
-    # alpha != 1 (agent weights depend on the graph): the host pipeline, still a fresh network per run
-    pa = CNVMParameters(network_generator=ErdosRenyiGenerator(n, p, rng=np.random.default_rng(8), force_no_isolates=True), alpha=0.5, **kw)
-    _, ca = sample_many_runs(pa, states[0], 1.0, 3, 2, collective_variable=cv, rng=np.random.default_rng(1))
-    assert ca.shape == (2, 3, M) and (ca.sum(-1) == n).all()
+    # alpha != 1: agent weights, event rate and noise probability of every chain come from its own graph
+    for alpha in (0.5, 0.0, 2.0):
+        pa = CNVMParameters(network_generator=ErdosRenyiGenerator(n, p, rng=np.random.default_rng(8), force_no_isolates=True), alpha=alpha, **kw)
+        ta, xa = sample_many_runs(pa, states, 1.5, 3, 3, rng=np.random.default_rng(1))
+        pa = CNVMParameters(network_generator=ErdosRenyiGenerator(n, p, rng=np.random.default_rng(8), force_no_isolates=True), alpha=alpha, **kw)
+        _, ca = sample_many_runs(pa, states, 1.5, 3, 3, collective_variable=cv, rng=np.random.default_rng(1))
+        assert xa.shape == (S, 3, 3, n) and ca.shape == (S, 3, 3, M)
+        wb = engine.GraphBatch(n, p, gseed, S, 3, 0, 3, force_no_isolates=True)
+        for j, i in ((0, 0), (1, 2)):
+            rp, col = wb.csr(j * 3 + i)
+            ox, oc = _oracle_chain(oracle, dict(alpha=alpha, **kw), rp, col, states[j], ta, seed, j * 3 + i)
+            np.testing.assert_array_equal(xa[j, i], ox)
+            np.testing.assert_array_equal(ca[j, i], oc.astype(float))
+        wb.close()
 
 
 def test_per_run_networks_agree_with_the_host_pipeline_statistically():
@@ -434,3 +449,22 @@ def test_sample_many_runs_with_a_regular_generator(oracle):
         ox, oc = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
         np.testing.assert_array_equal(x[i], ox)
         np.testing.assert_array_equal(c[i], oc.astype(float))
+
+
+def test_weighted_agents_on_scale_free_batches(oracle):
+    """alpha = 0 on Barabasi-Albert per-run graphs: agents are picked proportionally to their degree (hubs of several hundred
+    neighbours), through per-graph alias tables built on the device -- equal to the sequential oracle with the alias table
+    of sponet/sampling.py:54-96 on the same graph."""
+    from sponet_b200 import BarabasiAlbertGenerator, CNVMParameters, engine, sample_many_runs
+
+    n, m, R, M = 3000, 3, 4, 3
+    kw = dict(num_opinions=M, r=[[0, 1, 2], [1, 0, 1], [2, 0, 0]], r_tilde=[[0, .2, .1], [0, 0, .1], [.1, .2, 0]], alpha=0.0)
+    x0 = np.random.default_rng(5).integers(0, M, n)
+    t, x = sample_many_runs(CNVMParameters(network_generator=BarabasiAlbertGenerator(n, m, rng=np.random.default_rng(2)), **kw),
+                            x0, 0.02, 3, R, rng=np.random.default_rng(3))
+    gseed = BarabasiAlbertGenerator(n, m, rng=np.random.default_rng(2)).draw_batch_seed()
+    seed = engine.draw_seed(np.random.default_rng(3))
+    for i in range(R):
+        rp, col = oracle.ba_graph(n, m, gseed, i)
+        ox, _ = _oracle_chain(oracle, kw, rp, col, x0, t, seed, i)
+        np.testing.assert_array_equal(x[i], ox)
