@@ -32,7 +32,7 @@ RT3 = np.array([[0, 0.2, 0.1], [0, 0, 0.1], [0.1, 0.2, 0]], dtype=float)
 RUNS = 12_000
 SEEDS = {"cnvm_er500": 101, "cnvm_ba400_alpha0": 102, "cnvm_complete300": 103, "cntm_er400": 104,
          "cnvm_er1e4": 201, "cnvm_er1e5": 202, "cntm_ba1e4": 203, "cntm_ba1e5": 204,
-         "cnvm_pernet_er1000": 301, "cnvm_pernet_ba1000": 302, "cnvm_pernet_ws1000": 303, "cnvm_pernet_reg1000": 304}
+         "cnvm_pernet_er1000": 301, "cnvm_pernet_ba1000": 302, "cnvm_pernet_ws1000": 303, "cnvm_pernet_reg1000": 304, "cnvm_pernet_ba1000_alpha0": 305}
 ONLY = set(sys.argv[1:])
 
 
@@ -138,3 +138,7 @@ run("cnvm_pernet_ws1000",
 run("cnvm_pernet_reg1000",
     CNVMParameters(num_opinions=3, network_generator=ng.RandomRegularGenerator(1000, 6, rng=np.random.default_rng(14)), r=R3, r_tilde=RT3),
     3, x0, 4.0, 5, dict(model="cnvm_pernet", generator="regular", num_agents=1000, d=6, r=R3, r_tilde=RT3, alpha=1.0))
+run("cnvm_pernet_ba1000_alpha0",
+    CNVMParameters(num_opinions=3, network_generator=ng.BarabasiAlbertGenerator(1000, 3, rng=np.random.default_rng(15)), r=R3, r_tilde=RT3,
+                   alpha=0.0),
+    3, x0, 0.5, 5, dict(model="cnvm_pernet", generator="ba", num_agents=1000, m=3, r=R3, r_tilde=RT3, alpha=0.0))

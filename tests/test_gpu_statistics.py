@@ -70,7 +70,8 @@ def _native_counts(g, runs, seed, scale_noise=1.0):
                else BarabasiAlbertGenerator(n, int(g["m"]), rng=grng) if kind == "ba"
                else WattsStrogatzGenerator(n, int(g["k"]), float(g["p"]), rng=grng) if kind == "ws"
                else RandomRegularGenerator(n, int(g["d"]), rng=grng))
-        params = CNVMParameters(num_opinions=M, network_generator=gen, r=g["r"], r_tilde=g["r_tilde"] * scale_noise)
+        params = CNVMParameters(num_opinions=M, network_generator=gen, r=g["r"], r_tilde=g["r_tilde"] * scale_noise,
+                                alpha=float(g["alpha"]))
     elif "workload" in g:
         params = _workload_params(g, scale_noise)
     elif model == "cntm":
@@ -126,7 +127,8 @@ def test_native_mode_matches_reference_distribution(name):
     assert pmin >= ALPHA / n_cmp, f"KS rejects: p = {pmin:.3g}"
 
 
-@pytest.mark.parametrize("name", ["cnvm_pernet_er1000", "cnvm_pernet_ba1000", "cnvm_pernet_ws1000", "cnvm_pernet_reg1000"])
+@pytest.mark.parametrize("name", ["cnvm_pernet_er1000", "cnvm_pernet_ba1000", "cnvm_pernet_ws1000", "cnvm_pernet_reg1000",
+                                  "cnvm_pernet_ba1000_alpha0"])
 def test_per_run_networks_match_the_reference_distribution(name):
     """`params.network_generator`: the reference draws a networkx graph per realization (its ErdosRenyiGenerator /
     BarabasiAlbertGenerator / WattsStrogatzGenerator / RandomRegularGenerator, 1.2e4 realizations through its own `sample_many_runs`); here the graphs of all realizations are
