@@ -12,4 +12,4 @@ prof() {  # name, kernel regex, title, command...
 }
 prof r2_cnvm_batch cnvm_native "round 2 (final): cnvm_native_kernel<2,smem,csr,noalias,coop> on a batch of 2368 per-run ER graphs (N=1e5, 64-byte agent records, 4 warps per chain), t_max=2" python tools/probe_batch_kernel.py 2368 2 1
 cat gpurun_out/plain_r2_cnvm_batch.log
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+
